@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Headline benchmark: Griffin-Lim audio-seconds per second (64 iterations, 24 kHz) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch: BASELINE.json config 2, a Fisher-test-shaped
+ragged batch of 256 synthetic log-mel utterances (T ~ U{56..400}, seed 0, length-sorted) taken
+through inverse-mel, the initial inverse and 64 fused STFT/iSTFT Griffin-Lim iterations.  With N > 1
+every rank runs its own batch of that shape (weak scaling, no collective on the data path).
+
+Prints ONE JSON line (rank 0).  ``value`` is device-timed with inputs resident in HBM; ``e2e`` goes
+through the public API from pinned host buffers (H2D of log-mel + initial phase, D2H of waveforms
+inside the timed region); ``roofline`` is the fused iteration kernel against the measured HBM peak;
+``cpu_baseline`` is the numpy oracle timed on this box's host cores on a bounded sample.
+``--impl reference`` times that CPU port with all host cores instead (the reference is Python/PyTorch
+CPU code that cannot travel to the GPU box).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "speech-to-speech-translation_b200"
+
+SR, N_FFT, WIN, HOP, N_MELS, F_MIN, F_MAX, N_ITER = 24000, 2048, 1200, 300, 80, 20.0, 8000.0, 64
+N_UTTS = 256
+ALGO_BYTES_PER_FRAME_ITER = 6500        # 1200 B wave in + 4100 B magnitude + 1200 B wave out
+ALGO_BYTES_PER_FRAME_ONCE = 13820       # inverse-mel + initial inverse
+WORKLOAD = ("Fisher-test-shaped batch: 256 synthetic log-mel utterances, 56-400 frames length-bucketed, "
+            "64 Griffin-Lim iters per GPU")
+
+
+def batch_frames(seed):
+    rng = np.random.RandomState(seed)
+    return sorted(int(t) for t in rng.randint(56, 401, size=N_UTTS))
+
+
+def synth_logmel_np(T, seed):
+    """SURVEY 8(d) speech-like log-mel: smooth random walk in time + spectral tilt, clamped."""
+    rng = np.random.RandomState(seed)
+    x = 0.1 * np.cumsum(rng.randn(T, N_MELS), axis=0) + np.linspace(0, -4, N_MELS)[None, :] - 2.0
+    return np.clip(x, np.log(1e-5), 2.0).astype(np.float32)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_time(frames_subset, seed, n_iter, basis):
+    """Time the numpy oracle (the CPU port of the reference path) on the given utterances, 1 core."""
+    from oracle import griffin_lim as ogl
+    t0 = time.perf_counter()
+    audio = 0.0
+    for i, T in enumerate(frames_subset):
+        x = synth_logmel_np(T, seed + i)
+        np.random.seed(seed + i)
+        phase = ogl.random_phase((N_FFT // 2 + 1, T))
+        y = ogl.vocoder_forward(x, phase, n_iter, basis=basis)
+        audio += y.shape[0] / SR
+    return audio, time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    frames, seed, n_iter = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import griffin_lim as ogl
+    basis = ogl.pinv_mel_basis(SR, N_FFT, N_MELS, F_MIN, F_MAX)
+    return cpu_port_time(frames, seed, n_iter, basis)[0]
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    frames = batch_frames(0)
+    # bounded sample: a length-stratified subset, 2 utterances per core (capped), same iteration count
+    n_sample = max(1, min(len(frames), 2 * cores, 32))
+    sample = [frames[int(i)] for i in np.linspace(0, len(frames) - 1, n_sample)]
+    chunks = [(sample[i::cores], 1000 + i, N_ITER) for i in range(min(cores, n_sample))]
+    ctx = mp.get_context("spawn")
+    times = []
+    audio = 0.0
+    with ctx.Pool(len(chunks)) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            audio = sum(pool.map(_cpu_worker, chunks))
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = audio / (ms / 1e3)
+    sample_desc = f"{n_sample} of the {N_UTTS} utterances (length-stratified, {sum(sample)} frames), {N_ITER} iters"
+    print(json.dumps({
+        "impl": "reference", "metric": "griffin_lim_audio_seconds_per_second", "value": value,
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 transforms / f32 state",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_iter": N_ITER, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": len(chunks), "kind": "port",
+                         "sample": sample_desc},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__
+    __graft_entry__.build()
+    pkg = importlib.import_module(PKG)
+    voc = pkg.GriffinLimVocoder(SR, WIN, HOP, N_FFT, N_MELS, F_MIN, F_MAX, torch.hann_window,
+                                spec_bwd_max_iter=N_ITER).to(dev)
+    plan = voc._plan(dev)
+
+    frames = batch_frames(rank)  # config 2 length law; every rank its own batch (weak scaling)
+    total = int(sum(frames))
+    n_bins = N_FFT // 2 + 1
+    audio_s = sum((T - 1) * HOP for T in frames) / SR
+    # host (pinned) inputs: denormalised log-mel, frame-major, and the seeded initial phase, frame-major
+    logmel_h = torch.from_numpy(np.concatenate([synth_logmel_np(T, 1234 + 1000 * rank + i) for i, T in enumerate(frames)])).pin_memory()
+    rng = np.random.RandomState(100 + rank)
+    phase_h = torch.from_numpy(np.angle(np.exp(2j * np.pi * rng.rand(total, n_bins))).astype(np.float32)).pin_memory()
+    n_samples = (total - len(frames)) * HOP
+    wave_h = torch.empty(n_samples, dtype=torch.float32).pin_memory()
+    logmel_d = logmel_h.to(dev)
+    phase_d = phase_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident timing (value) ----------------------------------------------------------
+    for _ in range(args.warmup):
+        voc.synthesize_flat(logmel_d, frames, phase_d)
+    plan.set_pass_timing(True)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        wave_d = voc.synthesize_flat(logmel_d, frames, phase_d)
+        pass_ms.append(None)  # filled below, after the timed region (reading events synchronises)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    # per-pass device times of the last timed step, recorded inside the timed region by the library
+    last_pass_ms = plan.pass_times_ms()
+    plan.set_pass_timing(False)
+    iter_ms = float(np.mean(last_pass_ms[1:])) if len(last_pass_ms) > 1 else float("nan")
+    assert torch.isfinite(wave_d).all()
+
+    # ---- end to end through the public API, host buffers in and out (e2e) -------------------------
+    def e2e_step():
+        lm = logmel_h.to(dev, non_blocking=True)
+        ph = phase_h.to(dev, non_blocking=True)
+        w = voc.synthesize_flat(lm, frames, ph)
+        wave_h.copy_(w, non_blocking=True)
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1) / args.steps, e2e_wall_ms))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    algo_bytes_iter = ALGO_BYTES_PER_FRAME_ITER * total
+    achieved = algo_bytes_iter / (iter_ms * 1e-3) / 1e9
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------------
+    from oracle import griffin_lim as ogl
+    basis = voc.inv_mel_transform.basis.cpu().numpy()
+    sample = [frames[int(i)] for i in np.linspace(0, len(frames) - 1, 6)]
+    cpu_audio, cpu_s = cpu_port_time(sample, 4321, N_ITER, basis)
+    # parity spot check on the way (checker only): first utterance of the batch vs the oracle
+    T0 = frames[0]
+    ref0 = ogl.vocoder_forward(logmel_h[:T0].numpy(), np.ascontiguousarray(phase_h[:T0].numpy().T), N_ITER, basis=basis)
+    parity = ogl.rel_l2(wave_h[: (T0 - 1) * HOP].numpy(), ref0)
+
+    launches = plan.gl_launch_count(N_ITER, True) * args.steps
+    out = {
+        "metric": "griffin_lim_audio_seconds_per_second", "value": world * audio_s / (ms_step * 1e-3),
+        "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "utterances_per_gpu": N_UTTS, "frames_per_gpu": total,
+                   "audio_seconds_per_gpu": audio_s, "n_iter": N_ITER, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP,
+                   "win": WIN, "l2_policy": "per-step working set (magnitudes + phase + waveform buffers, "
+                   f"{(total * (684 + 1025) * 4 + 4 * n_samples * 4) / 1e6:.0f} MB) exceeds the 126 MB L2"},
+        "e2e": {"value": world * audio_s / (e2e_ms * 1e-3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(logmel_h.numel() * 4 + phase_h.numel() * 4),
+                "d2h_bytes_per_step": int(wave_h.numel() * 4), "ms_per_step": e2e_ms,
+                "api": "GriffinLimVocoder.synthesize_flat from pinned host buffers"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_gl_pass<19,false> (fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
+                     "launch_ms": iter_ms, "launches_per_step": N_ITER,
+                     "share_of_step": float(np.sum(last_pass_ms[1:]) / ms_step) if len(last_pass_ms) > 1 else None},
+        "cpu_baseline": {"value": cpu_audio / cpu_s, "unit": "audio-s/s", "cores": 1, "kind": "port",
+                         "sample": f"6 length-stratified utterances of the batch ({sum(sample)} frames), {N_ITER} iters, "
+                                   f"numpy FFT oracle, {cpu_s:.1f} s"},
+        "clocks": clocks,
+        "parity_rel_l2_vs_oracle": parity,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

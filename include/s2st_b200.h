@@ -1,0 +1,169 @@
+/*
+ * s2st_b200.h -- C ABI of the B200 (sm_100a) waveform-synthesis / feature front-end library.
+ *
+ * This is the drop-in boundary for the hot path of fengpeng-yue/speech-to-speech-translation
+ * (a fairseq fork).  The reference's path is Python/PyTorch; the binding a maintainer adds is
+ * the ctypes stub shown in INTEGRATION.md.  Every entry point cites the reference interface
+ * it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes; no torch / C++ types, no exceptions across the boundary.
+ *   - every function returns an int status: 0 = S2ST_OK, otherwise an S2ST_E* code;
+ *     s2st_last_error() returns a thread-local human-readable message for the last failure.
+ *   - pointers named *_dev are device pointers on the plan's device; *_host are host pointers.
+ *   - the CALLER owns every input / output / workspace buffer; the library never allocates per
+ *     call, enqueues all work on the caller's stream (cudaStream_t passed as void*) and never
+ *     synchronises.  The only device memory the library owns are the plan's constants.
+ *   - all arithmetic is fp32.  Ragged batches are concatenated frame-major:
+ *       frame_offsets[B+1]  (int32, device)  cumulative frame counts, frame_offsets[0] = 0
+ *       features            [total_frames, n_mels]     row-major (the reference's [T, 80] layout)
+ *       waveforms           concatenated; utterance i starts at (frame_offsets[i] - i) * hop and
+ *                           has (T_i - 1) * hop samples (vocoder.py:98-99)
+ */
+#ifndef S2ST_B200_H_
+#define S2ST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2ST_OK 0
+#define S2ST_EINVAL 1      /* bad argument / unsupported configuration */
+#define S2ST_ECUDA 2       /* a CUDA runtime call failed */
+#define S2ST_EWORKSPACE 3  /* workspace too small */
+
+#define S2ST_ABI_VERSION 1
+
+typedef struct s2st_plan s2st_plan; /* opaque: owns only constants (windows, twiddles, mel matrices) */
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                     */
+int s2st_abi_version(void);
+const char* s2st_last_error(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* plan = the constants of GriffinLimVocoder.__init__ (fairseq/models/text_to_speech/vocoder.py:114-134),
+ * GriffinLim.__init__ (:50-69), TTSSpectrogram.__init__ / TTSMelScale.__init__
+ * (fairseq/data/audio/audio_utils.py:246-257, 275-282).
+ *   window_host       [win_length]              the un-padded window (window_fn(win_length))
+ *   inv_mel_host      [n_fft/2+1, n_mels]       pseudo-inverse mel basis (vocoder.py:28-32), may be NULL
+ *   mel_host          [n_mels, n_fft/2+1]       mel filterbank (audio_utils.py:234-242), may be NULL
+ * n_fft must be 2048 in this version (S2ST_EINVAL otherwise). */
+int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length, int hop_length,
+                     int n_mels, const float* window_host, const float* inv_mel_host,
+                     const float* mel_host);
+int s2st_plan_destroy(s2st_plan* plan);
+/* number of leading spectrogram bins that can be non-zero after the inverse-mel projection
+ * (rows of inv_mel beyond it are exactly zero; n_fft/2+1 when no inv_mel was given). */
+int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Griffin-Lim ragged batch: GriffinLimVocoder.forward (vocoder.py:136-144) for B utterances at once.
+ *   logmel_dev      [total_frames, n_mels]  denormalised log-mel, or NULL when mag_dev is given
+ *   mag_dev         [total_frames, n_fft/2+1] linear magnitudes (GriffinLim.forward input,
+ *                   vocoder.py:102, transposed to frame-major), or NULL when logmel_dev is given
+ *   init_phase_dev  [total_frames, n_fft/2+1] initial phase in radians, frame-major.  The
+ *                   reference draws it from numpy's global RNG on the host (vocoder.py:103-104);
+ *                   the host shim does the same and uploads it.
+ *   n_iter          spec_bwd_max_iter (n_iter forward + n_iter+1 inverse transforms)
+ *   wave_out_dev    concatenated waveforms, (total_frames - B) * hop floats
+ * Every utterance must have T >= 1; when n_iter > 0, (T-1)*hop must exceed n_fft/2 (the
+ * reference's reflect padding raises otherwise) -- checked by the host shim, not here. */
+int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_frames, size_t* bytes_out);
+int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
+                       const int32_t* frame_offsets_dev, const float* logmel_dev,
+                       const float* mag_dev, const float* init_phase_dev, int n_iter,
+                       float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
+                       void* stream);
+/* Profiling aid (not part of the reference's interface): when enabled, s2st_gl_synthesize / s2st_istft
+ * record a CUDA event on the caller's stream before every Griffin-Lim pass and after the last one;
+ * s2st_plan_get_pass_times waits for the last event and returns the device time of each pass of the
+ * most recent call in milliseconds (pass 0 = initial inverse, passes 1..n_iter = fused iterations). */
+int s2st_plan_set_pass_timing(s2st_plan* plan, int enabled);
+int s2st_plan_get_pass_times(s2st_plan* plan, float* ms_out_host, int capacity, int* n_passes_out);
+/* number of kernel launches one s2st_gl_synthesize call enqueues (for bench.py's gpu_launches) */
+int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int* launches_out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* building blocks (test surface + the reference's public sub-modules)                         */
+
+/* PseudoInverseMelScale.forward (vocoder.py:34-46), optionally fused with the exp of
+ * GriffinLimVocoder.forward (vocoder.py:141):
+ *   mag[t, f] = max(0, sum_m inv_mel[f, m] * g(mel[t, m])),  g = exp if input_is_log else identity,
+ *   mel_dev [n_frames, n_mels], mag_dev [n_frames, n_fft/2+1] */
+int s2st_inverse_mel(const s2st_plan* plan, int64_t n_frames, const float* mel_dev, int input_is_log,
+                     float* mag_dev, void* stream);
+
+/* TTSMelScale.forward (audio_utils.py:284-285) on frame-major data:
+ *   mel_out[t, m] = sum_f mel[m, f] * spec[t, f] */
+int s2st_mel_project(const s2st_plan* plan, int64_t n_frames, const float* spec_dev,
+                     float* mel_out_dev, void* stream);
+
+/* TTSSpectrogram.forward (audio_utils.py:259-271) for a ragged batch of waveforms:
+ *   wave_offsets_dev [B+1] int64 sample offsets, frame_offsets_dev [B+1] int32 with
+ *   T_i = 1 + n_i / hop.  mag_out / phase_out are [total_frames, n_fft/2+1]; phase_out may be NULL. */
+int s2st_stft(const s2st_plan* plan, int n_utts, int64_t total_frames,
+              const int64_t* wave_offsets_dev, const int32_t* frame_offsets_dev,
+              const float* wave_dev, float* mag_out_dev, float* phase_out_dev, void* stream);
+
+/* GriffinLim.inverse (vocoder.py:84-100): frame-major mag / phase -> concatenated waveforms.
+ * Uses the same workspace as s2st_gl_synthesize. */
+int s2st_istft(const s2st_plan* plan, int n_utts, int64_t total_frames,
+               const int32_t* frame_offsets_dev, const float* mag_dev, const float* phase_dev,
+               float* wave_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* batched 2048-point real FFT / inverse (numpy rfft / irfft conventions), test surface for the
+ * warp-level transform:  in [n, 2048] -> out [n, 1025, 2] (re, im)   and back. */
+int s2st_rfft2048(const s2st_plan* plan, int64_t n, const float* in_dev, float* out_dev, void* stream);
+int s2st_irfft2048(const s2st_plan* plan, int64_t n, const float* in_dev, float* out_dev, void* stream);
+
+/* GriffinLim.get_window_sum_square (vocoder.py:71-82), host-side, out_host [n_fft + hop*(n_frames-1)] */
+int s2st_window_sum_square(int n_frames, int hop_length, int win_length, int n_fft,
+                           const float* window_host, float* out_host);
+
+/* ------------------------------------------------------------------------------------------ */
+/* feature front-end                                                                           */
+
+/* logmelspec80: extract_logmel_spectrogram (examples/speech_synthesis/data_utils.py:46-76):
+ *   out[t, m] = log(max(eps, sum_f mel[m, f] * |STFT(wave)|[t, f])), optionally followed by
+ *   global CMVN (feature_transforms/global_cmvn.py:26-29) when cmvn_mean_dev != NULL.
+ *   Same ragged layout as s2st_stft; out_dev [total_frames, n_mels]. */
+int s2st_logmel(const s2st_plan* plan, int n_utts, int64_t total_frames,
+                const int64_t* wave_offsets_dev, const int32_t* frame_offsets_dev,
+                const float* wave_dev, float eps, const float* cmvn_mean_dev,
+                const float* cmvn_std_dev, float* out_dev, void* stream);
+
+/* fbank80: _get_torchaudio_fbank (audio_utils.py:136-149) == torchaudio.compliance.kaldi.fbank with
+ * num_mel_bins = n_bins, sample_frequency = sample_rate and every other option at its default.
+ * The Kaldi plan owns the povey window, FFT twiddles and the Kaldi mel banks. */
+typedef struct s2st_fbank_plan s2st_fbank_plan;
+int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_rate, int n_bins);
+int s2st_fbank_plan_destroy(s2st_fbank_plan* plan);
+/* window size / shift / padded FFT size of the plan: m_i = 1 + (n_i - win) / shift (0 if n_i < win) */
+int s2st_fbank_frame_params(const s2st_fbank_plan* plan, int* win_out, int* shift_out, int* padded_out);
+/*   wave_dev is the int16-scaled waveform (audio_utils.py:105-106); out_dev [total_frames, n_bins];
+ *   optional fused global CMVN as above. */
+int s2st_fbank(const s2st_fbank_plan* plan, int n_utts, int64_t total_frames,
+               const int64_t* wave_offsets_dev, const int32_t* frame_offsets_dev,
+               const float* wave_dev, const float* cmvn_mean_dev, const float* cmvn_std_dev,
+               float* out_dev, void* stream);
+
+/* GlobalCMVN.__call__ (feature_transforms/global_cmvn.py:26-29): out = (x - mean) / std, and its
+ * inverse gcmvn_denormalize (fairseq/speech_generator_for_s2st.py:21-29): out = x * std + mean.
+ * x_dev / out_dev [n_rows, n_cols] (in place allowed), mean / std [n_cols]. */
+int s2st_cmvn_apply(int64_t n_rows, int n_cols, const float* x_dev, const float* mean_dev,
+                    const float* std_dev, float* out_dev, void* stream);
+int s2st_cmvn_denormalize(int64_t n_rows, int n_cols, const float* x_dev, const float* mean_dev,
+                          const float* std_dev, float* out_dev, void* stream);
+/* get_global_cmvn's accumulation (examples/speech_synthesis/data_utils.py:190-220):
+ *   sums_dev [2, n_cols] += (sum_t x, sum_t x^2); the caller zeroes sums_dev and finishes
+ *   mean / std on the host. */
+int s2st_cmvn_accumulate(int64_t n_rows, int n_cols, const float* x_dev, double* sums_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2ST_B200_H_ */

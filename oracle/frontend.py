@@ -1,0 +1,86 @@
+"""Feature front-end oracle (test infrastructure only -- see oracle/__init__.py).
+
+* ``logmel_spectrogram``  examples/speech_synthesis/data_utils.py:46-76 via
+                          TTSSpectrogram (audio_utils.py:259-271, no phase) and
+                          TTSMelScale (audio_utils.py:274-285)
+* ``kaldi_fbank``         audio_utils.py:136-149 -> torchaudio.compliance.kaldi.fbank
+                          with every option but num_mel_bins / sample_frequency at
+                          its default (dither 0, povey window, pre-emphasis 0.97,
+                          DC removal, snip_edges, power spectrum, log, 20 Hz..Nyquist)
+* ``global_cmvn``         feature_transforms/global_cmvn.py:26-29
+* ``global_cmvn_stats``   examples/speech_synthesis/data_utils.py:190-220
+* ``gcmvn_denormalize``   fairseq/speech_generator_for_s2st.py:21-29
+"""
+import numpy as np
+
+from .griffin_lim import stft
+from .mel import kaldi_mel_banks, slaney_mel_filters
+
+FLT_EPS = np.float32(1.1920928955078125e-07)
+
+
+def logmel_spectrogram(wave, sample_rate=24000, win_length=1200, hop_length=300, n_fft=2048,
+                       n_mels=80, f_min=20.0, f_max=8000.0, eps=1e-5, mel=None):
+    """wave [n] float32 in [-1, 1] -> [1 + n // hop, n_mels] float32."""
+    mag, _ = stft(wave, n_fft, win_length, hop_length)  # [F, T]
+    if mel is None:
+        mel = slaney_mel_filters(sample_rate, n_fft, n_mels, f_min, f_max)
+    m = (mel.astype(np.float64) @ mag.astype(np.float64)).astype(np.float32)
+    return np.log(np.maximum(m, np.float32(eps))).astype(np.float32).T
+
+
+def kaldi_frame_params(sample_rate):
+    win = int(sample_rate * 25.0 * 0.001)
+    shift = int(sample_rate * 10.0 * 0.001)
+    padded = 1 if win == 0 else 2 ** (win - 1).bit_length()
+    return win, shift, padded
+
+
+def povey_window(win):
+    n = np.arange(win, dtype=np.float64)
+    hann = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / (win - 1))  # periodic=False
+    return np.power(hann.astype(np.float32), np.float32(0.85)).astype(np.float32)
+
+
+def kaldi_fbank(wave, sample_rate, n_bins=80):
+    """wave [n] float32 (int16-scaled) -> [m, n_bins] float32, m = 1 + (n - win)//shift."""
+    wave = np.asarray(wave, np.float32).reshape(-1)
+    win, shift, padded = kaldi_frame_params(sample_rate)
+    n = wave.shape[0]
+    if n < win:
+        return np.zeros((0, n_bins), np.float32)
+    m = 1 + (n - win) // shift
+    idx = np.arange(win)[None, :] + shift * np.arange(m)[:, None]
+    fr = wave[idx].astype(np.float64)
+    fr = fr - fr.mean(axis=1, keepdims=True)
+    prev = np.concatenate([fr[:, :1], fr[:, :-1]], axis=1)
+    fr = fr - 0.97 * prev
+    fr = fr * povey_window(win).astype(np.float64)[None, :]
+    spec = np.fft.rfft(fr, n=padded, axis=1)
+    power = (spec.real ** 2 + spec.imag ** 2)
+    banks = kaldi_mel_banks(n_bins, padded, float(sample_rate)).astype(np.float64)
+    e = (power @ banks.T).astype(np.float32)
+    return np.log(np.maximum(e, FLT_EPS)).astype(np.float32)
+
+
+def global_cmvn(x, mean, std):
+    return np.divide(np.subtract(x, mean), std)
+
+
+def gcmvn_denormalize(x, mean, std):
+    return (np.asarray(x, np.float32) * np.asarray(std, np.float32) + np.asarray(mean, np.float32)).astype(np.float32)
+
+
+def global_cmvn_stats(feature_list):
+    """Sum / sum-of-squares accumulation in the features' dtype, like the reference."""
+    sx = None
+    sx2 = None
+    n = 0
+    for f in feature_list:
+        f = np.asarray(f)
+        n += f.shape[0]
+        sx = f.sum(axis=0) if sx is None else sx + f.sum(axis=0)
+        sx2 = (f ** 2).sum(axis=0) if sx2 is None else sx2 + (f ** 2).sum(axis=0)
+    mean = sx / n
+    var = sx2 / n - mean ** 2
+    return {"mean": mean, "std": np.sqrt(np.maximum(var, 1e-10))}

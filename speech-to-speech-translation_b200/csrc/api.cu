@@ -1,0 +1,560 @@
+// C ABI of libs2st_b200.so (declared in include/s2st_b200.h): argument checking, plan construction
+// (host-side constant tables uploaded once), dispatch to the kernels.  No per-call allocation, no
+// synchronisation; errors become integer status codes + a thread-local message.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/s2st_b200.h"
+#include "plan.h"
+
+namespace s2st {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    if (src.empty()) return S2ST_OK;
+    S2ST_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(dst), sizeof(T) * src.size()));
+    S2ST_CUDA_CHECK(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return S2ST_OK;
+}
+
+// dense [rows, cols] -> CSR over non-zeros (column order kept ascending)
+void to_csr(const float* dense, int rows, int cols, std::vector<int>& ptr, std::vector<int>& idx,
+            std::vector<float>& val, int* max_row) {
+    ptr.assign(rows + 1, 0);
+    idx.clear();
+    val.clear();
+    *max_row = 0;
+    for (int r = 0; r < rows; ++r) {
+        for (int c = 0; c < cols; ++c) {
+            const float v = dense[(size_t)r * cols + c];
+            if (v != 0.0f) {
+                idx.push_back(c);
+                val.push_back(v);
+            }
+        }
+        ptr[r + 1] = (int)idx.size();
+        if (ptr[r + 1] - ptr[r] > *max_row) *max_row = ptr[r + 1] - ptr[r];
+    }
+}
+
+void free_plan_members(s2st_plan* p) {
+    for (int i = 0; i <= kMaxTimedPasses; ++i)
+        if (p->timing_events[i]) cudaEventDestroy(p->timing_events[i]);
+    cudaFree(p->win_a);
+    cudaFree(p->win_s);
+    cudaFree(p->w2);
+    cudaFree(p->inv_wss);
+    cudaFree(p->tw);
+    cudaFree(p->vtab);
+    cudaFree(p->inv_mel_t);
+    cudaFree(p->mel_ptr);
+    cudaFree(p->mel_idx);
+    cudaFree(p->mel_val);
+}
+
+}  // namespace
+}  // namespace s2st
+
+using namespace s2st;
+
+extern "C" {
+
+int s2st_abi_version(void) { return S2ST_ABI_VERSION; }
+
+const char* s2st_last_error(void) { return g_err; }
+
+int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length, int hop_length,
+                     int n_mels, const float* window_host, const float* inv_mel_host,
+                     const float* mel_host) {
+    if (!plan_out || !window_host) {
+        set_error("null argument");
+        return S2ST_EINVAL;
+    }
+    *plan_out = nullptr;
+    if (n_fft != kNfft) {
+        set_error("n_fft=%d is not supported by this build (only %d)", n_fft, kNfft);
+        return S2ST_EINVAL;
+    }
+    if (win_length < 1 || win_length > n_fft || hop_length < 1 || n_mels < 1) {
+        set_error("bad geometry: win_length=%d hop_length=%d n_mels=%d", win_length, hop_length, n_mels);
+        return S2ST_EINVAL;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("cannot select CUDA device %d", device);
+        return S2ST_ECUDA;
+    }
+    // padded window (audio_utils.py:218-223)
+    std::vector<float> w(n_fft, 0.0f);
+    const int pl = (n_fft - win_length) / 2;
+    for (int i = 0; i < win_length; ++i) w[pl + i] = window_host[i];
+    int lo = -1, hi = -1;
+    for (int i = 0; i < n_fft; ++i)
+        if (w[i] != 0.0f) {
+            if (lo < 0) lo = i;
+            hi = i;
+        }
+    if (lo < 0) {
+        set_error("window is identically zero");
+        return S2ST_EINVAL;
+    }
+    s2st_plan* p = new s2st_plan();
+    std::memset(p, 0, sizeof(*p));
+    p->device = device;
+    p->n_fft = n_fft;
+    p->win_length = win_length;
+    p->hop = hop_length;
+    p->n_mels = n_mels;
+    // frames are processed circularly rotated so that the window support starts at sample 0; when it
+    // fits in 19*64 samples the 13 structurally-zero inputs of every in-lane FFT are pruned.
+    int rot = lo & ~1;
+    if (hi - rot < 19 * 64 && rot + 19 * 64 <= n_fft) {
+        p->nz = 19;
+    } else {
+        p->nz = 32;
+        rot = 0;
+    }
+    p->rot = rot;
+    p->wp = 64 * p->nz;
+    p->ws = ((hi - rot + 1) + 1) & ~1;
+    if (p->ws > p->wp) p->ws = p->wp;
+    const int overlap = (p->ws + hop_length - 1) / hop_length;
+    p->nphase = overlap < kTileFrames ? overlap : kTileFrames;
+
+    std::vector<float> win_a(p->wp), win_s(p->wp), w2(p->ws), inv_wss(hop_length);
+    for (int m = 0; m < p->wp; ++m) {
+        const float v = (rot + m < n_fft) ? w[rot + m] : 0.0f;
+        win_a[m] = v;
+        win_s[m] = v / (float)n_fft;
+    }
+    for (int m = 0; m < p->ws; ++m) w2[m] = win_a[m] * win_a[m];
+    for (int r = 0; r < hop_length; ++r) {
+        // ascending frame order == descending offset, float accumulation like vocoder.py:78-81
+        float acc = 0.0f;
+        int imax = -1;
+        for (int i = 0; r + i * hop_length < p->ws; ++i) imax = i;
+        for (int i = imax; i >= 0; --i) acc += w2[r + i * hop_length];
+        inv_wss[r] = acc > 1.1754944e-38f ? (float)(1.0 / (double)acc) : 1.0f;
+    }
+    std::vector<float2> tw(1024), vtab(1024);
+    const double pi = 3.14159265358979323846;
+    for (int r = 0; r < 32; ++r)
+        for (int l = 0; l < 32; ++l) {
+            const double a = -2.0 * pi * (double)((r * l) % 1024) / 1024.0;
+            tw[r * 32 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    for (int k = 0; k < 1024; ++k) {
+        const double a = 2.0 * pi * (double)k / 2048.0;  // -i * exp(-i a) = (-sin a, -cos a)
+        vtab[k] = make_float2((float)(-std::sin(a)), (float)(-std::cos(a)));
+    }
+    vtab[0] = make_float2(0.0f, -1.0f);
+    vtab[512] = make_float2(-1.0f, 0.0f);
+
+    int rc = S2ST_OK;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        set_error("cudaGetDeviceProperties failed");
+        rc = S2ST_ECUDA;
+    } else {
+        p->num_sms = prop.multiProcessorCount;
+    }
+    if (rc == S2ST_OK) rc = upload(&p->win_a, win_a);
+    if (rc == S2ST_OK) rc = upload(&p->win_s, win_s);
+    if (rc == S2ST_OK) rc = upload(&p->w2, w2);
+    if (rc == S2ST_OK) rc = upload(&p->inv_wss, inv_wss);
+    if (rc == S2ST_OK) rc = upload(&p->tw, tw);
+    if (rc == S2ST_OK) rc = upload(&p->vtab, vtab);
+
+    p->kb = kBins;
+    if (rc == S2ST_OK && inv_mel_host) {
+        int last = 0;
+        for (int f = 0; f < kBins; ++f)
+            for (int m = 0; m < n_mels; ++m)
+                if (inv_mel_host[(size_t)f * n_mels + m] != 0.0f) last = f;
+        p->kb = last + 1;
+        p->kb_pad = (p->kb + 3) & ~3;
+        std::vector<float> t((size_t)n_mels * p->kb_pad, 0.0f);
+        for (int f = 0; f < p->kb; ++f)
+            for (int m = 0; m < n_mels; ++m) t[(size_t)m * p->kb_pad + f] = inv_mel_host[(size_t)f * n_mels + m];
+        rc = upload(&p->inv_mel_t, t);
+    }
+    if (rc == S2ST_OK && mel_host) {
+        std::vector<int> ptr, idx;
+        std::vector<float> val;
+        to_csr(mel_host, n_mels, kBins, ptr, idx, val, &p->mel_max_row);
+        p->mel_nnz = (int)idx.size();
+        if (idx.empty()) {  // keep the device arrays non-null
+            idx.push_back(0);
+            val.push_back(0.0f);
+        }
+        rc = upload(&p->mel_ptr, ptr);
+        if (rc == S2ST_OK) rc = upload(&p->mel_idx, idx);
+        if (rc == S2ST_OK) rc = upload(&p->mel_val, val);
+    }
+    if (rc != S2ST_OK) {
+        free_plan_members(p);
+        delete p;
+        return rc;
+    }
+    *plan_out = p;
+    return S2ST_OK;
+}
+
+int s2st_plan_destroy(s2st_plan* plan) {
+    if (!plan) return S2ST_OK;
+    DeviceGuard guard(plan->device);
+    free_plan_members(plan);
+    delete plan;
+    return S2ST_OK;
+}
+
+int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out) {
+    if (!plan || !active_bins_out) {
+        set_error("null argument");
+        return S2ST_EINVAL;
+    }
+    *active_bins_out = plan->kb;
+    return S2ST_OK;
+}
+
+int s2st_plan_set_pass_timing(s2st_plan* plan, int enabled) {
+    if (!plan) {
+        set_error("null plan");
+        return S2ST_EINVAL;
+    }
+    plan->timing_enabled = enabled != 0;
+    plan->timing_recorded = 0;
+    return S2ST_OK;
+}
+
+int s2st_plan_get_pass_times(s2st_plan* plan, float* ms_out_host, int capacity, int* n_passes_out) {
+    if (!plan || !ms_out_host || !n_passes_out) {
+        set_error("null argument");
+        return S2ST_EINVAL;
+    }
+    const int n = plan->timing_recorded - 1;
+    if (n <= 0 || n > capacity) {
+        set_error("no pass timing recorded (enable it before the call) or capacity %d too small for %d", capacity, n);
+        return S2ST_EINVAL;
+    }
+    S2ST_CUDA_CHECK(cudaEventSynchronize(plan->timing_events[n]));
+    for (int i = 0; i < n; ++i)
+        S2ST_CUDA_CHECK(cudaEventElapsedTime(ms_out_host + i, plan->timing_events[i], plan->timing_events[i + 1]));
+    *n_passes_out = n;
+    return S2ST_OK;
+}
+
+static int check_gl_geometry(const s2st_plan* plan) {
+    if (plan->ws > kTileFrames * plan->hop) {
+        set_error("window support %d exceeds %d hops of %d samples: overlap factor not supported", plan->ws,
+                  kTileFrames, plan->hop);
+        return S2ST_EINVAL;
+    }
+    return S2ST_OK;
+}
+
+int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_frames, size_t* bytes_out) {
+    if (!plan || !bytes_out || n_utts <= 0 || total_frames < n_utts) {
+        set_error("bad argument to s2st_gl_workspace_bytes");
+        return S2ST_EINVAL;
+    }
+    *bytes_out = gl_workspace_bytes(plan, n_utts, total_frames);
+    return S2ST_OK;
+}
+
+int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
+                       const int32_t* frame_offsets_dev, const float* logmel_dev,
+                       const float* mag_dev, const float* init_phase_dev, int n_iter,
+                       float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
+                       void* stream) {
+    if (!plan || !frame_offsets_dev || !init_phase_dev || !wave_out_dev || n_iter < 0 ||
+        ((logmel_dev == nullptr) == (mag_dev == nullptr))) {
+        set_error("bad argument to s2st_gl_synthesize (exactly one of logmel / mag must be given)");
+        return S2ST_EINVAL;
+    }
+    int rc = check_gl_geometry(plan);
+    if (rc != S2ST_OK) return rc;
+    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, logmel_dev, mag_dev, kBins,
+                  init_phase_dev, n_iter, wave_out_dev, workspace_dev, workspace_bytes,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int* launches_out) {
+    if (!plan || !launches_out || n_iter < 0) {
+        set_error("bad argument");
+        return S2ST_EINVAL;
+    }
+    // build_tiles + [inverse_mel] + (n_iter + 1) passes + resolve
+    *launches_out = 1 + (from_logmel ? 1 : 0) + (n_iter + 1) + 1;
+    return S2ST_OK;
+}
+
+int s2st_inverse_mel(const s2st_plan* plan, int64_t n_frames, const float* mel_dev, int input_is_log,
+                     float* mag_dev, void* stream) {
+    if (!plan || !mel_dev || !mag_dev || n_frames < 0) {
+        set_error("bad argument to s2st_inverse_mel");
+        return S2ST_EINVAL;
+    }
+    return launch_inverse_mel(plan, n_frames, mel_dev, input_is_log != 0, mag_dev, kBins, kBins,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int s2st_mel_project(const s2st_plan* plan, int64_t n_frames, const float* spec_dev, float* mel_out_dev,
+                     void* stream) {
+    if (!plan || !spec_dev || !mel_out_dev || n_frames < 0) {
+        set_error("bad argument to s2st_mel_project");
+        return S2ST_EINVAL;
+    }
+    return launch_mel_project(plan, n_frames, spec_dev, mel_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_stft(const s2st_plan* plan, int n_utts, int64_t total_frames, const int64_t* wave_offsets_dev,
+              const int32_t* frame_offsets_dev, const float* wave_dev, float* mag_out_dev,
+              float* phase_out_dev, void* stream) {
+    if (!plan || !wave_offsets_dev || !frame_offsets_dev || !wave_dev || !mag_out_dev || n_utts <= 0) {
+        set_error("bad argument to s2st_stft");
+        return S2ST_EINVAL;
+    }
+    return launch_stft(plan, n_utts, total_frames, wave_offsets_dev, frame_offsets_dev, wave_dev, mag_out_dev,
+                       phase_out_dev, nullptr, 0.0f, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_istft(const s2st_plan* plan, int n_utts, int64_t total_frames, const int32_t* frame_offsets_dev,
+               const float* mag_dev, const float* phase_dev, float* wave_out_dev, void* workspace_dev,
+               size_t workspace_bytes, void* stream) {
+    if (!plan || !frame_offsets_dev || !mag_dev || !phase_dev || !wave_out_dev) {
+        set_error("bad argument to s2st_istft");
+        return S2ST_EINVAL;
+    }
+    int rc = check_gl_geometry(plan);
+    if (rc != S2ST_OK) return rc;
+    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, nullptr, mag_dev, kBins, phase_dev, 0,
+                  wave_out_dev, workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_rfft2048(const s2st_plan* plan, int64_t n, const float* in_dev, float* out_dev, void* stream) {
+    if (!plan || !in_dev || !out_dev || n < 0) {
+        set_error("bad argument to s2st_rfft2048");
+        return S2ST_EINVAL;
+    }
+    return launch_rfft2048(plan, n, in_dev, out_dev, false, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_irfft2048(const s2st_plan* plan, int64_t n, const float* in_dev, float* out_dev, void* stream) {
+    if (!plan || !in_dev || !out_dev || n < 0) {
+        set_error("bad argument to s2st_irfft2048");
+        return S2ST_EINVAL;
+    }
+    return launch_rfft2048(plan, n, in_dev, out_dev, true, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_window_sum_square(int n_frames, int hop_length, int win_length, int n_fft, const float* window_host,
+                           float* out_host) {
+    if (n_frames < 1 || hop_length < 1 || win_length < 1 || win_length > n_fft || !window_host || !out_host) {
+        set_error("bad argument to s2st_window_sum_square");
+        return S2ST_EINVAL;
+    }
+    std::vector<float> w2(n_fft, 0.0f);
+    const int pl = (n_fft - win_length) / 2;
+    for (int i = 0; i < win_length; ++i) w2[pl + i] = window_host[i] * window_host[i];
+    const long long n = (long long)n_fft + (long long)hop_length * (n_frames - 1);
+    for (long long i = 0; i < n; ++i) out_host[i] = 0.0f;
+    for (int t = 0; t < n_frames; ++t) {
+        const long long o = (long long)t * hop_length;
+        for (int i = 0; i < n_fft && o + i < n; ++i) out_host[o + i] += w2[i];
+    }
+    return S2ST_OK;
+}
+
+int s2st_logmel(const s2st_plan* plan, int n_utts, int64_t total_frames, const int64_t* wave_offsets_dev,
+                const int32_t* frame_offsets_dev, const float* wave_dev, float eps,
+                const float* cmvn_mean_dev, const float* cmvn_std_dev, float* out_dev, void* stream) {
+    if (!plan || !wave_offsets_dev || !frame_offsets_dev || !wave_dev || !out_dev || n_utts <= 0 ||
+        ((cmvn_mean_dev == nullptr) != (cmvn_std_dev == nullptr))) {
+        set_error("bad argument to s2st_logmel");
+        return S2ST_EINVAL;
+    }
+    return launch_stft(plan, n_utts, total_frames, wave_offsets_dev, frame_offsets_dev, wave_dev, nullptr, nullptr,
+                       out_dev, eps, cmvn_mean_dev, cmvn_std_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_rate, int n_bins) {
+    if (!plan_out || sample_rate <= 0 || n_bins < 4) {
+        set_error("bad argument to s2st_fbank_plan_create");
+        return S2ST_EINVAL;
+    }
+    *plan_out = nullptr;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("cannot select CUDA device %d", device);
+        return S2ST_ECUDA;
+    }
+    // kaldi.py _get_waveform_and_window_properties: python float arithmetic, truncated
+    const double sf = (double)sample_rate;
+    const int shift = (int)(sf * 10.0 * 0.001);
+    const int win = (int)(sf * 25.0 * 0.001);
+    int padded = 1;
+    while (padded < win) padded <<= 1;
+    if (win < 2 || shift < 1 || padded > 4096 || padded < 64) {
+        set_error("unsupported sample rate %d (window %d, padded %d)", sample_rate, win, padded);
+        return S2ST_EINVAL;
+    }
+    s2st_fbank_plan* p = new s2st_fbank_plan();
+    std::memset(p, 0, sizeof(*p));
+    p->device = device;
+    p->sample_rate = sample_rate;
+    p->n_bins = n_bins;
+    p->win = win;
+    p->shift = shift;
+    p->padded = padded;
+    const double pi = 3.14159265358979323846;
+    std::vector<float> window(win);
+    for (int i = 0; i < win; ++i) {
+        const float hann = (float)(0.5 - 0.5 * std::cos(2.0 * pi * (double)i / (double)(win - 1)));
+        window[i] = std::pow(hann, 0.85f);
+    }
+    std::vector<float2> tw(padded / 2);
+    for (int j = 0; j < padded / 2; ++j) {
+        const double a = -2.0 * pi * (double)j / (double)padded;
+        tw[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    // kaldi.py get_mel_banks (no VTLN), evaluated in float32 like torchaudio does
+    const int nfb = padded / 2;
+    const double nyquist = 0.5 * sf;
+    const double low = 20.0, high = nyquist;
+    const double bin_width = sf / (double)padded;
+    const double mel_low = 1127.0 * std::log(1.0 + low / 700.0);
+    const double mel_high = 1127.0 * std::log(1.0 + high / 700.0);
+    const double delta = (mel_high - mel_low) / (double)(n_bins + 1);
+    std::vector<float> dense((size_t)n_bins * (nfb + 1), 0.0f);
+    for (int b = 0; b < n_bins; ++b) {
+        const float left = (float)mel_low + (float)b * (float)delta;
+        const float center = (float)mel_low + ((float)b + 1.0f) * (float)delta;
+        const float right = (float)mel_low + ((float)b + 2.0f) * (float)delta;
+        for (int k = 0; k < nfb; ++k) {
+            const float freq = (float)bin_width * (float)k;
+            const float mel = 1127.0f * std::log(1.0f + freq / 700.0f);
+            const float up = (mel - left) / (center - left);
+            const float down = (right - mel) / (right - center);
+            const float v = std::fmax(0.0f, std::fmin(up, down));
+            dense[(size_t)b * (nfb + 1) + k] = v;
+        }
+    }
+    std::vector<int> ptr, idx;
+    std::vector<float> val;
+    int max_row = 0;
+    to_csr(dense.data(), n_bins, nfb + 1, ptr, idx, val, &max_row);
+    p->mel_nnz = (int)idx.size();
+    if (idx.empty()) {
+        idx.push_back(0);
+        val.push_back(0.0f);
+    }
+    int rc = S2ST_OK;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        set_error("cudaGetDeviceProperties failed");
+        rc = S2ST_ECUDA;
+    } else {
+        p->num_sms = prop.multiProcessorCount;
+    }
+    if (rc == S2ST_OK) rc = upload(&p->window, window);
+    if (rc == S2ST_OK) rc = upload(&p->tw, tw);
+    if (rc == S2ST_OK) rc = upload(&p->mel_ptr, ptr);
+    if (rc == S2ST_OK) rc = upload(&p->mel_idx, idx);
+    if (rc == S2ST_OK) rc = upload(&p->mel_val, val);
+    if (rc != S2ST_OK) {
+        s2st_fbank_plan_destroy(p);
+        return rc;
+    }
+    *plan_out = p;
+    return S2ST_OK;
+}
+
+int s2st_fbank_plan_destroy(s2st_fbank_plan* plan) {
+    if (!plan) return S2ST_OK;
+    DeviceGuard guard(plan->device);
+    cudaFree(plan->window);
+    cudaFree(plan->tw);
+    cudaFree(plan->mel_ptr);
+    cudaFree(plan->mel_idx);
+    cudaFree(plan->mel_val);
+    delete plan;
+    return S2ST_OK;
+}
+
+int s2st_fbank_frame_params(const s2st_fbank_plan* plan, int* win_out, int* shift_out, int* padded_out) {
+    if (!plan) {
+        set_error("null plan");
+        return S2ST_EINVAL;
+    }
+    if (win_out) *win_out = plan->win;
+    if (shift_out) *shift_out = plan->shift;
+    if (padded_out) *padded_out = plan->padded;
+    return S2ST_OK;
+}
+
+int s2st_fbank(const s2st_fbank_plan* plan, int n_utts, int64_t total_frames, const int64_t* wave_offsets_dev,
+               const int32_t* frame_offsets_dev, const float* wave_dev, const float* cmvn_mean_dev,
+               const float* cmvn_std_dev, float* out_dev, void* stream) {
+    if (!plan || !wave_offsets_dev || !frame_offsets_dev || !wave_dev || !out_dev || n_utts <= 0 ||
+        ((cmvn_mean_dev == nullptr) != (cmvn_std_dev == nullptr))) {
+        set_error("bad argument to s2st_fbank");
+        return S2ST_EINVAL;
+    }
+    return launch_fbank(plan, n_utts, total_frames, wave_offsets_dev, frame_offsets_dev, wave_dev, cmvn_mean_dev,
+                        cmvn_std_dev, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_cmvn_apply(int64_t n_rows, int n_cols, const float* x_dev, const float* mean_dev, const float* std_dev,
+                    float* out_dev, void* stream) {
+    if (!x_dev || !mean_dev || !std_dev || !out_dev || n_rows < 0 || n_cols < 1) {
+        set_error("bad argument to s2st_cmvn_apply");
+        return S2ST_EINVAL;
+    }
+    return launch_cmvn(n_rows, n_cols, x_dev, mean_dev, std_dev, out_dev, false, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_cmvn_denormalize(int64_t n_rows, int n_cols, const float* x_dev, const float* mean_dev,
+                          const float* std_dev, float* out_dev, void* stream) {
+    if (!x_dev || !mean_dev || !std_dev || !out_dev || n_rows < 0 || n_cols < 1) {
+        set_error("bad argument to s2st_cmvn_denormalize");
+        return S2ST_EINVAL;
+    }
+    return launch_cmvn(n_rows, n_cols, x_dev, mean_dev, std_dev, out_dev, true, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_cmvn_accumulate(int64_t n_rows, int n_cols, const float* x_dev, double* sums_dev, void* stream) {
+    if (!x_dev || !sums_dev || n_rows < 0 || n_cols < 1) {
+        set_error("bad argument to s2st_cmvn_accumulate");
+        return S2ST_EINVAL;
+    }
+    return launch_cmvn_accumulate(n_rows, n_cols, x_dev, sums_dev, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Shared declarations of the s2st_b200 CUDA library (internal; the public ABI is include/s2st_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s2st {
+
+constexpr int kNfft = 2048;
+constexpr int kBins = kNfft / 2 + 1;  // 1025
+constexpr int kTileFrames = 8;        // frames per tile == warps per CTA of the GL kernel
+constexpr int kGlThreads = 32 * kTileFrames;
+
+struct UttDesc {
+    long long wave_off;  // first sample of this utterance in the concatenated waveform buffers
+    int frame_off;       // first row in the frame-major tensors
+    int n_frames;        // T
+};
+
+struct TileDesc {
+    int utt;  // utterance index
+    int f0;   // first frame (utterance-local) of the tile; tile index within the utterance = f0 / kTileFrames
+    int nf;   // frames in the tile (1..kTileFrames)
+    int pad;
+};
+
+// Everything the Griffin-Lim kernels need, passed by value.
+struct GlParams {
+    // geometry
+    int hop;       // H
+    int half;      // n_fft / 2 (reflect padding, trimmed from both ends)
+    int rot;       // s: first frame sample kept (even); frames are processed circularly rotated by s
+    int ws;        // even upper bound of the window support in rotated coordinates (<= wp)
+    int wp;        // 64 * NZ: samples each lane-register layout covers
+    int nphase;    // overlap-add phases = min(ceil(ws / hop), kTileFrames)
+    int kb;        // bins >= kb have zero target magnitude
+    int mag_stride, phase_stride;
+    // constants (device global memory, owned by the plan)
+    const float* win_a;      // [wp] analysis window, rotated
+    const float* win_s;      // [wp] synthesis window / n_fft, rotated
+    const float* w2;         // [ws] squared window, rotated (edge window-sum-square)
+    const float* inv_wss;    // [hop] 1 / steady-state window-sum-square by (q mod hop)
+    const float2* tw;        // [32*32] exp(-2 pi i r l / 1024)
+    const float2* vtab;      // [1024]  -i exp(-2 pi i k / 2048)
+    // batch tables (workspace)
+    const UttDesc* utts;
+    const TileDesc* tiles;
+    const int* n_tiles;
+    // data
+    const float* mag;        // [total_frames, mag_stride]
+    const float* phase;      // [total_frames, phase_stride] (first pass only)
+    const float* in0;        // parity buffers written by the previous pass
+    const float* in1;
+    float* out0;             // parity buffers written by this pass
+    float* out1;
+};
+
+struct s2st_error_state;
+void set_error(const char* fmt, ...);
+
+#define S2ST_CUDA_CHECK(expr)                                                               \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::s2st::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                              __LINE__);                                                    \
+            return S2ST_ECUDA;                                                              \
+        }                                                                                   \
+    } while (0)
+
+}  // namespace s2st

@@ -1,0 +1,72 @@
+// Plan objects: device-resident constants only (internal).
+#pragma once
+#include "common.cuh"
+
+constexpr int kMaxTimedPasses = 1025;
+
+struct s2st_plan {
+    int device;
+    int n_fft, win_length, hop, n_mels;
+    int rot, ws, wp, nz, nphase;
+    int kb;        // active bins of the inverse-mel basis (kBins when none was given)
+    int kb_pad;    // row pitch of inv_mel_t
+    int num_sms;
+    // device constants
+    float* win_a;
+    float* win_s;
+    float* w2;
+    float* inv_wss;
+    float2* tw;
+    float2* vtab;
+    float* inv_mel_t;   // [n_mels, kb_pad] transposed pseudo-inverse (NULL if absent)
+    int* mel_ptr;       // CSR of the mel filterbank: [n_mels + 1]
+    int* mel_idx;       // [nnz] bin indices, ascending per row
+    float* mel_val;     // [nnz]
+    int mel_nnz;
+    int mel_max_row;    // longest CSR row
+    // profiling aid (s2st_plan_set_pass_timing): CUDA events around every Griffin-Lim pass of the LAST call
+    int timing_enabled;
+    int timing_recorded;          // events recorded by the last gl_run (passes + 1), 0 if none
+    cudaEvent_t timing_events[kMaxTimedPasses + 1];
+};
+
+struct s2st_fbank_plan {
+    int device;
+    int sample_rate, n_bins;
+    int win, shift, padded, log2_half;  // padded = FFT size, half = padded / 2 complex points
+    int num_sms;
+    float* window;      // [win] povey
+    float2* tw;         // [padded / 2] exp(-2 pi i j / padded)   (covers both the half-size FFT and the split)
+    int* mel_ptr;
+    int* mel_idx;
+    float* mel_val;
+    int mel_nnz;
+};
+
+namespace s2st {
+
+// gl_kernels.cu
+size_t gl_workspace_bytes(const s2st_plan* plan, int n_utts, long long total_frames);
+int gl_run(const s2st_plan* plan, int n_utts, long long total_frames, const int32_t* frame_offsets,
+           const float* logmel, const float* mag, int mag_kb, const float* phase, int n_iter,
+           float* wave_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* logmel, bool is_log, float* mag,
+                       int out_stride, int n_out, cudaStream_t stream);
+int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* out, bool inverse,
+                    cudaStream_t stream);
+
+// frontend_kernels.cu
+int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const int64_t* wave_offsets,
+                const int32_t* frame_offsets, const float* wave, float* mag_out, float* phase_out,
+                float* logmel_out, float eps, const float* cmvn_mean, const float* cmvn_std,
+                cudaStream_t stream);
+int launch_mel_project(const s2st_plan* plan, long long n_frames, const float* spec, float* out,
+                       cudaStream_t stream);
+int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames,
+                 const int64_t* wave_offsets, const int32_t* frame_offsets, const float* wave,
+                 const float* cmvn_mean, const float* cmvn_std, float* out, cudaStream_t stream);
+int launch_cmvn(long long n_rows, int n_cols, const float* x, const float* mean, const float* std,
+                float* out, bool denorm, cudaStream_t stream);
+int launch_cmvn_accumulate(long long n_rows, int n_cols, const float* x, double* sums, cudaStream_t stream);
+
+}  // namespace s2st

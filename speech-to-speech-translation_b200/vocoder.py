@@ -1,0 +1,256 @@
+"""Drop-in for ``fairseq/models/text_to_speech/vocoder.py`` (Griffin-Lim part), B200-native.
+
+Same classes, constructor arguments, ``forward`` contract and error behaviour as the reference
+(``PseudoInverseMelScale`` :24-46, ``GriffinLim`` :49-110, ``GriffinLimVocoder`` :113-158,
+``get_vocoder`` :191-197).  All arithmetic runs in the sm_100a CUDA library through the C ABI
+(``include/s2st_b200.h``); there is no CPU path.  On top of the per-utterance ``forward`` the
+vocoder has a ragged batched entry, ``synthesize_batch``, which is the data-parallel hot path:
+one kernel launch per Griffin-Lim iteration for the whole batch.
+"""
+import logging
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .audio_utils import TTSSpectrogram, get_mel_filters
+from .plans import get_stft_plan, require_cuda
+
+logger = logging.getLogger(__name__)
+
+
+def draw_initial_phase(shape) -> np.ndarray:
+    """The reference's initial phase (vocoder.py:103): consumes the GLOBAL numpy RNG in float64."""
+    return np.angle(np.exp(2j * np.pi * np.random.rand(*shape))).astype(np.float32)
+
+
+class PseudoInverseMelScale(torch.nn.Module):
+    def __init__(self, n_stft, n_mels, sample_rate, f_min, f_max) -> None:
+        super().__init__()
+        self.n_mels, self.n_stft = n_mels, n_stft
+        self.n_fft = (n_stft - 1) * 2
+        mel = get_mel_filters(sample_rate, self.n_fft, n_mels, f_min, f_max)
+        self.register_buffer("basis", torch.pinverse(mel))  # F x F_mel, as the reference builds it
+
+    def _plan(self, device):
+        return get_stft_plan(device, self.n_fft, self.n_fft, self.n_fft // 4, self.n_mels,
+                             torch.ones(self.n_fft), inv_mel=self.basis)
+
+    def forward(self, melspec: torch.Tensor) -> torch.Tensor:
+        """melspec [..., F_mel, T] (linear mel magnitudes) -> [..., F, T], clamped at 0."""
+        shape = melspec.shape
+        n_mels, time = shape[-2], shape[-1]
+        assert self.n_mels == n_mels, (self.n_mels, n_mels)
+        dev = require_cuda(melspec.device)
+        x = melspec.detach().to(dev, torch.float32).reshape(-1, n_mels, time).transpose(1, 2).contiguous()
+        rows = x.shape[0] * time
+        out = torch.empty(rows, self.n_stft, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().s2st_inverse_mel(self._plan(dev).handle, rows, _lib.ptr(x), 0, _lib.ptr(out),
+                                              _lib.stream_ptr(dev))
+        _lib.check(rc, "s2st_inverse_mel")
+        out = out.view(-1, time, self.n_stft).transpose(1, 2)
+        return out.reshape(shape[:-2] + (self.n_stft, time)).to(melspec.device, melspec.dtype)
+
+
+class GriffinLim(torch.nn.Module):
+    def __init__(self, n_fft: int, win_length: int, hop_length: int, n_iter: int, window_fn=torch.hann_window):
+        super().__init__()
+        self.transform = TTSSpectrogram(n_fft, win_length, hop_length, window_fn=window_fn, return_phase=True)
+        self.register_buffer("window", window_fn(win_length).float())
+        self.n_fft, self.win_length, self.hop_length, self.n_iter = n_fft, win_length, hop_length, n_iter
+        self.tiny = 1.1754944e-38
+
+    @classmethod
+    def get_window_sum_square(cls, n_frames, hop_length, win_length, n_fft, window_fn=torch.hann_window) -> torch.Tensor:
+        """sum_t w^2[n - t*hop], length n_fft + hop*(n_frames-1) (host helper of the C library)."""
+        import ctypes
+        w = np.ascontiguousarray(window_fn(win_length).float().numpy())
+        out = np.empty(n_fft + hop_length * (n_frames - 1), np.float32)
+        rc = _lib.load().s2st_window_sum_square(n_frames, hop_length, win_length, n_fft,
+                                                ctypes.c_void_p(w.ctypes.data), ctypes.c_void_p(out.ctypes.data))
+        _lib.check(rc, "s2st_window_sum_square")
+        return torch.from_numpy(out)
+
+    def _plan(self, device):
+        return get_stft_plan(device, self.n_fft, self.win_length, self.hop_length, 1, self.window)
+
+    def _run(self, mag_fm, phase_fm, n_utts, frames_per_utt, n_iter, dev):
+        """mag_fm / phase_fm: frame-major [B*T, F] float32 on dev -> [B, L]."""
+        plan = self._plan(dev)
+        total = n_utts * frames_per_utt
+        fo = torch.arange(0, total + 1, frames_per_utt, dtype=torch.int32, device=dev)
+        L = (frames_per_utt - 1) * self.hop_length
+        wave = torch.empty(n_utts, L, dtype=torch.float32, device=dev)
+        if L == 0:
+            return wave
+        ws = plan.workspace(n_utts, total)
+        with torch.cuda.device(dev):
+            rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo), None, _lib.ptr(mag_fm),
+                                                _lib.ptr(phase_fm), n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
+                                                _lib.stream_ptr(dev))
+        _lib.check(rc, "s2st_gl_synthesize")
+        return wave
+
+    def inverse(self, magnitude: torch.Tensor, phase) -> torch.Tensor:
+        """magnitude, phase [B, F, T] -> [B, 1, (T-1)*hop] (iSTFT with window-sum-square normalisation)."""
+        dev = require_cuda(magnitude.device)
+        B, F, T = magnitude.shape
+        mag = magnitude.detach().to(dev, torch.float32).transpose(1, 2).reshape(B * T, F).contiguous()
+        ph = torch.as_tensor(phase).detach().to(dev, torch.float32).transpose(1, 2).reshape(B * T, F).contiguous()
+        wave = self._run(mag, ph, B, T, 0, dev)
+        return wave.unsqueeze(1).to(magnitude.device, magnitude.dtype)
+
+    def forward(self, specgram: torch.Tensor) -> torch.Tensor:
+        """specgram [F, T] or [B, F, T] linear magnitudes -> waveform(s); random initial phase from the
+        global numpy RNG exactly like the reference."""
+        angles = draw_initial_phase(specgram.shape)
+        dev = require_cuda(specgram.device)
+        spec = specgram.detach().reshape(-1, specgram.shape[-2], specgram.shape[-1])
+        B, F, T = spec.shape
+        _check_length(T, self.hop_length, self.n_fft, self.n_iter)
+        mag = spec.to(dev, torch.float32).transpose(1, 2).reshape(B * T, F).contiguous()
+        ph = torch.from_numpy(np.ascontiguousarray(angles.reshape(B, F, T).transpose(0, 2, 1))).to(dev).reshape(B * T, F)
+        wave = self._run(mag, ph, B, T, self.n_iter, dev)
+        return wave.squeeze(0).to(specgram.device, specgram.dtype)
+
+
+def _check_length(T, hop, n_fft, n_iter):
+    # the reference's STFT reflect-pads n_fft//2 and F.pad raises when padding >= length
+    L = (T - 1) * hop
+    if n_iter > 0 and L <= n_fft // 2:
+        raise RuntimeError(
+            f"Argument #4: Padding size should be less than the corresponding input dimension, but got: padding "
+            f"({n_fft // 2}, {n_fft // 2}) at dimension 2 of input [1, 1, {L}] ({T} frames are too few for "
+            f"n_fft {n_fft}, hop {hop})")
+
+
+class GriffinLimVocoder(nn.Module):
+    def __init__(self, sample_rate, win_size, hop_size, n_fft, n_mels, f_min, f_max, window_fn,
+                 spec_bwd_max_iter=32, fp16=False):
+        super().__init__()
+        self.inv_mel_transform = PseudoInverseMelScale(n_stft=n_fft // 2 + 1, n_mels=n_mels, sample_rate=sample_rate,
+                                                       f_min=f_min, f_max=f_max)
+        self.gl_transform = GriffinLim(n_fft=n_fft, win_length=win_size, hop_length=hop_size, window_fn=window_fn,
+                                       n_iter=spec_bwd_max_iter)
+        self.sample_rate, self.n_mels = sample_rate, n_mels
+        # the kernels compute in fp32; with fp16=True inputs / outputs are half like the reference's
+        # (the S2ST recipe never passes --fp16 at synthesis, run_baseline.sh:143-150)
+        self.fp16 = fp16
+        self.float()
+
+    # -- plans ----------------------------------------------------------------------------------
+    def _plan(self, device):
+        g = self.gl_transform
+        return get_stft_plan(device, g.n_fft, g.win_length, g.hop_length, self.n_mels, g.window.float(),
+                             inv_mel=self.inv_mel_transform.basis.float())
+
+    def _device(self, x):
+        if x.device.type == "cuda":
+            return require_cuda(x.device)
+        b = self.inv_mel_transform.basis
+        return require_cuda(b.device if b.device.type == "cuda" else None)
+
+    # -- the reference API ----------------------------------------------------------------------
+    def forward(self, x):
+        """x: (B x) T x n_mels denormalised log-mel -> (B x) (T-1)*hop waveform on x's device / dtype."""
+        self.eval()
+        g = self.gl_transform
+        batched = x.dim() == 3
+        feats = x.detach()
+        B = feats.shape[0] if batched else 1
+        T = feats.shape[-2]
+        assert feats.shape[-1] == self.n_mels, (self.n_mels, feats.shape[-1])
+        # initial phase: one draw of shape (B x) F x T from numpy's global RNG (vocoder.py:103)
+        shape = ((B,) if batched else ()) + (g.n_fft // 2 + 1, T)
+        angles = draw_initial_phase(shape).reshape(B, g.n_fft // 2 + 1, T)
+        _check_length(T, g.hop_length, g.n_fft, g.n_iter)
+        dev = self._device(feats)
+        phase_fm = torch.from_numpy(np.ascontiguousarray(angles.transpose(0, 2, 1)).reshape(B * T, -1))
+        waves = self._synthesize_flat(feats.reshape(B * T, self.n_mels).to(dev, torch.float32).contiguous(),
+                                      [T] * B, phase_fm.to(dev, non_blocking=True), g.n_iter, dev)
+        out = waves.view(B, -1)
+        out = out.squeeze(0) if (not batched or B == 1) else out
+        return out.to(x.device, x.dtype)
+
+    @classmethod
+    def from_data_cfg(cls, args, data_cfg):
+        feat_cfg = data_cfg.config["features"]
+        window_fn = getattr(torch, feat_cfg["window_fn"] + "_window")
+        return cls(sample_rate=feat_cfg["sample_rate"],
+                   win_size=int(feat_cfg["win_len_t"] * feat_cfg["sample_rate"]),
+                   hop_size=int(feat_cfg["hop_len_t"] * feat_cfg["sample_rate"]),
+                   n_fft=feat_cfg["n_fft"], n_mels=feat_cfg["n_mels"],
+                   f_min=feat_cfg["f_min"], f_max=feat_cfg["f_max"],
+                   window_fn=window_fn, spec_bwd_max_iter=args.spec_bwd_max_iter, fp16=args.fp16)
+
+    # -- the data-parallel entry ----------------------------------------------------------------
+    def _synthesize_flat(self, logmel_flat, frames: Sequence[int], phase_fm, n_iter, dev):
+        plan = self._plan(dev)
+        n_utts, total = len(frames), int(sum(frames))
+        fo = np.zeros(n_utts + 1, np.int32)
+        fo[1:] = np.cumsum(frames)
+        fo_d = torch.from_numpy(fo).to(dev, non_blocking=True)
+        n_samples = (total - n_utts) * self.gl_transform.hop_length
+        wave = torch.empty(max(n_samples, 0), dtype=torch.float32, device=dev)
+        if n_samples <= 0:
+            return wave
+        ws = plan.workspace(n_utts, total)
+        with torch.cuda.device(dev):
+            rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo_d), _lib.ptr(logmel_flat), None,
+                                                _lib.ptr(phase_fm), n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
+                                                _lib.stream_ptr(dev))
+        _lib.check(rc, "s2st_gl_synthesize")
+        return wave
+
+    def synthesize_batch(self, feats: List[torch.Tensor], init_phase: Optional[List] = None,
+                         n_iter: Optional[int] = None, device=None) -> List[torch.Tensor]:
+        """Ragged batch: feats[i] is [T_i, n_mels] denormalised log-mel -> list of [(T_i-1)*hop] CUDA tensors.
+
+        init_phase[i] (optional) is the reference-layout [F, T_i] initial phase (numpy or tensor); when
+        omitted, phases are drawn from numpy's global RNG utterance by utterance, i.e. exactly what
+        calling ``forward`` on each utterance in order would consume.
+        """
+        g = self.gl_transform
+        n_iter = g.n_iter if n_iter is None else n_iter
+        F = g.n_fft // 2 + 1
+        frames = [int(f.shape[0]) for f in feats]
+        for T in frames:
+            _check_length(T, g.hop_length, g.n_fft, n_iter)
+        dev = require_cuda(device) if device is not None else self._device(feats[0])
+        if init_phase is None:
+            init_phase = [draw_initial_phase((F, T)) for T in frames]
+        ph = []
+        for p, T in zip(init_phase, frames):
+            if isinstance(p, torch.Tensor):
+                assert p.shape == (F, T)
+                ph.append(p.to(dev, torch.float32).t())
+            else:
+                p = np.asarray(p, np.float32)
+                assert p.shape == (F, T)
+                ph.append(torch.from_numpy(np.ascontiguousarray(p.T)).to(dev, non_blocking=True))
+        phase_fm = torch.cat(ph).contiguous()
+        flat = torch.cat([f.detach().to(dev, torch.float32) for f in feats]).contiguous()
+        wave = self._synthesize_flat(flat, frames, phase_fm, n_iter, dev)
+        lens = [(T - 1) * g.hop_length for T in frames]
+        return list(torch.split(wave, lens))
+
+    def synthesize_flat(self, logmel_flat: torch.Tensor, frames: Sequence[int], phase_fm: torch.Tensor,
+                        n_iter: Optional[int] = None) -> torch.Tensor:
+        """Lowest-overhead entry: everything already resident and frame-major on one CUDA device:
+        logmel_flat [sum T, n_mels], phase_fm [sum T, F] -> concatenated waveforms [sum (T_i-1)*hop]."""
+        n_iter = self.gl_transform.n_iter if n_iter is None else n_iter
+        dev = require_cuda(logmel_flat.device)
+        assert logmel_flat.is_cuda and phase_fm.is_cuda and logmel_flat.dtype == phase_fm.dtype == torch.float32
+        return self._synthesize_flat(logmel_flat.contiguous(), frames, phase_fm.contiguous(), n_iter, dev)
+
+
+def get_vocoder(args, data_cfg):
+    if args.vocoder == "griffin_lim":
+        return GriffinLimVocoder.from_data_cfg(args, data_cfg)
+    elif args.vocoder == "hifigan":
+        raise NotImplementedError("the HiFi-GAN neural vocoder is outside this package's scope (Griffin-Lim hot path only)")
+    else:
+        raise ValueError("Unknown vocoder")

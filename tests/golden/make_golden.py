@@ -1,0 +1,211 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED
+reference implementation from /root/reference (build container only; the GPU
+box has no /root/reference and never runs this script).
+
+    python tests/golden/make_golden.py
+
+The reference modules are loaded by file path with stub parent packages
+(SURVEY.md appendix B): ``import fairseq`` itself fails here (omegaconf, hydra
+missing) but audio_utils.py / vocoder.py / feature_transforms only need numpy
+and torch.  ``librosa`` is not installed; the stand-in below implements
+librosa.filters.mel's Slaney recipe (the only librosa call on the path).  The
+stand-in is deliberately an independent implementation from oracle/mel.py: it
+is cross-checked against torchaudio.functional.melscale_fbanks here.
+
+Outputs (float32 unless noted), all produced by reference code:
+  gl_small.npz     logmel [T,80], init phase [1025,T], waveform after n_iter
+                   iterations, for a few (T, n_iter, kind) cases; spectral
+                   convergence of the reference output
+  basis.npz        mel filterbank [80,1025] (sparse form) and its torch.pinverse
+                   [1025,80] (rows >= 683 are exactly zero; stored truncated)
+  logmel.npz       waveform -> extract_logmel_spectrogram features
+  fbank.npz        int16-scaled waveform -> _get_torchaudio_fbank features, 16 kHz and 8 kHz
+  cmvn.npz         features, stats, GlobalCMVN output, gcmvn_denormalize output
+  wss.npz          GriffinLim.get_window_sum_square for a few frame counts
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _slaney_mel_standin(sr, n_fft, n_mels=128, fmin=0.0, fmax=None):
+    """librosa.filters.mel restated via torchaudio's slaney filterbank (independent of oracle/)."""
+    import torchaudio.functional as taf
+    fmax = sr / 2.0 if fmax is None else fmax
+    fb = taf.melscale_fbanks(n_fft // 2 + 1, float(fmin), float(fmax), n_mels, sr,
+                             norm="slaney", mel_scale="slaney")
+    return fb.T.contiguous().numpy().astype(np.float32)
+
+
+def load_reference():
+    for name in ["fairseq", "fairseq.data", "fairseq.data.audio", "fairseq.models",
+                 "fairseq.models.text_to_speech"]:
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    librosa = types.ModuleType("librosa")
+    librosa.filters = types.ModuleType("librosa.filters")
+    librosa.filters.mel = _slaney_mel_standin
+    sys.modules["librosa"] = librosa
+    sys.modules["librosa.filters"] = librosa.filters
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    au = load("fairseq.data.audio.audio_utils", "fairseq/data/audio/audio_utils.py")
+    stub = types.ModuleType("fairseq.data.audio.speech_to_text_dataset")
+    stub.S2TDataConfig = type("S2TDataConfig", (), {})
+    sys.modules[stub.__name__] = stub
+    load("fairseq.models.text_to_speech.hifigan", "fairseq/models/text_to_speech/hifigan.py")
+    voc = load("fairseq.models.text_to_speech.vocoder", "fairseq/models/text_to_speech/vocoder.py")
+    ft_dir = os.path.join(REF, "fairseq/data/audio/feature_transforms")
+    spec = importlib.util.spec_from_file_location(
+        "fairseq.data.audio.feature_transforms", os.path.join(ft_dir, "__init__.py"),
+        submodule_search_locations=[ft_dir])
+    ft = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = ft
+    try:
+        spec.loader.exec_module(ft)
+    except ImportError as e:  # specaugment may need cv2; the cmvn modules are what we need
+        print("note: feature_transforms auto-import stopped at:", e)
+    return au, voc, ft
+
+
+def synth_logmel(T, seed, kind):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "smooth":
+        x = 0.1 * torch.cumsum(torch.randn(T, 80, generator=g), dim=0)
+        x = x + torch.linspace(0, -4, 80)[None, :] - 2.0
+        x = x.clamp(float(np.log(1e-5)), 2.0)
+    else:
+        x = torch.randn(T, 80, generator=g) - 3.0
+    return x.float()
+
+
+def synth_audio(n, sr, seed):
+    rng = np.random.RandomState(seed)
+    t = np.arange(n) / sr
+    x = 0.1 * rng.randn(n)
+    for _ in range(3):
+        x += rng.uniform(0.05, 0.3) * np.sin(2 * np.pi * rng.uniform(80, 0.45 * sr) * t + rng.uniform(0, 6.28))
+    return np.clip(x, -1, 1).astype(np.float32)
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    au, voc_mod, ft = load_reference()
+    voc = voc_mod.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window,
+                                    spec_bwd_max_iter=64)
+    # ---- basis -------------------------------------------------------------------
+    mel = au.get_mel_filters(24000, 2048, 80, 20, 8000).numpy()
+    pinv = voc.inv_mel_transform.basis.numpy()
+    nz_rows = np.nonzero(np.abs(pinv).sum(axis=1))[0]
+    last = int(nz_rows.max())
+    assert np.all(pinv[last + 1:] == 0)
+    r, c = np.nonzero(mel)
+    np.savez_compressed(os.path.join(HERE, "basis.npz"), mel_rows=r.astype(np.int16), mel_cols=c.astype(np.int16),
+                        mel_vals=mel[r, c], pinv_head=pinv[: last + 1], last_nonzero_row=last)
+    print("basis: mel nnz", len(r), "pinv last nonzero row", last)
+
+    # ---- Griffin-Lim ---------------------------------------------------------------
+    out = {}
+    cases = [("c0", 60, 64, "smooth", 11), ("c1", 37, 8, "iid", 12), ("c2", 5, 4, "smooth", 13),
+             ("c3", 96, 64, "iid", 14)]
+    for name, T, n_iter, kind, seed in cases:
+        x = synth_logmel(T, 1234 + seed, kind)
+        np.random.seed(seed)
+        phase = np.angle(np.exp(2j * np.pi * np.random.rand(1025, T))).astype(np.float32)
+        voc.gl_transform.n_iter = n_iter
+        np.random.seed(seed)  # forward() draws the same phase from the global RNG
+        with torch.no_grad():
+            y = voc(x).numpy()
+            mag = voc.inv_mel_transform(x.exp().transpose(-1, -2))
+            m2, _ = voc.gl_transform.transform(torch.from_numpy(y)[None])
+            sc = float(torch.norm(m2[0] - mag) / torch.norm(mag))
+        out[name + "_logmel"] = x.numpy()
+        out[name + "_phase"] = phase.astype(np.float16)  # regenerated exactly from the seed in tests
+        out[name + "_seed"] = seed
+        out[name + "_n_iter"] = n_iter
+        out[name + "_wave"] = y
+        out[name + "_sc"] = sc
+        print("gl", name, T, n_iter, kind, "L", y.shape, "sc", sc)
+    # one STFT / ISTFT pair on a fixed signal, to pin the transforms separately
+    w = synth_audio(6000, 24000, 5)
+    with torch.no_grad():
+        mg, ph = voc.gl_transform.transform(torch.from_numpy(w)[None])
+        back = voc.gl_transform.inverse(mg, ph).squeeze().numpy()
+    out["stft_in"] = w
+    out["stft_mag"] = mg[0].numpy()
+    out["stft_phase"] = ph[0].numpy()
+    out["istft_out"] = back
+    for k in list(out):
+        if k.endswith("_phase") and k != "stft_phase":
+            del out[k]  # the seed reproduces it bit-exactly; keep the fixture small
+    np.savez_compressed(os.path.join(HERE, "gl_small.npz"), **out)
+
+    # batched forward [B,T,80] draws one [B,1025,T] phase tensor
+    xb = torch.stack([synth_logmel(24, 77, "smooth"), synth_logmel(24, 78, "iid")])
+    voc.gl_transform.n_iter = 4
+    np.random.seed(21)
+    with torch.no_grad():
+        yb = voc(xb).numpy()
+    np.savez_compressed(os.path.join(HERE, "gl_batched.npz"), logmel=xb.numpy(), seed=21, n_iter=4, wave=yb)
+
+    # ---- window sum square -------------------------------------------------------------
+    wss = {"T%d" % t: voc_mod.GriffinLim.get_window_sum_square(t, 300, 1200, 2048).numpy() for t in (1, 5, 9, 40)}
+    np.savez_compressed(os.path.join(HERE, "wss.npz"), **wss)
+
+    # ---- log-mel front-end (speech_synthesis/data_utils.py:46-76 restated with the reference modules) ----
+    spec_t = au.TTSSpectrogram(n_fft=2048, win_length=1200, hop_length=300, window_fn=torch.hann_window)
+    mel_t = au.TTSMelScale(n_mels=80, sample_rate=24000, f_min=20, f_max=8000, n_stft=1025)
+    lm = {}
+    for i, n in enumerate((12000, 7777, 2400)):
+        w = synth_audio(n, 24000, 40 + i)
+        with torch.no_grad():
+            f = torch.clamp(mel_t(spec_t(torch.from_numpy(w)[None])), min=1e-5).log().squeeze().t().numpy()
+        lm["wave%d" % i] = w
+        lm["feat%d" % i] = f
+        print("logmel", n, f.shape)
+    np.savez_compressed(os.path.join(HERE, "logmel.npz"), **lm)
+
+    # ---- fbank ------------------------------------------------------------------------------
+    fb = {}
+    for i, (sr, n) in enumerate(((16000, 16000), (16000, 5003), (8000, 6000), (16000, 400))):
+        w = (synth_audio(n, sr, 60 + i) * (2 ** 15)).astype(np.float32)
+        f = au._get_torchaudio_fbank(w[None, :], sr, 80)
+        fb["wave%d" % i] = w
+        fb["sr%d" % i] = sr
+        fb["feat%d" % i] = f
+        print("fbank", sr, n, f.shape)
+    np.savez_compressed(os.path.join(HERE, "fbank.npz"), **fb)
+
+    # ---- CMVN ---------------------------------------------------------------------------------
+    rng = np.random.RandomState(7)
+    mean = rng.randn(80).astype(np.float32) - 4.0
+    std = rng.uniform(0.5, 2.0, 80).astype(np.float32)
+    stats_path = "/tmp/_golden_stats.npz"
+    np.savez(stats_path, mean=mean, std=std)
+    x = rng.randn(50, 80).astype(np.float32) * 2 - 4
+    reg = ft.AUDIO_FEATURE_TRANSFORM_REGISTRY
+    outs = {n: reg[n].from_config_dict({"stats_npz_path": stats_path})(x)
+            for n in ("global_cmvn", "src_global_cmvn", "tgt_global_cmvn")}
+    xt = torch.from_numpy(outs["global_cmvn"])[None]
+    den = (xt * torch.from_numpy(std).view(1, 1, -1).expand_as(xt) + torch.from_numpy(mean).view(1, 1, -1).expand_as(xt))
+    np.savez_compressed(os.path.join(HERE, "cmvn.npz"), x=x, mean=mean, std=std, denorm=den[0].numpy(), **outs)
+    print("cmvn ok", {k: v.dtype for k, v in outs.items()})
+
+
+if __name__ == "__main__":
+    main()

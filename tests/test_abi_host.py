@@ -1,0 +1,142 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header declares;
+host logic (registry, mel filters, window-sum-square, sharding plans); product fails loudly without CUDA."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "s2st_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2st_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg, built_lib):
+    declared = _header_functions()
+    assert len(declared) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (s2st_[a-z0-9_]+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert set(declared) == set(pkg._lib.SIGNATURES), set(declared) ^ set(pkg._lib.SIGNATURES)
+    assert built_lib.s2st_abi_version() == 1
+
+
+def test_library_is_sm100a(pkg, built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_window_sum_square_host_entry(pkg, built_lib):
+    w = load_golden("wss.npz")
+    for k in w.files:
+        mine = pkg.GriffinLim.get_window_sum_square(int(k[1:]), 300, 1200, 2048).numpy()
+        assert mine.shape == w[k].shape and np.abs(mine - w[k]).max() < 1e-6
+
+
+def test_bad_arguments_return_status_not_crash(pkg, built_lib):
+    rc = built_lib.s2st_window_sum_square(0, 300, 1200, 2048, None, None)
+    assert rc == 1 and b"bad argument" in built_lib.s2st_last_error()
+    with pytest.raises(ValueError):
+        pkg._lib.check(rc, "s2st_window_sum_square")
+
+
+def test_mel_filters_and_pinv_match_reference(pkg, golden_basis):
+    mel, pinv = golden_basis
+    mine = pkg.get_mel_filters(24000, 2048, 80, 20, 8000).numpy()
+    assert np.abs(mine - mel).max() <= 2.4e-7 and (mine != 0).sum() == 1334
+    voc = pkg.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window, spec_bwd_max_iter=64)
+    b = voc.inv_mel_transform.basis.numpy()
+    assert b.shape == (1025, 80) and np.all(b[683:] == 0)
+    assert np.linalg.norm(b - pinv) / np.linalg.norm(pinv) < 5e-5
+    assert voc.gl_transform.n_iter == 64 and voc.gl_transform.hop_length == 300
+
+
+def test_get_window_and_fourier_basis(pkg):
+    w = pkg.get_window(torch.hann_window, 2048, 1200)
+    assert w.shape == (2048,) and w[:425].abs().sum() == 0 and w[1624:].abs().sum() == 0 and w[425] > 0
+    b = pkg.get_fourier_basis(16).numpy()
+    ref = np.fft.fft(np.eye(16))
+    assert np.allclose(b, np.vstack([ref.real[:9], ref.imag[:9]]), atol=1e-6)
+
+
+def test_from_data_cfg_and_get_vocoder(pkg):
+    class Cfg:
+        config = {"features": dict(window_fn="hann", sample_rate=24000, win_len_t=0.05, hop_len_t=0.0125, n_fft=2048,
+                                   n_mels=80, f_min=20, f_max=8000)}
+
+    class Args:
+        vocoder, spec_bwd_max_iter, fp16 = "griffin_lim", 64, False
+
+    v = pkg.get_vocoder(Args, Cfg)
+    assert isinstance(v, pkg.GriffinLimVocoder)
+    assert (v.gl_transform.win_length, v.gl_transform.hop_length, v.gl_transform.n_iter) == (1200, 300, 64)
+    Args.vocoder = "wavenet"
+    with pytest.raises(ValueError, match="Unknown vocoder"):
+        pkg.get_vocoder(Args, Cfg)
+
+
+def test_registry_semantics(pkg):
+    ft = pkg.feature_transforms
+    for name in ("global_cmvn", "src_global_cmvn", "tgt_global_cmvn"):
+        assert issubclass(ft.get_audio_feature_transform(name), ft.AudioFeatureTransform)
+    with pytest.raises(ValueError, match="duplicate transform"):
+        ft.register_audio_feature_transform("global_cmvn")(type("X1", (ft.AudioFeatureTransform,), {}))
+    with pytest.raises(ValueError, match="must extend"):
+        ft.register_audio_feature_transform("not_a_transform")(type("X2", (), {}))
+    with pytest.raises(ValueError, match="duplicate class name"):
+        ft.register_audio_feature_transform("another_name")(type("GlobalCMVN", (ft.AudioFeatureTransform,), {}))
+    assert ft.CompositeAudioFeatureTransform.from_config_dict(None) is None
+    assert ft.CompositeAudioFeatureTransform.from_config_dict_for_src({"tgt_transforms": []}) is None
+
+
+def test_composite_from_yaml_style_config(pkg, tmp_path):
+    ft = pkg.feature_transforms
+    p = tmp_path / "stats.npz"
+    np.savez(p, mean=np.zeros(80, np.float32), std=np.ones(80, np.float32))
+    cfg = {"src_transforms": ["src_global_cmvn"], "src_global_cmvn": {"stats_npz_path": str(p)},
+           "tgt_transforms": ["tgt_global_cmvn"], "tgt_global_cmvn": {"stats_npz_path": str(p)}}
+    c = ft.CompositeAudioFeatureTransform.from_config_dict_for_src(cfg)
+    assert len(c.transforms) == 1 and isinstance(c.transforms[0], pkg.SRCGlobalCMVN)
+    assert "SRCGlobalCMVN" in repr(c)
+    t = ft.CompositeAudioFeatureTransform.from_config_dict_for_tgt(cfg)
+    assert isinstance(t.transforms[0], pkg.TGTGlobalCMVN)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_cuda(pkg):
+    voc = pkg.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window, spec_bwd_max_iter=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        voc(torch.zeros(10, 80))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.logmel_batch([torch.zeros(4000)])
+
+
+def test_missing_library_fails_loudly(pkg, built_lib, monkeypatch):
+    monkeypatch.setattr(pkg._lib, "_lib", None)
+    monkeypatch.setattr(pkg._lib, "LIB_PATH", "/nonexistent/libs2st_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg._lib.load()
+
+
+def test_short_utterance_raises_like_reference(pkg):
+    from importlib import import_module
+    voc_mod = import_module(pkg.__name__ + ".vocoder")
+    with pytest.raises(RuntimeError, match="Padding size should be less"):
+        voc_mod._check_length(4, 300, 2048, 8)  # reference: reflect pad 1024 >= 900 samples
+    voc_mod._check_length(5, 300, 2048, 8)
+    voc_mod._check_length(1, 300, 2048, 0)  # inverse only: any T
+
+
+def test_product_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "speech-to-speech-translation_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().lower().replace("no oracle", ""), f

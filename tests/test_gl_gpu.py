@@ -1,0 +1,224 @@
+"""GPU parity tests for the Griffin-Lim path: CUDA kernels (through the C ABI) vs the oracle and the
+reference's golden vectors.  Tolerances are BASELINE.json's: waveform rel-L2 <= 1e-3 after the
+iterations, spectral convergence within 1e-4."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, seeded_phase, synth_audio, synth_logmel
+from oracle import griffin_lim as ogl
+
+pytestmark = pytest.mark.gpu
+CFG = dict(n_fft=2048, win_length=1200, hop_length=300)
+
+
+@pytest.fixture(scope="module")
+def voc(pkg, built_lib):
+    v = pkg.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window, spec_bwd_max_iter=64)
+    return v.cuda()
+
+
+@pytest.fixture(scope="module")
+def basis(voc):
+    return voc.inv_mel_transform.basis.cpu().numpy()
+
+
+def test_native_library_is_loaded(pkg, built_lib):
+    assert isinstance(built_lib, ctypes.CDLL)
+    assert "libs2st_b200.so" in open("/proc/self/maps").read()
+
+
+def test_rfft_irfft_2048(pkg, built_lib):
+    from importlib import import_module
+    plans = import_module(pkg.__name__ + ".plans")
+    plan = plans.get_stft_plan("cuda", 2048, 1200, 300, 1, torch.hann_window(1200))
+    rng = np.random.RandomState(0)
+    n = 37
+    x = rng.randn(n, 2048).astype(np.float32)
+    x[3] = 0
+    x[4, :] = 1.0
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty(n, 1025, 2, device="cuda")
+    pkg._lib.check(built_lib.s2st_rfft2048(plan.handle, n, pkg._lib.ptr(xd), pkg._lib.ptr(out), pkg._lib.stream_ptr(xd.device)), "rfft")
+    ref = np.fft.rfft(x.astype(np.float64), axis=1)
+    got = out[..., 0].cpu().numpy() + 1j * out[..., 1].cpu().numpy()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-6
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-6
+    # inverse of a Hermitian half-spectrum, with junk in the imaginary parts of DC / Nyquist (ignored)
+    spec = np.stack([ref.real, ref.imag], -1).astype(np.float32)
+    spec[:, 0, 1] = 5.0
+    sd = torch.from_numpy(spec).cuda()
+    back = torch.empty(n, 2048, device="cuda")
+    pkg._lib.check(built_lib.s2st_irfft2048(plan.handle, n, pkg._lib.ptr(sd), pkg._lib.ptr(back), pkg._lib.stream_ptr(sd.device)), "irfft")
+    assert np.abs(back.cpu().numpy() - x).max() < 5e-6
+
+
+def test_stft_matches_oracle_and_reference(pkg, voc):
+    g = load_golden("gl_small.npz")
+    w = torch.from_numpy(g["stft_in"]).cuda()[None]
+    mag, ph = voc.gl_transform.transform(w)
+    assert mag.shape == (1, 1025, 21)
+    mag, ph = mag[0].cpu().numpy(), ph[0].cpu().numpy()
+    for ref_mag, ref_ph in ((g["stft_mag"], g["stft_phase"]), ogl.stft(g["stft_in"], **CFG)):
+        assert ogl.rel_l2(mag, ref_mag) < 2e-6
+        d = np.angle(np.exp(1j * (ph.astype(np.float64) - ref_ph)))
+        assert np.sqrt((ref_mag * d ** 2).sum() / ref_mag.sum()) < 1e-5
+
+
+def test_istft_matches_oracle_and_reference(pkg, voc):
+    g = load_golden("gl_small.npz")
+    mag = torch.from_numpy(g["stft_mag"]).cuda()[None]
+    ph = torch.from_numpy(g["stft_phase"]).cuda()[None]
+    y = voc.gl_transform.inverse(mag, ph)
+    assert y.shape == (1, 1, 6000)
+    y = y[0, 0].cpu().numpy()
+    assert ogl.rel_l2(y, g["istft_out"]) < 5e-6
+    assert ogl.rel_l2(y, ogl.istft(g["stft_mag"], g["stft_phase"], **CFG)) < 5e-6
+
+
+@pytest.mark.parametrize("T", [1, 2, 5, 8, 9, 16, 17, 23])
+def test_inverse_only_ragged_tile_edges(pkg, voc, T):
+    """n_iter = 0 (initial inverse only) across tile boundaries (8 frames per tile), incl. T < 5."""
+    rng = np.random.RandomState(T)
+    mag = np.abs(rng.randn(1025, T)).astype(np.float32)
+    ph = rng.uniform(-np.pi, np.pi, (1025, T)).astype(np.float32)
+    y = voc.gl_transform.inverse(torch.from_numpy(mag).cuda()[None], torch.from_numpy(ph).cuda()[None])[0, 0].cpu().numpy()
+    ref = ogl.istft(mag, ph, **CFG)
+    assert y.shape == ref.shape == ((T - 1) * 300,)
+    if T > 1:
+        assert ogl.rel_l2(y, ref) < 5e-6
+
+
+def test_inverse_mel_matches_oracle(pkg, voc, basis):
+    x = synth_logmel(50, 5).cuda()
+    spec = voc.inv_mel_transform(x.exp().t())  # reference surface: [n_mels, T] linear mel in
+    ref = ogl.inverse_mel(x.cpu().numpy(), basis)
+    assert spec.shape == (1025, 50)
+    s = spec.cpu().numpy()
+    assert np.all(s >= 0) and np.all(s[683:] == 0)
+    assert ogl.rel_l2(s, ref) < 2e-6
+
+
+@pytest.mark.parametrize("case", ["c0", "c1", "c2", "c3"])
+def test_forward_matches_reference_golden(pkg, voc, basis, case):
+    """Drop-in forward(): consumes numpy's global RNG like the reference, so seeding reproduces its output."""
+    g = load_golden("gl_small.npz")
+    x, n_iter, seed = g[case + "_logmel"], int(g[case + "_n_iter"]), int(g[case + "_seed"])
+    voc.gl_transform.n_iter = n_iter
+    np.random.seed(seed)
+    y = voc(torch.from_numpy(x).cuda())
+    voc.gl_transform.n_iter = 64
+    assert y.is_cuda and y.dtype == torch.float32 and y.shape == ((x.shape[0] - 1) * 300,)
+    y = y.cpu().numpy()
+    assert ogl.rel_l2(y, g[case + "_wave"]) < 1e-3
+    sc = ogl.spectral_convergence(y, ogl.inverse_mel(x, basis), **CFG)
+    assert abs(sc - float(g[case + "_sc"])) < 1e-4
+    # and against the oracle on the same inputs
+    ref = ogl.vocoder_forward(x, seeded_phase(seed, x.shape[0]), n_iter, basis=basis)
+    assert ogl.rel_l2(y, ref) < 1e-3
+
+
+def test_batched_dense_forward_matches_reference(pkg, voc):
+    g = load_golden("gl_batched.npz")
+    voc.gl_transform.n_iter = int(g["n_iter"])
+    np.random.seed(int(g["seed"]))
+    y = voc(torch.from_numpy(g["logmel"]).cuda())
+    voc.gl_transform.n_iter = 64
+    assert y.shape == g["wave"].shape
+    for b in range(2):
+        assert ogl.rel_l2(y[b].cpu().numpy(), g["wave"][b]) < 1e-3
+
+
+def test_ragged_batch_equals_per_utterance_and_oracle(pkg, voc, basis):
+    """The data-parallel entry: ragged lengths incl. tile-boundary cases; bitwise equal to one-at-a-time."""
+    frames = [5, 8, 9, 31, 56, 64, 65, 100]
+    feats = [synth_logmel(T, 100 + i, "smooth" if i % 2 else "iid") for i, T in enumerate(frames)]
+    phases = [seeded_phase(200 + i, T) for i, T in enumerate(frames)]
+    outs = voc.synthesize_batch([f.cuda() for f in feats], init_phase=phases, n_iter=16)
+    assert [o.numel() for o in outs] == [(T - 1) * 300 for T in frames]
+    for i in (0, 2, 5, 7):
+        single = voc.synthesize_batch([feats[i].cuda()], init_phase=[phases[i]], n_iter=16)[0]
+        assert torch.equal(single, outs[i])  # batch composition must not change results
+        ref = ogl.vocoder_forward(feats[i].numpy(), phases[i], 16, basis=basis)
+        assert ogl.rel_l2(outs[i].cpu().numpy(), ref) < 1e-3
+    # deterministic run to run
+    again = voc.synthesize_batch([f.cuda() for f in feats], init_phase=phases, n_iter=16)
+    assert all(torch.equal(a, b) for a, b in zip(outs, again))
+
+
+def test_config1_500_frames_64_iters(pkg, voc, basis):
+    """BASELINE config 1: one 500-frame utterance, 64 iterations, seeded phase."""
+    x = synth_logmel(500, 1234)
+    phase = seeded_phase(0, 500)
+    y = voc.synthesize_batch([x.cuda()], init_phase=[phase], n_iter=64)[0].cpu().numpy()
+    ref = ogl.vocoder_forward(x.numpy(), phase, 64, basis=basis)
+    assert y.shape == ref.shape == (149700,)
+    assert ogl.rel_l2(y, ref) < 1e-3
+    mag = ogl.inverse_mel(x.numpy(), basis)
+    assert abs(ogl.spectral_convergence(y, mag, **CFG) - ogl.spectral_convergence(ref, mag, **CFG)) < 1e-4
+
+
+def test_full_size_properties_long_form(pkg, voc, basis):
+    """Config 5 shape (4800 frames): size-independent properties instead of a slow oracle run --
+    finite, right length, spectral convergence improves with iterations, first frames match the oracle
+    run on a prefix-independent quantity (the initial inverse, which is local)."""
+    T = 4800
+    x = synth_logmel(T, 99)
+    phase = seeded_phase(7, T)
+    xc = x.cuda()
+    mag = ogl.inverse_mel(x.numpy(), basis)
+    sc = []
+    for n_iter in (0, 4, 32):
+        y = voc.synthesize_batch([xc], init_phase=[phase], n_iter=n_iter)[0]
+        assert y.shape == ((T - 1) * 300,) and torch.isfinite(y).all()
+        m = voc.gl_transform.transform(y[None])[0][0].cpu().numpy()
+        sc.append(np.linalg.norm(m - mag) / np.linalg.norm(mag))
+        if n_iter == 0:
+            ref0 = ogl.istft(mag[:, :40], phase[:, :40], **CFG)
+            # samples covered only by frames < 37 are identical to the 40-frame problem's
+            assert ogl.rel_l2(y[:9000].cpu().numpy(), ref0[:9000]) < 5e-6
+    assert sc[0] > sc[1] > sc[2]
+
+
+def test_half_precision_io(pkg, voc):
+    x = synth_logmel(20, 3).cuda()
+    voc.gl_transform.n_iter = 2
+    np.random.seed(1)
+    y32 = voc(x)
+    np.random.seed(1)
+    y16 = voc(x.half())
+    voc.gl_transform.n_iter = 64
+    assert y16.dtype == torch.float16 and y16.shape == y32.shape
+    assert torch.isfinite(y16).all()
+
+
+def test_cpu_tensor_in_gives_cpu_tensor_out(pkg, voc):
+    x = synth_logmel(12, 4)
+    voc.gl_transform.n_iter = 1
+    np.random.seed(2)
+    y = voc(x)
+    voc.gl_transform.n_iter = 64
+    assert y.device.type == "cpu" and y.shape == (3300,)
+
+
+def test_short_utterance_raises(pkg, voc):
+    with pytest.raises(RuntimeError, match="Padding size"):
+        voc(synth_logmel(4, 1).cuda())
+    with pytest.raises(AssertionError):
+        voc(torch.zeros(10, 79).cuda())
+
+
+def test_griffin_lim_module_forward_on_magnitudes(pkg, voc, basis):
+    """GriffinLim.forward on a full 1025-bin magnitude (no zero tail): exercises kb = 1025 incl. Nyquist."""
+    rng = np.random.RandomState(5)
+    T = 12
+    mag = np.abs(rng.randn(1025, T)).astype(np.float32) + 0.1
+    gl = voc.gl_transform
+    gl.n_iter = 3
+    np.random.seed(9)
+    y = gl(torch.from_numpy(mag).cuda()).cpu().numpy()
+    gl.n_iter = 64
+    ref = ogl.griffin_lim(mag, seeded_phase(9, T), 3, **CFG)
+    assert ogl.rel_l2(y, ref) < 1e-4

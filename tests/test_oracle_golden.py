@@ -1,0 +1,118 @@
+"""The oracle (oracle/, numpy restatement) against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py, run in the build container).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, seeded_phase
+from oracle import frontend as fe
+from oracle import griffin_lim as gl
+from oracle import mel as omel
+
+CFG = dict(n_fft=2048, win_length=1200, hop_length=300)
+
+
+def test_slaney_mel_matches_reference(golden_basis):
+    mel, _ = golden_basis
+    mine = omel.slaney_mel_filters(24000, 2048, 80, 20, 8000)
+    assert (mine != 0).sum() == (mel != 0).sum() == 1334
+    assert np.abs(mine - mel).max() <= 2.4e-7
+
+
+def test_pinv_basis_matches_reference(golden_basis):
+    _, pinv = golden_basis
+    mine = gl.pinv_mel_basis(24000, 2048, 80, 20, 8000)
+    assert np.all(mine[683:] == 0) and np.all(pinv[683:] == 0)  # f_max = 8 kHz -> bins >= 683 are exactly zero
+    assert gl.rel_l2(mine, pinv) < 5e-5
+
+
+def test_window_sum_square_matches_reference():
+    w = load_golden("wss.npz")
+    for k in w.files:
+        mine = gl.window_sum_square(int(k[1:]), 300, 1200, 2048)
+        assert mine.shape == w[k].shape
+        assert np.abs(mine - w[k]).max() < 1e-6
+
+
+def test_stft_istft_match_reference():
+    g = load_golden("gl_small.npz")
+    mag, ph = gl.stft(g["stft_in"], **CFG)
+    assert mag.shape == g["stft_mag"].shape
+    assert gl.rel_l2(mag, g["stft_mag"]) < 2e-6
+    d = np.angle(np.exp(1j * (ph.astype(np.float64) - g["stft_phase"])))
+    assert np.sqrt((g["stft_mag"] * d ** 2).sum() / g["stft_mag"].sum()) < 1e-5
+    back = gl.istft(g["stft_mag"], g["stft_phase"], **CFG)
+    assert back.shape == g["istft_out"].shape
+    assert gl.rel_l2(back, g["istft_out"]) < 5e-6
+
+
+@pytest.mark.parametrize("case", ["c0", "c1", "c2", "c3"])
+def test_griffin_lim_matches_reference(case, golden_basis):
+    """Waveform rel-L2 <= 1e-3 and spectral convergence within 1e-4 (BASELINE.json tolerances)."""
+    _, pinv = golden_basis
+    g = load_golden("gl_small.npz")
+    x, n_iter, seed = g[case + "_logmel"], int(g[case + "_n_iter"]), int(g[case + "_seed"])
+    T = x.shape[0]
+    phase = seeded_phase(seed, T)
+    for basis in (pinv, gl.pinv_mel_basis(24000, 2048, 80, 20, 8000)):
+        y = gl.vocoder_forward(x, phase, n_iter, basis=basis)
+        assert y.shape == g[case + "_wave"].shape == ((T - 1) * 300,)
+        assert gl.rel_l2(y, g[case + "_wave"]) < 1e-3
+        sc = gl.spectral_convergence(y, gl.inverse_mel(x, basis), **CFG)
+        assert abs(sc - float(g[case + "_sc"])) < 1e-4
+
+
+def test_batched_forward_phase_layout(golden_basis):
+    """[B,T,80] input draws ONE [B,1025,T] phase tensor from the global RNG (vocoder.py:103)."""
+    _, pinv = golden_basis
+    g = load_golden("gl_batched.npz")
+    x = g["logmel"]
+    np.random.seed(int(g["seed"]))
+    ph = np.angle(np.exp(2j * np.pi * np.random.rand(2, 1025, x.shape[1]))).astype(np.float32)
+    for b in range(2):
+        y = gl.vocoder_forward(x[b], ph[b], int(g["n_iter"]), basis=pinv)
+        assert gl.rel_l2(y, g["wave"][b]) < 1e-3
+
+
+def test_short_input_raises_like_reference():
+    with pytest.raises(RuntimeError):
+        gl.stft(np.zeros(900, np.float32), **CFG)  # T=4 -> L=900 <= 1024
+
+
+def test_logmel_matches_reference():
+    l = load_golden("logmel.npz")
+    for i in range(3):
+        f = fe.logmel_spectrogram(l["wave%d" % i])
+        r = l["feat%d" % i]
+        assert f.shape == r.shape == (1 + len(l["wave%d" % i]) // 300, 80)
+        assert gl.rel_l2(f, r) < 1e-5
+        assert np.abs(f - r).max() < 1e-4  # the reference's own fp32 conv noise is ~1.5e-5 abs here
+
+
+def test_fbank_matches_reference():
+    """torchaudio's own fp32-vs-fp64 self-noise on these inputs is up to 5.5e-4 abs, so the
+    1e-5 criterion is applied as relative L2 over the feature matrix, plus a loose elementwise bound."""
+    fb = load_golden("fbank.npz")
+    for i in range(4):
+        f = fe.kaldi_fbank(fb["wave%d" % i], int(fb["sr%d" % i]))
+        r = fb["feat%d" % i]
+        assert f.shape == r.shape
+        assert gl.rel_l2(f, r) < 1e-5
+        assert np.abs(f - r).max() < 2e-3
+    assert fe.kaldi_fbank(np.zeros(399, np.float32), 16000).shape == (0, 80)  # shorter than one window
+
+
+def test_cmvn_matches_reference_bit_exact():
+    c = load_golden("cmvn.npz")
+    y = fe.global_cmvn(c["x"], c["mean"], c["std"])
+    for name in ("global_cmvn", "src_global_cmvn", "tgt_global_cmvn"):
+        assert y.dtype == c[name].dtype and np.array_equal(y, c[name])
+    assert np.array_equal(fe.gcmvn_denormalize(c["global_cmvn"], c["mean"], c["std"]), c["denorm"])
+
+
+def test_cmvn_stats_roundtrip():
+    rng = np.random.RandomState(0)
+    feats = [rng.randn(n, 80).astype(np.float32) * 3 + 1 for n in (50, 70, 31)]
+    st = fe.global_cmvn_stats(feats)
+    allf = np.concatenate(feats)
+    assert np.allclose(st["mean"], allf.mean(0), atol=1e-4)
+    assert np.allclose(st["std"], allf.std(0), atol=1e-3)
