@@ -151,9 +151,12 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                     const int k = 32 * r + lane;
                     if (32 * r < p.kb && k < p.kb) {
                         const float m = __ldg(magrow + k);
-                        float sn, cs;
+                        float sn, cs, rs, rc;
                         sincosf(__ldg(phrow + k), &sn, &cs);
-                        a[r] = make_float2(m * cs, m * sn);
+                        // the caller's phase refers to the un-rotated frame; frames are processed rotated
+                        // by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048)
+                        sincospif((float)((k * p.rot) & 2047) * (1.0f / 1024.0f), &rs, &rc);
+                        a[r] = make_float2(m * fmaf(cs, rc, -sn * rs), m * fmaf(cs, rs, sn * rc));
                     } else {
                         a[r] = make_float2(0.0f, 0.0f);
                     }
