@@ -310,8 +310,8 @@ int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int
         set_error("bad argument");
         return S2ST_EINVAL;
     }
-    // build_tiles + [inverse_mel] + (n_iter + 1) passes + resolve
-    *launches_out = 1 + (from_logmel ? 1 : 0) + (n_iter + 1) + 1;
+    // build_tiles + [inverse_mel] + (n_iter + 1) passes (plus one cudaMemsetAsync, not a kernel of ours)
+    *launches_out = 1 + (from_logmel ? 1 : 0) + (n_iter + 1);
     return S2ST_OK;
 }
 

@@ -48,10 +48,9 @@ struct GlParams {
     // data
     const float* mag;        // [total_frames, mag_stride]
     const float* phase;      // [total_frames, phase_stride] (first pass only)
-    const float* in0;        // parity buffers written by the previous pass
-    const float* in1;
-    float* out0;             // parity buffers written by this pass
-    float* out1;
+    const float* in;         // normalised waveforms written by the previous pass
+    float* out;              // waveforms written by this pass (seams pre-zeroed)
+    float* zero_next;        // buffer the NEXT pass writes: this pass zeroes its seams
 };
 
 struct s2st_error_state;

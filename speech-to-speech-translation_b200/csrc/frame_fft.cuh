@@ -42,17 +42,19 @@ __device__ __forceinline__ void warp_transpose(float2 (&a)[32], float2* scratch,
     __syncwarp();
 }
 
-// Forward.  In: a[n2] for n2 < NZ (others ignored).  Out: a[k1] = 2*X[32*k1+lane] for 32*k1 < kb
-// (the other registers are left undefined), nyq = 2*X[1024]
-// (valid in lane 0).  tw[r*32 + lane] = exp(-2*pi*i*r*lane/1024), vtab[k] = -i*exp(-2*pi*i*k/2048).
+// Forward, first half: in-lane FFT over n2, twiddle, transpose.  In: a[n2] for n2 < NZ (others ignored).
 template <int NZ>
-__device__ __forceinline__ void frame_fwd(float2 (&a)[32], float& nyq, float2* scratch,
-                                          const float2* __restrict__ tw,
-                                          const float2* __restrict__ vtab, int lane, int kb = 1024) {
+__device__ __forceinline__ void frame_fwd_a(float2 (&a)[32], float2* scratch, const float2* __restrict__ tw, int lane) {
     fft32<NZ, false>(a);
 #pragma unroll
     for (int r = 1; r < 32; ++r) a[r] = cmul(a[r], tw[r * 32 + lane]);
     warp_transpose(a, scratch, lane);
+}
+
+// Forward, second half.  Out: a[k1] = 2*X[32*k1+lane] for 32*k1 < kb (the other registers are left
+// undefined), nyq = 2*X[1024] (valid in lane 0).  vtab[k] = -i*exp(-2*pi*i*k/2048).
+__device__ __forceinline__ void frame_fwd_b(float2 (&a)[32], float& nyq, float2* scratch,
+                                            const float2* __restrict__ vtab, int lane, int kb) {
     fft32<32, false>(a);
     // pair exchange: Zs[k] = Z[k], Zs[1024] = Z[0]
 #pragma unroll
@@ -71,6 +73,15 @@ __device__ __forceinline__ void frame_fwd(float2 (&a)[32], float& nyq, float2* s
         a[r] = make_float2(fmaf(v.x, dx, fmaf(-v.y, dy, sx)), fmaf(v.x, dy, fmaf(v.y, dx, sy)));
     }
     __syncwarp();
+}
+
+// Forward = both halves.  tw[r*32 + lane] = exp(-2*pi*i*r*lane/1024).
+template <int NZ>
+__device__ __forceinline__ void frame_fwd(float2 (&a)[32], float& nyq, float2* scratch,
+                                          const float2* __restrict__ tw,
+                                          const float2* __restrict__ vtab, int lane, int kb = 1024) {
+    frame_fwd_a<NZ>(a, scratch, tw, lane);
+    frame_fwd_b(a, nyq, scratch, vtab, lane, kb);
 }
 
 // Inverse.  In: a[k1] = Y[32*k1+lane] (Hermitian half-spectrum, imag of DC ignored), ynyq = Y[1024]

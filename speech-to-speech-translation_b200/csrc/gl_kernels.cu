@@ -4,15 +4,18 @@
 // (fairseq/models/text_to_speech/vocoder.py:84-110, fairseq/data/audio/audio_utils.py:259-271):
 // the reference runs each STFT / ISTFT as a dense 2050x2048 convolution plus a host-side Python
 // loop for the window-sum-square; here one persistent kernel launch per Griffin-Lim iteration does
-//   stage-in (resolve seams, 1/wss, reflect) -> window -> rFFT-2048 -> magnitude re-imposition
-//   -> irFFT-2048 -> window -> overlap-add in shared memory -> write partial sums
+//   frame load (reflect) -> window -> rFFT-2048 -> magnitude re-imposition -> irFFT-2048 -> window
+//   -> overlap-add in shared memory -> 1/window-sum-square -> store
 // for a ragged batch of utterances.  The only state between iterations is the waveform.
 //
 // Tiling: a tile = 8 consecutive frames of one utterance = one CTA pass (8 warps, one frame per
-// warp).  A tile writes the un-normalised overlap-add of ITS frames over its whole span into the
-// parity buffer (tile index & 1): spans of same-parity tiles never overlap, so plain stores
-// suffice and the result is deterministic.  The next pass adds the (at most two) partial sums that
-// cover a sample and divides by the window-sum-square while staging its input.
+// warp).  A tile owns the samples only its frames touch and stores them normalised with plain
+// stores.  The "seam" samples it shares with the next / previous tile receive exactly two
+// contributions; both are added with red.global.add onto a zeroed location, so the result is the
+// same whichever lands first (a + b == b + a) and the output stays bitwise deterministic.  Three
+// waveform buffers rotate: pass i reads buf[(i-1)%3], writes buf[i%3] and zeroes the seams of
+// buf[(i+1)%3] for the next pass.  Readers therefore see a finished, normalised waveform and a
+// frame load is 19 independent 8-byte loads per lane.
 #include <math_constants.h>
 
 #include "../../include/s2st_b200.h"
@@ -24,34 +27,17 @@ namespace s2st {
 namespace {
 
 constexpr float kTiny = 1.1754944e-38f;  // vocoder.py:69
+constexpr int kMagRegs = 22;             // magnitude rows prefetched into registers (covers kb <= 704)
 
-__device__ __forceinline__ int reflect_index(int j, int L) {
-    // F.pad(mode='reflect'): no repeat of the edge sample (audio_utils.py:262-263)
-    if (j < 0) j = -j;
-    if (j >= L) j = 2 * (L - 1) - j;
-    return j;
-}
-
-// Value of the normalised waveform at output sample j (0 <= j < L) from the two parity buffers.
-__device__ __forceinline__ float resolve_sample(const GlParams& p, const float* __restrict__ b0,
-                                                const float* __restrict__ b1, long long woff,
-                                                int j, int T, const float* __restrict__ inv_wss) {
-    const int q = j + p.half - p.rot;  // position relative to frame 0's first kept sample, > 0
-    const int t_hi_u = q / p.hop;
-    const int t_hi = min(t_hi_u, T - 1);
-    const int t_lo = (q < p.ws) ? 0 : (q - p.ws) / p.hop + 1;
-    const int k_lo = t_lo / kTileFrames, k_hi = t_hi / kTileFrames;
-    float v = ((k_lo & 1) ? b1 : b0)[woff + j];
-    if (k_hi != k_lo) v += ((k_hi & 1) ? b1 : b0)[woff + j];
-    float inv;
-    if (q + p.hop >= p.ws && t_hi_u <= T - 1) {
-        inv = inv_wss[q - t_hi_u * p.hop];
-    } else {
-        float acc = 0.0f;  // frame order, like get_window_sum_square (vocoder.py:78-81)
-        for (int t = t_lo; t <= t_hi; ++t) acc += __ldg(p.w2 + (q - t * p.hop));
-        inv = acc > kTiny ? 1.0f / acc : 1.0f;
-    }
-    return v * inv;
+// two consecutive samples of the reflect-padded waveform (audio_utils.py:262-263), j even
+__device__ __forceinline__ float2 load_pair(const float* __restrict__ y, int j, int L, bool vec_ok) {
+    if (vec_ok && j >= 0 && j + 1 < L) return *reinterpret_cast<const float2*>(y + j);
+    int j0 = j < 0 ? -j : j, j1 = j + 1 < 0 ? -(j + 1) : j + 1;
+    j0 = j0 >= L ? 2 * (L - 1) - j0 : j0;
+    j1 = j1 >= L ? 2 * (L - 1) - j1 : j1;
+    j0 = min(max(j0, 0), L - 1);  // only reachable where the window is zero
+    j1 = min(max(j1, 0), L - 1);
+    return make_float2(y[j0], y[j1]);
 }
 
 // One Griffin-Lim pass.  FIRST: spectra come from (mag, initial phase) -> inverse only.
@@ -64,7 +50,7 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
     float* s_win_a = reinterpret_cast<float*>(s_scratch + kTileFrames * kScratchFloat2);
     float* s_win_s = s_win_a + 64 * NZ;
     float* s_inv_wss = s_win_s + 64 * NZ;                          // hop (rounded up to 4)
-    float* s_span = s_inv_wss + ((p.hop + 3) & ~3);                // (kTileFrames-1)*hop + wp
+    float* s_ola = s_inv_wss + ((p.hop + 3) & ~3);                 // (kTileFrames-1)*hop + ws
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += kGlThreads) {
@@ -79,56 +65,62 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
     float2* scratch = s_scratch + warp * kScratchFloat2;
     const int n_tiles = *p.n_tiles;
     const bool hop_even = (p.hop & 1) == 0;
+    // increments of (i / hop, i % hop) when i advances by the CTA size
+    const int step_q = kGlThreads / p.hop, step_r = kGlThreads % p.hop;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileDesc td = p.tiles[tile];
         const UttDesc ud = p.utts[td.utt];
         const int T = ud.n_frames, L = (T - 1) * p.hop;
-        const int span_pos = td.f0 * p.hop + p.rot;  // padded coordinate of s_span[0]
-        __syncthreads();  // tables loaded / previous tile's write-out finished
-        float2 a[32];
+        const int span_out = (td.nf - 1) * p.hop + p.ws;
+        const int j_base = td.f0 * p.hop + p.rot - p.half;  // output sample of s_ola[0]
         const bool active = warp < td.nf;
         const size_t row = (size_t)ud.frame_off + td.f0 + warp;
+        const float* magrow = p.mag + row * p.mag_stride;
+        float2 a[32];
 
+        // ---- issue this frame's global loads first: they fly while the overlap-add buffer is cleared
         if constexpr (!FIRST) {
-            const int span_in = (td.nf - 1) * p.hop + 64 * NZ;
-            for (int i = tid; i < span_in; i += kGlThreads) {
-                const int j = reflect_index(span_pos + i - p.half, L);
-                s_span[i] = resolve_sample(p, p.in0, p.in1, ud.wave_off, j, T, s_inv_wss);
-            }
-            __syncthreads();
             if (active) {
-                const float* src = s_span + warp * p.hop + 2 * lane;
-                const float* w = s_win_a + 2 * lane;
-                if (hop_even) {
+                const float* y = p.in + ud.wave_off;
+                const int j0 = j_base + warp * p.hop + 2 * lane;
+                const bool vec_ok = hop_even && ((ud.wave_off & 1) == 0);
 #pragma unroll
-                    for (int r = 0; r < NZ; ++r) {
-                        const float2 v = *reinterpret_cast<const float2*>(src + 64 * r);
-                        const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
-                        a[r] = make_float2(v.x * ww.x, v.y * ww.y);
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < NZ; ++r)
-                        a[r] = make_float2(src[64 * r] * w[64 * r], src[64 * r + 1] * w[64 * r + 1]);
-                }
+                for (int r = 0; r < NZ; ++r) a[r] = load_pair(y, j0 + 64 * r, L, vec_ok);
             }
-            __syncthreads();  // every frame is in registers; s_span becomes the overlap-add buffer
         }
-        const int span_out = (td.nf - 1) * p.hop + p.ws;
-        for (int i = tid; i < span_out; i += kGlThreads) s_span[i] = 0.0f;
+        __syncthreads();  // tables loaded / previous tile's write-out finished
+        for (int i = tid; i < span_out; i += kGlThreads) s_ola[i] = 0.0f;
 
         if (active) {
-            const float* magrow = p.mag + row * p.mag_stride;
             float ynyq = 0.0f;
             if constexpr (!FIRST) {
+                const float* w = s_win_a + 2 * lane;
+#pragma unroll
+                for (int r = 0; r < NZ; ++r) {
+                    const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
+                    a[r] = make_float2(a[r].x * ww.x, a[r].y * ww.y);
+                }
+                frame_fwd_a<NZ>(a, scratch, s_tw, lane);
+                // target magnitudes: prefetched here so the second in-lane FFT hides their latency
+                float mg[kMagRegs];
+                const bool pre = p.kb <= 32 * kMagRegs;
+                if (pre) {
+#pragma unroll
+                    for (int r = 0; r < kMagRegs; ++r) {
+                        const int k = 32 * r + lane;
+                        mg[r] = (k < p.kb) ? __ldg(magrow + k) : 0.0f;
+                    }
+                }
                 float nyq;
-                frame_fwd<NZ>(a, nyq, scratch, s_tw, s_vtab, lane, p.kb);
+                frame_fwd_b(a, nyq, scratch, s_vtab, lane, p.kb);
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                     if (32 * r < p.kb) {
                         const int k = 32 * r + lane;
-                        const float m = (k < p.kb) ? __ldg(magrow + k) : 0.0f;
+                        float m;
+                        if (r < kMagRegs && pre) m = mg[r < kMagRegs ? r : 0];
+                        else m = (k < p.kb) ? __ldg(magrow + k) : 0.0f;
                         float x = a[r].x, y = a[r].y;
                         float r2 = fmaf(x, x, y * y);
                         if (r2 < 1e-30f) {  // keep the phase of tiny (possibly denormal) bins
@@ -166,9 +158,10 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
             frame_inv(a, ynyq, scratch, s_tw, s_vtab, lane);
         }
         __syncthreads();  // zero-fill done
+        // overlap-add: frames of the same phase (w mod nphase) never overlap
         for (int c = 0; c < p.nphase; ++c) {
             if (active && (warp % p.nphase) == c) {
-                float* dst = s_span + warp * p.hop + 2 * lane;
+                float* dst = s_ola + warp * p.hop + 2 * lane;
                 const float* w = s_win_s + 2 * lane;
                 if (hop_even) {
 #pragma unroll
@@ -193,30 +186,43 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
             }
             __syncthreads();
         }
-        // write this tile's partial sums (kept samples only) to its parity buffer
-        float* outb = ((td.f0 / kTileFrames) & 1) ? p.out1 : p.out0;
-        for (int i = tid; i < span_out; i += kGlThreads) {
-            const int j = span_pos + i - p.half;
-            if (j >= 0 && j < L) outb[ud.wave_off + j] = s_span[i];
+        // ---- normalise and write.  Sample i of the tile sits at q = f0*hop + i from frame 0's origin,
+        // so q mod hop == i mod hop and the last frame that can cover it is f0 + i / hop.
+        {
+            float* out = p.out + ud.wave_off;
+            float* znext = p.zero_next + ud.wave_off;
+            const bool has_prev = td.f0 > 0, has_next = td.f0 + td.nf < T;
+            const int left_end = p.ws - p.hop;        // i < left_end  : also covered by the previous tile
+            const int right_beg = td.nf * p.hop;      // i >= right_beg: also covered by the next tile
+            int q = tid / p.hop, r = tid % p.hop;
+            for (int i = tid; i < span_out; i += kGlThreads) {
+                const int j = j_base + i;
+                if (j >= 0 && j < L) {
+                    const int t_hi_u = td.f0 + q;
+                    const int t_lo_u = i < p.ws ? td.f0 - (p.ws - 1 - i) / p.hop : td.f0 + (i - p.ws) / p.hop + 1;
+                    float inv;
+                    if (t_lo_u >= 0 && t_hi_u <= T - 1) {
+                        inv = s_inv_wss[r];
+                    } else {  // utterance edges: only the frames that exist (vocoder.py:78-81 order)
+                        float acc = 0.0f;
+                        const int qq = td.f0 * p.hop + i;
+                        for (int t = max(t_lo_u, 0); t <= min(t_hi_u, T - 1); ++t) acc += __ldg(p.w2 + (qq - t * p.hop));
+                        inv = acc > kTiny ? 1.0f / acc : 1.0f;
+                    }
+                    const float v = s_ola[i] * inv;
+                    const bool right_seam = has_next && i >= right_beg;
+                    if (right_seam || (has_prev && i < left_end)) atomicAdd(out + j, v);
+                    else out[j] = v;
+                    if (right_seam) znext[j] = 0.0f;
+                }
+                q += step_q;
+                r += step_r;
+                if (r >= p.hop) {
+                    r -= p.hop;
+                    ++q;
+                }
+            }
         }
-    }
-}
-
-// parity buffers -> normalised, trimmed waveforms (vocoder.py:95-99)
-__global__ void __launch_bounds__(256) k_gl_resolve(const __grid_constant__ GlParams p, int n_utts,
-                                                     long long total_samples, float* __restrict__ out) {
-    extern __shared__ float s_inv_wss[];
-    for (int i = threadIdx.x; i < p.hop; i += blockDim.x) s_inv_wss[i] = p.inv_wss[i];
-    __syncthreads();
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_samples;
-         g += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = n_utts - 1;  // last utterance with wave_off <= g
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (p.utts[mid].wave_off <= g) lo = mid; else hi = mid - 1;
-        }
-        const UttDesc ud = p.utts[lo];
-        out[g] = resolve_sample(p, p.in0, p.in1, ud.wave_off, (int)(g - ud.wave_off), ud.n_frames, s_inv_wss);
     }
 }
 
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict_
     if (tid == 0) *n_tiles = s_carry;
 }
 
-// mag[t, f] = max(0, sum_m inv_mel[f, m] * exp(logmel[t, m]))     (vocoder.py:42, 141)
+// mag[t, f] = max(0, sum_m inv_mel[f, m] * g(mel[t, m]))     (vocoder.py:42, 141)
 constexpr int kImFrames = 16;
 __global__ void __launch_bounds__(256) k_inverse_mel(const float* __restrict__ logmel, bool is_log, long long n_frames,
                                                       int n_mels, const float* __restrict__ inv_mel_t,
@@ -353,7 +359,7 @@ struct GlWorkspace {
     TileDesc* tiles;
     int* n_tiles;
     float* mag;
-    float* buf[4];
+    float* buf[2];
     size_t total;
     long long max_tiles;
     long long wave_samples;
@@ -376,7 +382,7 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
     w.tiles = reinterpret_cast<TileDesc*>(take(sizeof(TileDesc) * (size_t)w.max_tiles));
     w.n_tiles = reinterpret_cast<int*>(take(sizeof(int)));
     w.mag = reinterpret_cast<float*>(take(sizeof(float) * (size_t)total_frames * w.mag_stride));
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
         w.buf[i] = reinterpret_cast<float*>(take(sizeof(float) * (size_t)(w.wave_samples > 0 ? w.wave_samples : 1)));
     w.total = off;
     return w;
@@ -451,6 +457,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
         set_error("workspace too small: have %zu need %zu", workspace_bytes, w.total);
         return S2ST_EWORKSPACE;
     }
+    if (w.wave_samples <= 0) return S2ST_OK;  // every utterance has a single frame: nothing to write
     k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, w.utts, w.tiles, w.n_tiles);
     S2ST_CUDA_CHECK(cudaGetLastError());
 
@@ -485,12 +492,17 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     }
     const size_t smem = gl_pass_smem(plan);
     const int grid = (int)min((long long)plan->num_sms * 2, w.max_tiles);
-    int cur = 0;
+    // three rotating waveform buffers; the one the last pass writes is the caller's output
+    float* ring[3];
+    ring[n_iter % 3] = wave_out;
+    ring[(n_iter + 1) % 3] = w.buf[0];
+    ring[(n_iter + 2) % 3] = w.buf[1];
+    // pass 0 accumulates its seams into ring[0]: clear it (later passes get theirs cleared by the pass before)
+    S2ST_CUDA_CHECK(cudaMemsetAsync(ring[0], 0, sizeof(float) * (size_t)w.wave_samples, stream));
     for (int it = 0; it <= n_iter; ++it) {
-        p.in0 = w.buf[2 * cur];
-        p.in1 = w.buf[2 * cur + 1];
-        p.out0 = w.buf[2 * (cur ^ 1)];
-        p.out1 = w.buf[2 * (cur ^ 1) + 1];
+        p.in = ring[(it + 2) % 3];
+        p.out = ring[it % 3];
+        p.zero_next = ring[(it + 1) % 3];
         if (timed) {
             if (!plan->timing_events[it]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[it]));
             S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[it], stream));
@@ -498,19 +510,11 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
         int rc = (plan->nz == 19) ? launch_pass<19>(p, it == 0, grid, smem, stream)
                                   : launch_pass<32>(p, it == 0, grid, smem, stream);
         if (rc != S2ST_OK) return rc;
-        cur ^= 1;
     }
     if (timed) {
         if (!plan->timing_events[n_iter + 1]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[n_iter + 1]));
         S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[n_iter + 1], stream));
         plan->timing_recorded = n_iter + 2;
-    }
-    p.in0 = w.buf[2 * cur];
-    p.in1 = w.buf[2 * cur + 1];
-    if (w.wave_samples > 0) {
-        const int rgrid = (int)min((long long)plan->num_sms * 8, (w.wave_samples + 255) / 256);
-        k_gl_resolve<<<rgrid, 256, sizeof(float) * plan->hop, stream>>>(p, n_utts, w.wave_samples, wave_out);
-        S2ST_CUDA_CHECK(cudaGetLastError());
     }
     return S2ST_OK;
 }
