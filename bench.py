@@ -59,43 +59,62 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU through NVML from a thread of this process
+    (equivalent to the nvidia-smi --query-gpu clocks line, without a polling subprocess)."""
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, gpu_index, period_s=0.05):
+        import threading
+        self.samples, self.reasons, self.err = [], set(), None
+        self.sm_max = None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    phys = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            self.nv = None
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[4:8]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self._stop.set()
+        self.t.join(2)
+        sm = self.samples
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
+                "reasons": sorted(self.reasons), "source": "NVML, sampled in-process during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -211,24 +230,29 @@ def run_ours(args):
     # ---- device-resident timing (value) ----------------------------------------------------------
     for _ in range(args.warmup):
         voc.synthesize_flat(logmel_d, frames, phase_d)
-    plan.set_pass_timing(True)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pass_ms = []
     ev0.record()
     for _ in range(args.steps):
         wave_d = voc.synthesize_flat(logmel_d, frames, phase_d)
-        pass_ms.append(None)  # filled below, after the timed region (reading events synchronises)
     ev1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    # per-pass device times of the last timed step, recorded inside the timed region by the library
-    last_pass_ms = plan.pass_times_ms()
-    plan.set_pass_timing(False)
-    iter_ms = float(np.mean(last_pass_ms[1:])) if len(last_pass_ms) > 1 else float("nan")
     assert torch.isfinite(wave_d).all()
+    # per-launch device time of the fused iteration kernel: CUDA events recorded by the library on the
+    # launching stream around every pass, over the same steps again (kept out of `value`'s region so the
+    # extra event records cannot perturb it)
+    plan.set_pass_timing(True)
+    per_step = []
+    barrier()
+    for _ in range(args.steps):
+        voc.synthesize_flat(logmel_d, frames, phase_d)
+        per_step.append(plan.pass_times_ms())
+    plan.set_pass_timing(False)
+    last_pass_ms = np.mean(np.stack(per_step), axis=0)
+    iter_ms = float(np.mean(last_pass_ms[1:])) if len(last_pass_ms) > 1 else float("nan")
 
     # ---- end to end through the public API, host buffers in and out (e2e) -------------------------
     def e2e_step():
@@ -301,7 +325,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

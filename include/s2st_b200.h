@@ -62,6 +62,8 @@ int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Griffin-Lim ragged batch: GriffinLimVocoder.forward (vocoder.py:136-144) for B utterances at once.
+ *   frame_offsets_host  optional host copy of frame_offsets (NULL allowed): lets the library size its
+ *                   work decomposition exactly instead of from the average utterance length
  *   logmel_dev      [total_frames, n_mels]  denormalised log-mel, or NULL when mag_dev is given
  *   mag_dev         [total_frames, n_fft/2+1] linear magnitudes (GriffinLim.forward input,
  *                   vocoder.py:102, transposed to frame-major), or NULL when logmel_dev is given
@@ -74,7 +76,8 @@ int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
  * reference's reflect padding raises otherwise) -- checked by the host shim, not here. */
 int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_frames, size_t* bytes_out);
 int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
-                       const int32_t* frame_offsets_dev, const float* logmel_dev,
+                       const int32_t* frame_offsets_dev, const int32_t* frame_offsets_host,
+                       const float* logmel_dev,
                        const float* mag_dev, const float* init_phase_dev, int n_iter,
                        float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream);

@@ -145,7 +145,7 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
     p->ws = ((hi - rot + 1) + 1) & ~1;
     if (p->ws > p->wp) p->ws = p->wp;
     const int overlap = (p->ws + hop_length - 1) / hop_length;
-    p->nphase = overlap < kTileFrames ? overlap : kTileFrames;
+    p->nphase = overlap;
 
     std::vector<float> win_a(p->wp), win_s(p->wp), w2(p->ws), inv_wss(hop_length);
     for (int m = 0; m < p->wp; ++m) {
@@ -271,9 +271,9 @@ int s2st_plan_get_pass_times(s2st_plan* plan, float* ms_out_host, int capacity, 
 }
 
 static int check_gl_geometry(const s2st_plan* plan) {
-    if (plan->ws > kTileFrames * plan->hop) {
+    if (plan->nphase > 64) {
         set_error("window support %d exceeds %d hops of %d samples: overlap factor not supported", plan->ws,
-                  kTileFrames, plan->hop);
+                  64, plan->hop);
         return S2ST_EINVAL;
     }
     return S2ST_OK;
@@ -289,7 +289,7 @@ int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_fra
 }
 
 int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
-                       const int32_t* frame_offsets_dev, const float* logmel_dev,
+                       const int32_t* frame_offsets_dev, const int32_t* frame_offsets_host, const float* logmel_dev,
                        const float* mag_dev, const float* init_phase_dev, int n_iter,
                        float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream) {
@@ -300,7 +300,7 @@ int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
     }
     int rc = check_gl_geometry(plan);
     if (rc != S2ST_OK) return rc;
-    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, logmel_dev, mag_dev, kBins,
+    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, frame_offsets_host, logmel_dev, mag_dev, kBins,
                   init_phase_dev, n_iter, wave_out_dev, workspace_dev, workspace_bytes,
                   static_cast<cudaStream_t>(stream));
 }
@@ -354,7 +354,7 @@ int s2st_istft(const s2st_plan* plan, int n_utts, int64_t total_frames, const in
     }
     int rc = check_gl_geometry(plan);
     if (rc != S2ST_OK) return rc;
-    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, nullptr, mag_dev, kBins, phase_dev, 0,
+    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, nullptr, nullptr, mag_dev, kBins, phase_dev, 0,
                   wave_out_dev, workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

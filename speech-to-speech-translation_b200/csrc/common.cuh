@@ -7,8 +7,8 @@ namespace s2st {
 
 constexpr int kNfft = 2048;
 constexpr int kBins = kNfft / 2 + 1;  // 1025
-constexpr int kTileFrames = 8;        // frames per tile == warps per CTA of the GL kernel
-constexpr int kGlThreads = 32 * kTileFrames;
+constexpr int kMinStrip = 4;          // shortest strip (frames a warp runs in sequence); must cover the overlap
+constexpr int kGlThreads = 256;       // 8 warps per CTA, 2 CTAs per SM
 
 struct UttDesc {
     long long wave_off;  // first sample of this utterance in the concatenated waveform buffers
@@ -18,8 +18,8 @@ struct UttDesc {
 
 struct TileDesc {
     int utt;  // utterance index
-    int f0;   // first frame (utterance-local) of the tile; tile index within the utterance = f0 / kTileFrames
-    int nf;   // frames in the tile (1..kTileFrames)
+    int f0;   // first frame (utterance-local) of the strip
+    int nf;   // frames in the strip (1..S)
     int pad;
 };
 
@@ -31,7 +31,7 @@ struct GlParams {
     int rot;       // s: first frame sample kept (even); frames are processed circularly rotated by s
     int ws;        // even upper bound of the window support in rotated coordinates (<= wp)
     int wp;        // 64 * NZ: samples each lane-register layout covers
-    int nphase;    // overlap-add phases = min(ceil(ws / hop), kTileFrames)
+    int nphase;    // frames overlapping one sample = ceil(ws / hop)
     int kb;        // bins >= kb have zero target magnitude
     int mag_stride, phase_stride;
     // constants (device global memory, owned by the plan)

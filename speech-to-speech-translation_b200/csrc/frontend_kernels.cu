@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float2* s_vtab = s_tw + 1024;
-    float2* s_scratch = s_vtab + 1024;
-    float* s_win = reinterpret_cast<float*>(s_scratch + 8 * kScratchFloat2);
+    float* s_scratch = reinterpret_cast<float*>(s_vtab + 1024);
+    float* s_win = s_scratch + 8 * kScratchFloats;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += blockDim.x) {
         s_tw[i] = p.tw[i];
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
     }
     for (int i = tid; i < 64 * NZ; i += blockDim.x) s_win[i] = p.win_a[i];
     __syncthreads();
-    float2* scratch = s_scratch + warp * kScratchFloat2;
+    float* scratch = s_scratch + warp * kScratchFloats;
 
     for (long long f = (long long)blockIdx.x * 8 + warp; f < p.total_frames; f += (long long)gridDim.x * 8) {
         const int u = find_utt(p.frame_offsets, p.n_utts, f);
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
                 if (p.phase_out) p.phase_out[f * kBins + 1024] = atan2f(0.0f, nyq)  /* exp(-i pi rot) = 1, rot is even */;
             }
         } else {
-            float* spec = reinterpret_cast<float*>(scratch);
+            float* spec = scratch;  // 1025 floats fit in the warp scratch
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const float x = 0.5f * a[r].x, y = 0.5f * a[r].y;
@@ -327,7 +327,7 @@ int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const
     p.mel_ptr = plan->mel_ptr;
     p.mel_idx = plan->mel_idx;
     p.mel_val = plan->mel_val;
-    const size_t smem = sizeof(float2) * (2048 + 8 * kScratchFloat2) + sizeof(float) * plan->wp;
+    const size_t smem = sizeof(float2) * 2048 + sizeof(float) * (8 * kScratchFloats + plan->wp);
     const int grid = (int)min((long long)plan->num_sms * 2, (total_frames + 7) / 8);
 #define S2ST_LAUNCH_STFT(NZV, MODEV)                                                                          \
     do {                                                                                                      \

@@ -5,17 +5,20 @@
 // the reference runs each STFT / ISTFT as a dense 2050x2048 convolution plus a host-side Python
 // loop for the window-sum-square; here one persistent kernel launch per Griffin-Lim iteration does
 //   frame load (reflect) -> window -> rFFT-2048 -> magnitude re-imposition -> irFFT-2048 -> window
-//   -> overlap-add in shared memory -> 1/window-sum-square -> store
+//   -> overlap-add -> 1/window-sum-square -> store
 // for a ragged batch of utterances.  The only state between iterations is the waveform.
 //
-// Tiling: a tile = 8 consecutive frames of one utterance = one CTA pass (8 warps, one frame per
-// warp).  A tile owns the samples only its frames touch and stores them normalised with plain
-// stores.  The "seam" samples it shares with the next / previous tile receive exactly two
-// contributions; both are added with red.global.add onto a zeroed location, so the result is the
-// same whichever lands first (a + b == b + a) and the output stays bitwise deterministic.  Three
-// waveform buffers rotate: pass i reads buf[(i-1)%3], writes buf[i%3] and zeroes the seams of
-// buf[(i+1)%3] for the next pass.  Readers therefore see a finished, normalised waveform and a
-// frame load is 19 independent 8-byte loads per lane.
+// Work decomposition: a STRIP = S consecutive frames of one utterance, owned by ONE warp, which runs
+// them in order.  The warp keeps the overlap-add of its frames in a private shared-memory ring of
+// `ws` samples: once frame f has been added, hop f of the strip is final (later frames start after
+// it), so it is normalised and written out immediately and its ring slots are cleared for reuse.
+// Warps never synchronise with each other: there is no __syncthreads in the main loop.
+//
+// Only the first / last (ws - hop) samples of a strip are shared with the neighbouring strip.  Such
+// "seam" samples receive exactly two contributions, both added with red.global.add onto a zeroed
+// location, so the result does not depend on arrival order (a + b == b + a) and the output stays
+// bitwise deterministic.  Three waveform buffers rotate: pass i reads buf[(i-1)%3], writes buf[i%3]
+// and zeroes the seams of buf[(i+1)%3] for the next pass.
 #include <math_constants.h>
 
 #include "../../include/s2st_b200.h"
@@ -27,7 +30,7 @@ namespace s2st {
 namespace {
 
 constexpr float kTiny = 1.1754944e-38f;  // vocoder.py:69
-constexpr int kMagRegs = 22;             // magnitude rows prefetched into registers (covers kb <= 704)
+constexpr int kGlWarps = kGlThreads / 32;
 
 // two consecutive samples of the reflect-padded waveform (audio_utils.py:262-263), j even
 __device__ __forceinline__ float2 load_pair(const float* __restrict__ y, int j, int L, bool vec_ok) {
@@ -40,19 +43,68 @@ __device__ __forceinline__ float2 load_pair(const float* __restrict__ y, int j, 
     return make_float2(y[j0], y[j1]);
 }
 
+struct StripCtx {
+    int f0, nf, T, L, j_base;
+    bool has_prev, has_next;
+    float* out;
+    float* znext;
+};
+
+// Normalise and write samples [i0, i0 + n) of the strip (strip-relative index i), reading and clearing
+// the ring from slot `slot0`.  r0 = i0 mod hop.
+__device__ __forceinline__ void emit(const GlParams& p, const StripCtx& c, float* ring, const float* s_inv_wss,
+                                     int i0, int n, int slot0, int r0, int lane) {
+    const int left_end = p.ws - p.hop;     // i < left_end : the previous strip's frames cover it too
+    const int right_beg = c.nf * p.hop;    // i >= right_beg: the next strip's frames cover it too
+    for (int e = lane; e < n; e += 32) {
+        int slot = slot0 + e;
+        if (slot >= p.ws) slot -= p.ws;
+        const float acc = ring[slot];
+        ring[slot] = 0.0f;
+        const int i = i0 + e;
+        const int j = c.j_base + i;
+        if (j < 0 || j >= c.L) continue;
+        const bool in_left = i < left_end, in_right = i >= right_beg;
+        float inv;
+        // clipped at the utterance start (strip 0 only) or end (a frame index >= T would cover the sample)
+        if ((in_left && !c.has_prev) || i >= (c.T - c.f0) * p.hop) {
+            // utterance edges: only the frames that exist contribute (vocoder.py:78-81, frame order)
+            const int t_lo = i < p.ws ? c.f0 - (p.ws - 1 - i) / p.hop : c.f0 + (i - p.ws) / p.hop + 1;
+            const int t_hi = c.f0 + i / p.hop;
+            const int qq = c.f0 * p.hop + i;
+            float w = 0.0f;
+            for (int t = max(t_lo, 0); t <= min(t_hi, c.T - 1); ++t) w += __ldg(p.w2 + (qq - t * p.hop));
+            inv = w > kTiny ? 1.0f / w : 1.0f;
+        } else {
+            int r = r0 + e;
+            while (r >= p.hop) r -= p.hop;
+            inv = s_inv_wss[r];
+        }
+        const float v = acc * inv;
+        const bool right_seam = in_right && c.has_next;
+        if (right_seam || (in_left && c.has_prev)) atomicAdd(c.out + j, v);
+        else c.out[j] = v;
+        if (right_seam) c.znext[j] = 0.0f;
+    }
+}
+
 // One Griffin-Lim pass.  FIRST: spectra come from (mag, initial phase) -> inverse only.
-template <int NZ, bool FIRST>
+// PRUNED: every live bin is below 704 (kb <= 704): magnitudes are prefetched into registers and the
+// pair exchanges move 22 rows instead of 32.
+template <int NZ, bool FIRST, bool PRUNED>
 __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant__ GlParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);            // 1024
     float2* s_vtab = s_tw + 1024;                                  // 1024
-    float2* s_scratch = s_vtab + 1024;                             // 8 * kScratchFloat2
-    float* s_win_a = reinterpret_cast<float*>(s_scratch + kTileFrames * kScratchFloat2);
+    float* s_win_a = reinterpret_cast<float*>(s_vtab + 1024);
     float* s_win_s = s_win_a + 64 * NZ;
     float* s_inv_wss = s_win_s + 64 * NZ;                          // hop (rounded up to 4)
-    float* s_ola = s_inv_wss + ((p.hop + 3) & ~3);                 // (kTileFrames-1)*hop + ws
+    float* s_warp = s_inv_wss + ((p.hop + 3) & ~3);                // per warp: scratch + ring
+    const int ring_floats = (p.ws + 3) & ~3;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* scratch = s_warp + warp * (kScratchFloats + ring_floats);
+    float* ring = scratch + kScratchFloats;
     for (int i = tid; i < 1024; i += kGlThreads) {
         s_tw[i] = p.tw[i];
         s_vtab[i] = p.vtab[i];
@@ -62,37 +114,39 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
         s_win_s[i] = p.win_s[i];
     }
     for (int i = tid; i < p.hop; i += kGlThreads) s_inv_wss[i] = p.inv_wss[i];
-    float2* scratch = s_scratch + warp * kScratchFloat2;
-    const int n_tiles = *p.n_tiles;
+    for (int i = lane; i < ring_floats; i += 32) ring[i] = 0.0f;
+    __syncthreads();  // the only block-wide barrier: constant tables are in place
+
+    const int n_strips = *p.n_tiles;
     const bool hop_even = (p.hop & 1) == 0;
-    // increments of (i / hop, i % hop) when i advances by the CTA size
-    const int step_q = kGlThreads / p.hop, step_r = kGlThreads % p.hop;
+    const int kb = PRUNED ? min(p.kb, 32 * kPrunedRows) : p.kb;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileDesc td = p.tiles[tile];
+    for (int strip = blockIdx.x * kGlWarps + warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
+        const TileDesc td = p.tiles[strip];
         const UttDesc ud = p.utts[td.utt];
-        const int T = ud.n_frames, L = (T - 1) * p.hop;
-        const int span_out = (td.nf - 1) * p.hop + p.ws;
-        const int j_base = td.f0 * p.hop + p.rot - p.half;  // output sample of s_ola[0]
-        const bool active = warp < td.nf;
-        const size_t row = (size_t)ud.frame_off + td.f0 + warp;
-        const float* magrow = p.mag + row * p.mag_stride;
+        StripCtx c;
+        c.f0 = td.f0;
+        c.nf = td.nf;
+        c.T = ud.n_frames;
+        c.L = (c.T - 1) * p.hop;
+        c.j_base = td.f0 * p.hop + p.rot - p.half;  // output sample index of strip-relative sample 0
+        c.has_prev = td.f0 > 0;
+        c.has_next = td.f0 + td.nf < c.T;
+        c.out = p.out + ud.wave_off;
+        c.znext = p.zero_next + ud.wave_off;
+        const float* y = p.in + ud.wave_off;
+        const bool vec_ok = hop_even && ((ud.wave_off & 1) == 0);
+        const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0) * p.mag_stride;
+        const float* phrow = FIRST ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
+
         float2 a[32];
-
-        // ---- issue this frame's global loads first: they fly while the overlap-add buffer is cleared
         if constexpr (!FIRST) {
-            if (active) {
-                const float* y = p.in + ud.wave_off;
-                const int j0 = j_base + warp * p.hop + 2 * lane;
-                const bool vec_ok = hop_even && ((ud.wave_off & 1) == 0);
+            const int j0 = c.j_base + 2 * lane;
 #pragma unroll
-                for (int r = 0; r < NZ; ++r) a[r] = load_pair(y, j0 + 64 * r, L, vec_ok);
-            }
+            for (int r = 0; r < NZ; ++r) a[r] = load_pair(y, j0 + 64 * r, c.L, vec_ok);
         }
-        __syncthreads();  // tables loaded / previous tile's write-out finished
-        for (int i = tid; i < span_out; i += kGlThreads) s_ola[i] = 0.0f;
-
-        if (active) {
+        int slot0 = 0;  // ring slot of strip-relative sample f * hop
+        for (int f = 0; f < td.nf; ++f, magrow += p.mag_stride) {
             float ynyq = 0.0f;
             if constexpr (!FIRST) {
                 const float* w = s_win_a + 2 * lane;
@@ -102,46 +156,40 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                     a[r] = make_float2(a[r].x * ww.x, a[r].y * ww.y);
                 }
                 frame_fwd_a<NZ>(a, scratch, s_tw, lane);
-                // target magnitudes: prefetched here so the second in-lane FFT hides their latency
-                float mg[kMagRegs];
-                const bool pre = p.kb <= 32 * kMagRegs;
-                if (pre) {
+                // target magnitudes: requested here so the second in-lane FFT hides their latency
+                float mg[kPrunedRows];
+                if constexpr (PRUNED) {
 #pragma unroll
-                    for (int r = 0; r < kMagRegs; ++r) {
+                    for (int r = 0; r < kPrunedRows; ++r) {
                         const int k = 32 * r + lane;
-                        mg[r] = (k < p.kb) ? __ldg(magrow + k) : 0.0f;
+                        mg[r] = (k < kb) ? __ldg(magrow + k) : 0.0f;
                     }
                 }
                 float nyq;
-                frame_fwd_b(a, nyq, scratch, s_vtab, lane, p.kb);
+                frame_fwd_b<PRUNED>(a, nyq, scratch, s_vtab, lane);
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    if (32 * r < p.kb) {
-                        const int k = 32 * r + lane;
-                        float m;
-                        if (r < kMagRegs && pre) m = mg[r < kMagRegs ? r : 0];
-                        else m = (k < p.kb) ? __ldg(magrow + k) : 0.0f;
-                        float x = a[r].x, y = a[r].y;
-                        float r2 = fmaf(x, x, y * y);
-                        if (r2 < 1e-30f) {  // keep the phase of tiny (possibly denormal) bins
-                            x *= 1.1529215e18f;
-                            y *= 1.1529215e18f;
-                            r2 = fmaf(x, x, y * y);
-                        }
-                        const float sc = m * rsqrtf(r2);
-                        // atan2(0, +-0) = 0 / pi  ->  (+-mag, 0)
-                        a[r] = r2 > 0.0f ? make_float2(x * sc, y * sc) : make_float2(copysignf(m, x), 0.0f);
-                    } else {
-                        a[r] = make_float2(0.0f, 0.0f);
-                    }
-                }
-                if (p.kb > 1024) ynyq = copysignf(__ldg(magrow + 1024), nyq);
-            } else {
-                const float* phrow = p.phase + row * p.phase_stride;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
+                for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
                     const int k = 32 * r + lane;
-                    if (32 * r < p.kb && k < p.kb) {
+                    float m;
+                    if constexpr (PRUNED) m = mg[r];
+                    else m = (k < kb) ? __ldg(magrow + k) : 0.0f;
+                    float x = a[r].x, yy = a[r].y;
+                    float r2 = fmaf(x, x, yy * yy);
+                    if (r2 < 1e-30f) {  // keep the phase of tiny (possibly denormal) bins
+                        x *= 1.1529215e18f;
+                        yy *= 1.1529215e18f;
+                        r2 = fmaf(x, x, yy * yy);
+                    }
+                    const float sc = m * rsqrtf(r2);
+                    // atan2(0, +-0) = 0 / pi  ->  (+-mag, 0)
+                    a[r] = r2 > 0.0f ? make_float2(x * sc, yy * sc) : make_float2(copysignf(m, x), 0.0f);
+                }
+                if (kb > 1024) ynyq = copysignf(__ldg(magrow + 1024), nyq);
+            } else {
+#pragma unroll
+                for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
+                    const int k = 32 * r + lane;
+                    if (k < kb) {
                         const float m = __ldg(magrow + k);
                         float sn, cs, rs, rc;
                         sincosf(__ldg(phrow + k), &sn, &cs);
@@ -153,80 +201,56 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                         a[r] = make_float2(0.0f, 0.0f);
                     }
                 }
-                if (p.kb > 1024) ynyq = __ldg(magrow + 1024) * cosf(__ldg(phrow + 1024));
+                if (kb > 1024) ynyq = __ldg(magrow + 1024) * cosf(__ldg(phrow + 1024));
+                phrow += p.phase_stride;
             }
-            frame_inv(a, ynyq, scratch, s_tw, s_vtab, lane);
-        }
-        __syncthreads();  // zero-fill done
-        // overlap-add: frames of the same phase (w mod nphase) never overlap
-        for (int c = 0; c < p.nphase; ++c) {
-            if (active && (warp % p.nphase) == c) {
-                float* dst = s_ola + warp * p.hop + 2 * lane;
+            frame_inv<PRUNED>(a, ynyq, scratch, s_tw, s_vtab, lane);
+
+            // overlap-add into the private ring
+            {
                 const float* w = s_win_s + 2 * lane;
-                if (hop_even) {
 #pragma unroll
-                    for (int r = 0; r < NZ; ++r) {
-                        if (64 * r + 2 * lane < p.ws) {
-                            float2 o = *reinterpret_cast<float2*>(dst + 64 * r);
+                for (int r = 0; r < NZ; ++r) {
+                    const int m = 64 * r + 2 * lane;
+                    if (m < p.ws) {
+                        int slot = slot0 + m;
+                        if (slot >= p.ws) slot -= p.ws;
+                        if (hop_even) {
+                            float2 o = *reinterpret_cast<float2*>(ring + slot);
                             const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
                             o.x = fmaf(a[r].x, ww.x, o.x);
                             o.y = fmaf(a[r].y, ww.y, o.y);
-                            *reinterpret_cast<float2*>(dst + 64 * r) = o;
+                            *reinterpret_cast<float2*>(ring + slot) = o;
+                        } else {
+                            int slot1 = slot + 1;
+                            if (slot1 >= p.ws) slot1 -= p.ws;
+                            ring[slot] = fmaf(a[r].x, w[64 * r], ring[slot]);
+                            ring[slot1] = fmaf(a[r].y, w[64 * r + 1], ring[slot1]);
                         }
                     }
-                } else {
+                }
+            }
+            // next frame's samples: requested now, they arrive while this hop is written out
+            if constexpr (!FIRST) {
+                if (f + 1 < td.nf) {
+                    const int j0 = c.j_base + (f + 1) * p.hop + 2 * lane;
 #pragma unroll
-                    for (int r = 0; r < NZ; ++r) {
-                        if (64 * r + 2 * lane < p.ws) {
-                            dst[64 * r] = fmaf(a[r].x, w[64 * r], dst[64 * r]);
-                            dst[64 * r + 1] = fmaf(a[r].y, w[64 * r + 1], dst[64 * r + 1]);
-                        }
-                    }
+                    for (int r = 0; r < NZ; ++r) a[r] = load_pair(y, j0 + 64 * r, c.L, vec_ok);
                 }
             }
-            __syncthreads();
+            __syncwarp();
+            emit(p, c, ring, s_inv_wss, f * p.hop, p.hop, slot0, 0, lane);
+            slot0 += p.hop;
+            if (slot0 >= p.ws) slot0 -= p.ws;
+            __syncwarp();
         }
-        // ---- normalise and write.  Sample i of the tile sits at q = f0*hop + i from frame 0's origin,
-        // so q mod hop == i mod hop and the last frame that can cover it is f0 + i / hop.
-        {
-            float* out = p.out + ud.wave_off;
-            float* znext = p.zero_next + ud.wave_off;
-            const bool has_prev = td.f0 > 0, has_next = td.f0 + td.nf < T;
-            const int left_end = p.ws - p.hop;        // i < left_end  : also covered by the previous tile
-            const int right_beg = td.nf * p.hop;      // i >= right_beg: also covered by the next tile
-            int q = tid / p.hop, r = tid % p.hop;
-            for (int i = tid; i < span_out; i += kGlThreads) {
-                const int j = j_base + i;
-                if (j >= 0 && j < L) {
-                    const int t_hi_u = td.f0 + q;
-                    const int t_lo_u = i < p.ws ? td.f0 - (p.ws - 1 - i) / p.hop : td.f0 + (i - p.ws) / p.hop + 1;
-                    float inv;
-                    if (t_lo_u >= 0 && t_hi_u <= T - 1) {
-                        inv = s_inv_wss[r];
-                    } else {  // utterance edges: only the frames that exist (vocoder.py:78-81 order)
-                        float acc = 0.0f;
-                        const int qq = td.f0 * p.hop + i;
-                        for (int t = max(t_lo_u, 0); t <= min(t_hi_u, T - 1); ++t) acc += __ldg(p.w2 + (qq - t * p.hop));
-                        inv = acc > kTiny ? 1.0f / acc : 1.0f;
-                    }
-                    const float v = s_ola[i] * inv;
-                    const bool right_seam = has_next && i >= right_beg;
-                    if (right_seam || (has_prev && i < left_end)) atomicAdd(out + j, v);
-                    else out[j] = v;
-                    if (right_seam) znext[j] = 0.0f;
-                }
-                q += step_q;
-                r += step_r;
-                if (r >= p.hop) {
-                    r -= p.hop;
-                    ++q;
-                }
-            }
-        }
+        // the tail of the last frame: [nf*hop, (nf-1)*hop + ws)
+        emit(p, c, ring, s_inv_wss, td.nf * p.hop, p.ws - p.hop, slot0, 0, lane);
+        __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict__ fo, int n_utts, int hop,
+__global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict__ fo, int n_utts, int hop, int S,
                                                        UttDesc* __restrict__ utts,
                                                        TileDesc* __restrict__ tiles, int* __restrict__ n_tiles) {
     __shared__ int s_warp[32];
@@ -237,7 +261,7 @@ __global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict_
     for (int base = 0; base < n_utts; base += 1024) {
         const int u = base + tid;
         const int T = u < n_utts ? fo[u + 1] - fo[u] : 0;
-        const int nt = (T + kTileFrames - 1) / kTileFrames;
+        const int nt = (T + S - 1) / S;
         int incl = nt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -266,8 +290,8 @@ __global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict_
             for (int k = 0; k < nt; ++k) {
                 TileDesc t;
                 t.utt = u;
-                t.f0 = k * kTileFrames;
-                t.nf = min(kTileFrames, T - k * kTileFrames);
+                t.f0 = k * S;
+                t.nf = min(S, T - k * S);
                 t.pad = 0;
                 tiles[first + k] = t;
             }
@@ -318,14 +342,14 @@ __global__ void __launch_bounds__(256) k_rfft2048(const float2* __restrict__ tw_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float2* s_vtab = s_tw + 1024;
-    float2* s_scratch = s_vtab + 1024;
+    float* s_scratch = reinterpret_cast<float*>(s_vtab + 1024);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += blockDim.x) {
         s_tw[i] = tw_g[i];
         s_vtab[i] = vtab_g[i];
     }
     __syncthreads();
-    float2* scratch = s_scratch + warp * kScratchFloat2;
+    float* scratch = s_scratch + warp * kScratchFloats;
     for (long long f = (long long)blockIdx.x * 8 + warp; f < n; f += (long long)gridDim.x * 8) {
         float2 a[32];
         if constexpr (!INVERSE) {
@@ -343,7 +367,7 @@ __global__ void __launch_bounds__(256) k_rfft2048(const float2* __restrict__ tw_
 #pragma unroll
             for (int r = 0; r < 32; ++r) a[r] = src[32 * r + lane];
             const float ynyq = src[1024].x;
-            frame_inv(a, ynyq, scratch, s_tw, s_vtab, lane);
+            frame_inv<false>(a, ynyq, scratch, s_tw, s_vtab, lane);
             float2* dst = reinterpret_cast<float2*>(out + f * kNfft);
             const float sc = 1.0f / 2048.0f;
 #pragma unroll
@@ -375,7 +399,7 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
         off += align_up(bytes, 256);
         return r;
     };
-    w.max_tiles = total_frames / kTileFrames + n_utts;
+    w.max_tiles = total_frames / kMinStrip + n_utts;
     w.wave_samples = (total_frames - n_utts) * (long long)plan->hop;
     w.mag_stride = (int)align_up((size_t)plan->kb, 4);
     w.utts = reinterpret_cast<UttDesc*>(take(sizeof(UttDesc) * (size_t)n_utts));
@@ -389,21 +413,47 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
 }
 
 size_t gl_pass_smem(const s2st_plan* plan) {
-    return sizeof(float2) * (2048 + kTileFrames * kScratchFloat2) +
-           sizeof(float) * (2 * plan->wp + ((plan->hop + 3) & ~3) + (kTileFrames - 1) * plan->hop + plan->wp);
+    return sizeof(float2) * 2048 +
+           sizeof(float) * (2 * plan->wp + ((plan->hop + 3) & ~3) + kGlWarps * (kScratchFloats + ((plan->ws + 3) & ~3)));
+}
+
+// Strip length: all strips cost the same, warps take them round-robin, so the pass lasts
+// ceil(n_strips / n_warps) strip times.  Pick the S that minimises that (exactly when the host knows the
+// utterance lengths, from the average otherwise).
+int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, const int32_t* fo_host) {
+    const long long n_warps = (long long)plan->num_sms * 2 * kGlWarps;
+    const int s_min = plan->nphase > kMinStrip ? plan->nphase : kMinStrip;
+    int best = s_min;
+    double best_cost = 1e300;
+    for (int S = s_min; S <= 64; ++S) {
+        long long strips = 0;
+        if (fo_host) {
+            for (int u = 0; u < n_utts; ++u) strips += (fo_host[u + 1] - fo_host[u] + S - 1) / S;
+        } else {
+            strips = total_frames / S + (n_utts + 1) / 2;
+        }
+        const long long waves = (strips + n_warps - 1) / n_warps;
+        const double cost = (double)waves * (S + 0.35);  // + the flush / seam work of a strip
+        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && S > best)) {
+            best_cost = cost;
+            best = S;
+        }
+    }
+    return best;
+}
+
+template <int NZ, bool FIRST, bool PRUNED>
+int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream) {
+    S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_gl_pass<NZ, FIRST, PRUNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gl_pass<NZ, FIRST, PRUNED><<<grid, kGlThreads, smem, stream>>>(p);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
 }
 
 template <int NZ>
-int launch_pass(const GlParams& p, bool first, int grid, size_t smem, cudaStream_t stream) {
-    if (first) {
-        S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_gl_pass<NZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gl_pass<NZ, true><<<grid, kGlThreads, smem, stream>>>(p);
-    } else {
-        S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_gl_pass<NZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gl_pass<NZ, false><<<grid, kGlThreads, smem, stream>>>(p);
-    }
-    S2ST_CUDA_CHECK(cudaGetLastError());
-    return S2ST_OK;
+int launch_pass(const GlParams& p, bool first, bool pruned, int grid, size_t smem, cudaStream_t stream) {
+    if (first) return pruned ? launch_pass_t<NZ, true, true>(p, grid, smem, stream) : launch_pass_t<NZ, true, false>(p, grid, smem, stream);
+    return pruned ? launch_pass_t<NZ, false, true>(p, grid, smem, stream) : launch_pass_t<NZ, false, false>(p, grid, smem, stream);
 }
 
 }  // namespace
@@ -429,7 +479,7 @@ int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* l
 int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* out, bool inverse,
                     cudaStream_t stream) {
     if (n <= 0) return S2ST_OK;
-    const size_t smem = sizeof(float2) * (2048 + 8 * kScratchFloat2);
+    const size_t smem = sizeof(float2) * 2048 + sizeof(float) * 8 * kScratchFloats;
     const int grid = (int)min((long long)plan->num_sms * 2, (n + 7) / 8);
     if (inverse) {
         S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_rfft2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -443,7 +493,7 @@ int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* 
 }
 
 int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const int32_t* frame_offsets,
-           const float* logmel, const float* mag, int mag_kb, const float* phase, int n_iter,
+           const int32_t* frame_offsets_host, const float* logmel, const float* mag, int mag_kb, const float* phase, int n_iter,
            float* wave_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     s2st_plan* plan = const_cast<s2st_plan*>(plan_c);  // only the profiling state is mutated
     if (n_utts <= 0 || total_frames < n_utts) {
@@ -458,7 +508,8 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
         return S2ST_EWORKSPACE;
     }
     if (w.wave_samples <= 0) return S2ST_OK;  // every utterance has a single frame: nothing to write
-    k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, w.utts, w.tiles, w.n_tiles);
+    const int S = choose_strip(plan, n_utts, total_frames, frame_offsets_host);
+    k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, S, w.utts, w.tiles, w.n_tiles);
     S2ST_CUDA_CHECK(cudaGetLastError());
 
     GlParams p;
@@ -491,7 +542,9 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
         p.kb = mag_kb;
     }
     const size_t smem = gl_pass_smem(plan);
-    const int grid = (int)min((long long)plan->num_sms * 2, w.max_tiles);
+    const long long strips_ub = total_frames / S + n_utts;
+    const int grid = (int)min((long long)plan->num_sms * 2, (strips_ub + kGlWarps - 1) / kGlWarps);
+    const bool pruned = p.kb <= 32 * kPrunedRows;
     // three rotating waveform buffers; the one the last pass writes is the caller's output
     float* ring[3];
     ring[n_iter % 3] = wave_out;
@@ -507,8 +560,8 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
             if (!plan->timing_events[it]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[it]));
             S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[it], stream));
         }
-        int rc = (plan->nz == 19) ? launch_pass<19>(p, it == 0, grid, smem, stream)
-                                  : launch_pass<32>(p, it == 0, grid, smem, stream);
+        int rc = (plan->nz == 19) ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
+                                  : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
         if (rc != S2ST_OK) return rc;
     }
     if (timed) {

@@ -81,14 +81,15 @@ class GriffinLim(torch.nn.Module):
         """mag_fm / phase_fm: frame-major [B*T, F] float32 on dev -> [B, L]."""
         plan = self._plan(dev)
         total = n_utts * frames_per_utt
-        fo = torch.arange(0, total + 1, frames_per_utt, dtype=torch.int32, device=dev)
+        fo_h = np.arange(0, total + 1, frames_per_utt, dtype=np.int32)
+        fo = torch.from_numpy(fo_h).to(dev)
         L = (frames_per_utt - 1) * self.hop_length
         wave = torch.empty(n_utts, L, dtype=torch.float32, device=dev)
         if L == 0:
             return wave
         ws = plan.workspace(n_utts, total)
         with torch.cuda.device(dev):
-            rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo), None, _lib.ptr(mag_fm),
+            rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo), fo_h.ctypes.data, None, _lib.ptr(mag_fm),
                                                 _lib.ptr(phase_fm), n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_ptr(dev))
         _lib.check(rc, "s2st_gl_synthesize")
@@ -199,7 +200,7 @@ class GriffinLimVocoder(nn.Module):
             return wave
         ws = plan.workspace(n_utts, total)
         with torch.cuda.device(dev):
-            rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo_d), _lib.ptr(logmel_flat), None,
+            rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo_d), fo.ctypes.data, _lib.ptr(logmel_flat), None,
                                                 _lib.ptr(phase_fm), n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_ptr(dev))
         _lib.check(rc, "s2st_gl_synthesize")
