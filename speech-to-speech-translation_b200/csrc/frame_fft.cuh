@@ -82,12 +82,12 @@ __device__ __forceinline__ void frame_fwd_a(float2 (&a)[32], float* scratch, con
     warp_transpose(a, scratch, lane);
 }
 
-// Forward, second half.  Out: a[k1] = 2*X[32*k1+lane] (PRUNED: only k1 < 22, the rest undefined),
-// nyq = 2*X[1024] (valid in lane 0).  vtab[k] = -i*exp(-2*pi*i*k/2048).
+// Pair exchange + real-signal split after the second in-lane FFT.  In: a[k1] = Z[32*k1+lane].
+// Out: a[k1] = 2*X[32*k1+lane] (PRUNED: only k1 < 22, the rest undefined), nyq = 2*X[1024] (valid in
+// lane 0).  vtab[k] = -i*exp(-2*pi*i*k/2048).
 template <bool PRUNED>
-__device__ __forceinline__ void frame_fwd_b(float2 (&a)[32], float& nyq, float* scratch,
-                                            const float2* __restrict__ vtab, int lane) {
-    fft32<32, false>(a);
+__device__ __forceinline__ void fwd_split(float2 (&a)[32], float& nyq, float* scratch,
+                                          const float2* __restrict__ vtab, int lane) {
     nyq = 2.0f * (a[0].x - a[0].y);
     float2* sc = reinterpret_cast<float2*>(scratch);
     if constexpr (PRUNED) {
@@ -128,6 +128,14 @@ __device__ __forceinline__ void frame_fwd_b(float2 (&a)[32], float& nyq, float* 
     }
 }
 
+// Forward, second half: in-lane FFT over n1, then the split.
+template <bool PRUNED>
+__device__ __forceinline__ void frame_fwd_b(float2 (&a)[32], float& nyq, float* scratch,
+                                            const float2* __restrict__ vtab, int lane) {
+    fft32<32, false>(a);
+    fwd_split<PRUNED>(a, nyq, scratch, vtab, lane);
+}
+
 // Forward = both halves, all bins.
 template <int NZ>
 __device__ __forceinline__ void frame_fwd(float2 (&a)[32], float& nyq, float* scratch,
@@ -137,12 +145,12 @@ __device__ __forceinline__ void frame_fwd(float2 (&a)[32], float& nyq, float* sc
     frame_fwd_b<false>(a, nyq, scratch, vtab, lane);
 }
 
-// Inverse.  In: a[k1] = Y[32*k1+lane] (Hermitian half-spectrum, imag of DC ignored; PRUNED: rows >= 22
-// are taken as zero whatever they hold), ynyq = Y[1024] (real, read from lane 0).
-// Out: a[n2] = 2048 * y[2*(lane+32*n2)] + i * 2048 * y[..+1].
-template <bool PRUNED>
-__device__ __forceinline__ void frame_inv(float2 (&a)[32], float ynyq, float* scratch,
-                                          const float2* __restrict__ tw,
+// Hermitian merge before the inverse transform.  In: a[k1] = Y[32*k1+lane] (half-spectrum, imag of DC
+// ignored; PRUNED: rows >= 22 are taken as zero whatever they hold), ynyq = Y[1024] (real, from lane 0).
+// Out: a[k1] = Z'[32*k1+lane], the packed 1024-point spectrum; SWAP: real and imaginary parts exchanged,
+// which turns the inverse transform into a forward one (IDFT(Z) = swap(DFT(swap(Z)))).
+template <bool PRUNED, bool SWAP>
+__device__ __forceinline__ void inv_merge(float2 (&a)[32], float ynyq, float* scratch,
                                           const float2* __restrict__ vtab, int lane) {
     if (lane == 0) a[0].y = 0.0f;
     float2* sc = reinterpret_cast<float2*>(scratch);
@@ -151,15 +159,30 @@ __device__ __forceinline__ void frame_inv(float2 (&a)[32], float ynyq, float* sc
         for (int r = 0; r < kPrunedRows; ++r) sc[32 * r + lane] = a[r];
         if (lane == 0) sc[704] = make_float2(ynyq, 0.0f);
         __syncwarp();
+        // partner bin 1024-k is live (< 704) iff k > 320: never for rows < 10, always for rows > 10, row 10
+        // except lane 0; bin 0 pairs with the Nyquist alias.  Rows >= 22 hold no Y of their own.
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
             const int k = 32 * r + lane;
-            const int pi = 1024 - k;  // partner bin; bins in [704, 1024) are zero
-            float2 p = make_float2(0.0f, 0.0f);
-            if (pi < 704) p = sc[pi];
-            else if (pi == 1024) p = sc[704];
-            const float2 y = (r < kPrunedRows) ? a[r] : make_float2(0.0f, 0.0f);
-            a[r] = merge_inv(y, p, vtab[k]);
+            const float2 v = vtab[k];
+            float2 z;
+            if (r < 10) {
+                float2 p = make_float2(0.0f, 0.0f);
+                if (r == 0 && lane == 0) p = sc[704];
+                z = (r == 0) ? merge_inv(a[r], p, v)
+                             : make_float2(fmaf(v.x, a[r].x, fmaf(v.y, a[r].y, a[r].x)), fmaf(v.x, a[r].y, fmaf(-v.y, a[r].x, a[r].y)));
+            } else if (r == 10) {
+                float2 p = make_float2(0.0f, 0.0f);
+                if (lane > 0) p = sc[1024 - k];
+                z = merge_inv(a[r], p, v);
+            } else if (r < kPrunedRows) {
+                z = merge_inv(a[r], sc[1024 - k], v);
+            } else {
+                // Y = 0: Z' = conj(P) - conj(V) conj(P)
+                const float2 p = sc[1024 - k];
+                z = make_float2(fmaf(-v.x, p.x, fmaf(v.y, p.y, p.x)), fmaf(v.x, p.y, fmaf(v.y, p.x, -p.y)));
+            }
+            a[r] = SWAP ? make_float2(z.y, z.x) : z;
         }
         __syncwarp();
     } else {
@@ -178,12 +201,39 @@ __device__ __forceinline__ void frame_inv(float2 (&a)[32], float ynyq, float* sc
         for (int r = 16; r < 32; ++r) {
             const int k = 32 * r + lane;
             const float2 p = (k == 512) ? a[r] : sc[1024 - k];
-            a[r] = merge_inv(a[r], p, vtab[k]);
+            const float2 z = merge_inv(a[r], p, vtab[k]);
+            a[r] = SWAP ? make_float2(z.y, z.x) : z;
         }
 #pragma unroll
-        for (int r = 0; r < 16; ++r) a[r] = merge_inv(a[r], t[r], vtab[32 * r + lane]);
+        for (int r = 0; r < 16; ++r) {
+            const float2 z = merge_inv(a[r], t[r], vtab[32 * r + lane]);
+            a[r] = SWAP ? make_float2(z.y, z.x) : z;
+        }
         __syncwarp();
     }
+}
+
+// The 1024-point complex forward DFT of the per-lane arrays, in place: in a[j] = z[lane + 32*j], out
+// a[j] = Z[lane + 32*j] -- input and output use the same (index mod 32, index div 32) layout, which is
+// what lets one routine serve both directions.  The in-lane FFT is emitted once and run twice.
+__device__ __forceinline__ void fwd1024(float2 (&a)[32], float* scratch, const float2* __restrict__ tw, int lane) {
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        fft32<32, false>(a);
+        if (h == 0) {
+#pragma unroll
+            for (int r = 1; r < 32; ++r) a[r] = cmul(a[r], tw[r * 32 + lane]);
+            warp_transpose(a, scratch, lane);
+        }
+    }
+}
+
+// Inverse.  In: as inv_merge.  Out: a[n2] = 2048 * y[2*(lane+32*n2)] + i * 2048 * y[..+1].
+template <bool PRUNED>
+__device__ __forceinline__ void frame_inv(float2 (&a)[32], float ynyq, float* scratch,
+                                          const float2* __restrict__ tw,
+                                          const float2* __restrict__ vtab, int lane) {
+    inv_merge<PRUNED, false>(a, ynyq, scratch, vtab, lane);
     fft32<32, true>(a);
 #pragma unroll
     for (int r = 1; r < 32; ++r) a[r] = cmul_conj(a[r], tw[r * 32 + lane]);

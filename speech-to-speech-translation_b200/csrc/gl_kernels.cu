@@ -32,59 +32,60 @@ namespace {
 constexpr float kTiny = 1.1754944e-38f;  // vocoder.py:69
 constexpr int kGlWarps = kGlThreads / 32;
 
-// two consecutive samples of the reflect-padded waveform (audio_utils.py:262-263), j even
-__device__ __forceinline__ float2 load_pair(const float* __restrict__ y, int j, int L, bool vec_ok) {
-    if (vec_ok && j >= 0 && j + 1 < L) return *reinterpret_cast<const float2*>(y + j);
-    int j0 = j < 0 ? -j : j, j1 = j + 1 < 0 ? -(j + 1) : j + 1;
-    j0 = j0 >= L ? 2 * (L - 1) - j0 : j0;
-    j1 = j1 >= L ? 2 * (L - 1) - j1 : j1;
-    j0 = min(max(j0, 0), L - 1);  // only reachable where the window is zero
-    j1 = min(max(j1, 0), L - 1);
-    return make_float2(y[j0], y[j1]);
+// Frame load, cold path: reflect padding (audio_utils.py:262-263) at utterance edges / unaligned data.
+template <int NZ>
+__device__ __forceinline__ void load_frame_edge(float2 (&a)[32], const float* __restrict__ y, int j, int L) {
+#pragma unroll 1
+    for (int r = 0; r < NZ; ++r, j += 64) {
+        int j0 = j < 0 ? -j : j, j1 = j + 1 < 0 ? -(j + 1) : j + 1;
+        j0 = j0 >= L ? 2 * (L - 1) - j0 : j0;
+        j1 = j1 >= L ? 2 * (L - 1) - j1 : j1;
+        j0 = min(max(j0, 0), L - 1);  // only reachable where the window is zero
+        j1 = min(max(j1, 0), L - 1);
+        const float2 v = make_float2(y[j0], y[j1]);
+        // registers cannot be indexed dynamically: scatter through a switch-free unrolled select
+#pragma unroll
+        for (int q = 0; q < NZ; ++q)
+            if (q == r) a[q] = v;
+    }
 }
 
-struct StripCtx {
-    int f0, nf, T, L, j_base;
-    bool has_prev, has_next;
-    float* out;
-    float* znext;
-};
-
-// Normalise and write samples [i0, i0 + n) of the strip (strip-relative index i), reading and clearing
-// the ring from slot `slot0`.  r0 = i0 mod hop.
-__device__ __forceinline__ void emit(const GlParams& p, const StripCtx& c, float* ring, const float* s_inv_wss,
-                                     int i0, int n, int slot0, int r0, int lane) {
-    const int left_end = p.ws - p.hop;     // i < left_end : the previous strip's frames cover it too
-    const int right_beg = c.nf * p.hop;    // i >= right_beg: the next strip's frames cover it too
+// Generic (cold) write-out of strip samples [i0, i0 + n): seams, utterance edges, unaligned layouts.
+// Kept out of line; everything it needs is passed by value.
+__device__ __noinline__ void emit_generic(float* __restrict__ ring, const float* __restrict__ s_inv_wss,
+                                          const float* __restrict__ w2, float* __restrict__ out,
+                                          float* __restrict__ znext, int hop, int ws, int f0, int nf, int T, int L,
+                                          int j_base, int i0, int n, int slot0, int lane) {
+    const bool has_prev = f0 > 0, has_next = f0 + nf < T;
+    const int left_end = ws - hop;     // i < left_end : the previous strip's frames cover it too
+    const int right_beg = nf * hop;    // i >= right_beg: the next strip's frames cover it too
+    const int clip_beg = (T - f0) * hop;  // a frame index >= T would be needed from here on
     for (int e = lane; e < n; e += 32) {
         int slot = slot0 + e;
-        if (slot >= p.ws) slot -= p.ws;
+        while (slot >= ws) slot -= ws;
         const float acc = ring[slot];
         ring[slot] = 0.0f;
         const int i = i0 + e;
-        const int j = c.j_base + i;
-        if (j < 0 || j >= c.L) continue;
+        const int j = j_base + i;
+        if (j < 0 || j >= L) continue;
         const bool in_left = i < left_end, in_right = i >= right_beg;
         float inv;
-        // clipped at the utterance start (strip 0 only) or end (a frame index >= T would cover the sample)
-        if ((in_left && !c.has_prev) || i >= (c.T - c.f0) * p.hop) {
+        if ((in_left && !has_prev) || i >= clip_beg) {
             // utterance edges: only the frames that exist contribute (vocoder.py:78-81, frame order)
-            const int t_lo = i < p.ws ? c.f0 - (p.ws - 1 - i) / p.hop : c.f0 + (i - p.ws) / p.hop + 1;
-            const int t_hi = c.f0 + i / p.hop;
-            const int qq = c.f0 * p.hop + i;
+            const int t_lo = i < ws ? f0 - (ws - 1 - i) / hop : f0 + (i - ws) / hop + 1;
+            const int t_hi = f0 + i / hop;
+            const int qq = f0 * hop + i;
             float w = 0.0f;
-            for (int t = max(t_lo, 0); t <= min(t_hi, c.T - 1); ++t) w += __ldg(p.w2 + (qq - t * p.hop));
+            for (int t = max(t_lo, 0); t <= min(t_hi, T - 1); ++t) w += __ldg(w2 + (qq - t * hop));
             inv = w > kTiny ? 1.0f / w : 1.0f;
         } else {
-            int r = r0 + e;
-            while (r >= p.hop) r -= p.hop;
-            inv = s_inv_wss[r];
+            inv = s_inv_wss[i % hop];
         }
         const float v = acc * inv;
-        const bool right_seam = in_right && c.has_next;
-        if (right_seam || (in_left && c.has_prev)) atomicAdd(c.out + j, v);
-        else c.out[j] = v;
-        if (right_seam) c.znext[j] = 0.0f;
+        const bool right_seam = in_right && has_next;
+        if (right_seam || (in_left && has_prev)) atomicAdd(out + j, v);
+        else out[j] = v;
+        if (right_seam) znext[j] = 0.0f;
     }
 }
 
@@ -118,134 +119,160 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
     __syncthreads();  // the only block-wide barrier: constant tables are in place
 
     const int n_strips = *p.n_tiles;
-    const bool hop_even = (p.hop & 1) == 0;
+    const int hop = p.hop, ws = p.ws;
     const int kb = PRUNED ? min(p.kb, 32 * kPrunedRows) : p.kb;
+    // fast paths need 16-byte friendly geometry (true for hop 300 / win 1200 / n_fft 2048)
+    const bool geom4 = (hop % 4 == 0) && (ws % hop == 0) && ((p.rot - p.half) % 4 == 0);
 
     for (int strip = blockIdx.x * kGlWarps + warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
         const TileDesc td = p.tiles[strip];
         const UttDesc ud = p.utts[td.utt];
-        StripCtx c;
-        c.f0 = td.f0;
-        c.nf = td.nf;
-        c.T = ud.n_frames;
-        c.L = (c.T - 1) * p.hop;
-        c.j_base = td.f0 * p.hop + p.rot - p.half;  // output sample index of strip-relative sample 0
-        c.has_prev = td.f0 > 0;
-        c.has_next = td.f0 + td.nf < c.T;
-        c.out = p.out + ud.wave_off;
-        c.znext = p.zero_next + ud.wave_off;
+        const int T = ud.n_frames, L = (T - 1) * hop;
+        const int j_base = td.f0 * hop + p.rot - p.half;  // output sample index of strip-relative sample 0
+        float* out = p.out + ud.wave_off;
+        float* znext = p.zero_next + ud.wave_off;
         const float* y = p.in + ud.wave_off;
-        const bool vec_ok = hop_even && ((ud.wave_off & 1) == 0);
+        const bool aligned = geom4 && ((ud.wave_off & 3) == 0);
         const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0) * p.mag_stride;
         const float* phrow = FIRST ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
 
         float2 a[32];
-        if constexpr (!FIRST) {
-            const int j0 = c.j_base + 2 * lane;
-#pragma unroll
-            for (int r = 0; r < NZ; ++r) a[r] = load_pair(y, j0 + 64 * r, c.L, vec_ok);
-        }
         int slot0 = 0;  // ring slot of strip-relative sample f * hop
-        for (int f = 0; f < td.nf; ++f, magrow += p.mag_stride) {
-            float ynyq = 0.0f;
-            if constexpr (!FIRST) {
-                const float* w = s_win_a + 2 * lane;
-#pragma unroll
-                for (int r = 0; r < NZ; ++r) {
-                    const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
-                    a[r] = make_float2(a[r].x * ww.x, a[r].y * ww.y);
-                }
-                frame_fwd_a<NZ>(a, scratch, s_tw, lane);
-                // target magnitudes: requested here so the second in-lane FFT hides their latency
+        // f = -1 only fetches frame 0; iteration f processes frame f and fetches frame f + 1, so the
+        // (single) copy of the load code overlaps with the write-out of the previous hop.
+#pragma unroll 1
+        for (int f = FIRST ? 0 : -1; f < td.nf; ++f) {
+            if (f >= 0) {
+                float ynyq = 0.0f;
                 float mg[kPrunedRows];
-                if constexpr (PRUNED) {
+                if constexpr (!FIRST) {
+                    const float* w = s_win_a + 2 * lane;
 #pragma unroll
-                    for (int r = 0; r < kPrunedRows; ++r) {
-                        const int k = 32 * r + lane;
-                        mg[r] = (k < kb) ? __ldg(magrow + k) : 0.0f;
+                    for (int r = 0; r < NZ; ++r) {
+                        const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
+                        a[r] = make_float2(a[r].x * ww.x, a[r].y * ww.y);
+                    }
+#pragma unroll
+                    for (int r = NZ; r < 32; ++r) a[r] = make_float2(0.0f, 0.0f);
+                    // target magnitudes: requested now, the forward transform hides their latency
+                    if constexpr (PRUNED) {
+#pragma unroll
+                        for (int r = 0; r < kPrunedRows; ++r) {
+                            const int k = 32 * r + lane;
+                            mg[r] = (k < kb) ? __ldg(magrow + k) : 0.0f;
+                        }
                     }
                 }
-                float nyq;
-                frame_fwd_b<PRUNED>(a, nyq, scratch, s_vtab, lane);
+                // pass 0: analysis (frame -> spectrum -> re-imposed magnitude); pass 1: synthesis.  The
+                // 1024-point transform is the same code in both directions (see inv_merge), emitted once.
+#pragma unroll 1
+                for (int pass = FIRST ? 1 : 0; pass < 2; ++pass) {
+                    if (pass == 1) {
+                        if constexpr (FIRST) {
 #pragma unroll
-                for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
-                    const int k = 32 * r + lane;
-                    float m;
-                    if constexpr (PRUNED) m = mg[r];
-                    else m = (k < kb) ? __ldg(magrow + k) : 0.0f;
-                    float x = a[r].x, yy = a[r].y;
-                    float r2 = fmaf(x, x, yy * yy);
-                    if (r2 < 1e-30f) {  // keep the phase of tiny (possibly denormal) bins
-                        x *= 1.1529215e18f;
-                        yy *= 1.1529215e18f;
-                        r2 = fmaf(x, x, yy * yy);
+                            for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
+                                const int k = 32 * r + lane;
+                                if (k < kb) {
+                                    const float m = __ldg(magrow + k);
+                                    float sn, cs, rs, rc;
+                                    sincosf(__ldg(phrow + k), &sn, &cs);
+                                    // the caller's phase refers to the un-rotated frame; frames are processed
+                                    // rotated by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048)
+                                    sincospif((float)((k * p.rot) & 2047) * (1.0f / 1024.0f), &rs, &rc);
+                                    a[r] = make_float2(m * fmaf(cs, rc, -sn * rs), m * fmaf(cs, rs, sn * rc));
+                                } else {
+                                    a[r] = make_float2(0.0f, 0.0f);
+                                }
+                            }
+                            if (kb > 1024) ynyq = __ldg(magrow + 1024) * cosf(__ldg(phrow + 1024));
+                            phrow += p.phase_stride;
+                        }
+                        inv_merge<PRUNED, true>(a, ynyq, scratch, s_vtab, lane);
                     }
-                    const float sc = m * rsqrtf(r2);
-                    // atan2(0, +-0) = 0 / pi  ->  (+-mag, 0)
-                    a[r] = r2 > 0.0f ? make_float2(x * sc, yy * sc) : make_float2(copysignf(m, x), 0.0f);
-                }
-                if (kb > 1024) ynyq = copysignf(__ldg(magrow + 1024), nyq);
-            } else {
+                    fwd1024(a, scratch, s_tw, lane);
+                    if constexpr (!FIRST) {
+                        if (pass == 0) {
+                            float nyq;
+                            fwd_split<PRUNED>(a, nyq, scratch, s_vtab, lane);
 #pragma unroll
-                for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
-                    const int k = 32 * r + lane;
-                    if (k < kb) {
-                        const float m = __ldg(magrow + k);
-                        float sn, cs, rs, rc;
-                        sincosf(__ldg(phrow + k), &sn, &cs);
-                        // the caller's phase refers to the un-rotated frame; frames are processed rotated
-                        // by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048)
-                        sincospif((float)((k * p.rot) & 2047) * (1.0f / 1024.0f), &rs, &rc);
-                        a[r] = make_float2(m * fmaf(cs, rc, -sn * rs), m * fmaf(cs, rs, sn * rc));
-                    } else {
-                        a[r] = make_float2(0.0f, 0.0f);
+                            for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
+                                const int k = 32 * r + lane;
+                                float m;
+                                if constexpr (PRUNED) m = mg[r];
+                                else m = (k < kb) ? __ldg(magrow + k) : 0.0f;
+                                const float x = a[r].x, yy = a[r].y;
+                                const float r2 = fmaf(x, x, yy * yy);
+                                const float sc = m * rsqrtf(r2);
+                                // |X| == 0: atan2(0, +-0) = 0 / pi  ->  (+-mag, 0)
+                                a[r] = r2 > 0.0f ? make_float2(x * sc, yy * sc) : make_float2(copysignf(m, x), 0.0f);
+                            }
+                            if (kb > 1024) ynyq = copysignf(__ldg(magrow + 1024), nyq);
+                        }
                     }
                 }
-                if (kb > 1024) ynyq = __ldg(magrow + 1024) * cosf(__ldg(phrow + 1024));
-                phrow += p.phase_stride;
-            }
-            frame_inv<PRUNED>(a, ynyq, scratch, s_tw, s_vtab, lane);
-
-            // overlap-add into the private ring
-            {
+                magrow += p.mag_stride;
+                // a[] holds the synthesis frame with the parts swapped (.y = even sample, .x = odd sample):
+                // window and overlap-add into the private ring
                 const float* w = s_win_s + 2 * lane;
 #pragma unroll
                 for (int r = 0; r < NZ; ++r) {
                     const int m = 64 * r + 2 * lane;
-                    if (m < p.ws) {
+                    if (m < ws) {
                         int slot = slot0 + m;
-                        if (slot >= p.ws) slot -= p.ws;
-                        if (hop_even) {
+                        if (slot >= ws) slot -= ws;
+                        if (geom4) {
                             float2 o = *reinterpret_cast<float2*>(ring + slot);
                             const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
-                            o.x = fmaf(a[r].x, ww.x, o.x);
-                            o.y = fmaf(a[r].y, ww.y, o.y);
+                            o.x = fmaf(a[r].y, ww.x, o.x);
+                            o.y = fmaf(a[r].x, ww.y, o.y);
                             *reinterpret_cast<float2*>(ring + slot) = o;
                         } else {
                             int slot1 = slot + 1;
-                            if (slot1 >= p.ws) slot1 -= p.ws;
-                            ring[slot] = fmaf(a[r].x, w[64 * r], ring[slot]);
-                            ring[slot1] = fmaf(a[r].y, w[64 * r + 1], ring[slot1]);
+                            if (slot1 >= ws) slot1 -= ws;
+                            ring[slot] = fmaf(a[r].y, w[64 * r], ring[slot]);
+                            ring[slot1] = fmaf(a[r].x, w[64 * r + 1], ring[slot1]);
                         }
                     }
                 }
             }
-            // next frame's samples: requested now, they arrive while this hop is written out
+            // fetch the next frame (the loads fly while the finished hop is written out)
             if constexpr (!FIRST) {
                 if (f + 1 < td.nf) {
-                    const int j0 = c.j_base + (f + 1) * p.hop + 2 * lane;
+                    const int jf = j_base + (f + 1) * hop;  // first sample of the frame (lane 0)
+                    if (aligned && jf >= 0 && jf + 64 * NZ <= L) {
+                        const float2* src = reinterpret_cast<const float2*>(y + jf) + lane;
 #pragma unroll
-                    for (int r = 0; r < NZ; ++r) a[r] = load_pair(y, j0 + 64 * r, c.L, vec_ok);
+                        for (int r = 0; r < NZ; ++r) a[r] = src[32 * r];
+                    } else {
+                        load_frame_edge<NZ>(a, y, jf + 2 * lane, L);
+                    }
                 }
             }
-            __syncwarp();
-            emit(p, c, ring, s_inv_wss, f * p.hop, p.hop, slot0, 0, lane);
-            slot0 += p.hop;
-            if (slot0 >= p.ws) slot0 -= p.ws;
-            __syncwarp();
+            if (f >= 0) {
+                __syncwarp();
+                // hop f of the strip is final: normalise, store, clear its ring slots
+                const int i0 = f * hop;
+                const int j0 = j_base + i0;
+                if (aligned && i0 >= ws - hop && j0 >= 0 && j0 + hop <= L) {
+                    // steady state: no seam, no edge -> 16-byte wide, straight stores
+                    float4* dst = reinterpret_cast<float4*>(out + j0);
+                    float4* rg = reinterpret_cast<float4*>(ring + slot0);
+                    const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
+                    for (int q = lane; q < (hop >> 2); q += 32) {
+                        const float4 v = rg[q], wv = iw[q];
+                        rg[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        dst[q] = make_float4(v.x * wv.x, v.y * wv.y, v.z * wv.z, v.w * wv.w);
+                    }
+                } else {
+                    emit_generic(ring, s_inv_wss, p.w2, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, i0, hop, slot0, lane);
+                }
+                slot0 += hop;
+                if (slot0 >= ws) slot0 -= ws;
+                __syncwarp();
+            }
         }
         // the tail of the last frame: [nf*hop, (nf-1)*hop + ws)
-        emit(p, c, ring, s_inv_wss, td.nf * p.hop, p.ws - p.hop, slot0, 0, lane);
+        emit_generic(ring, s_inv_wss, p.w2, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
         __syncwarp();
     }
 }
