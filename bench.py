@@ -202,7 +202,7 @@ def run_ours(args):
                                 spec_bwd_max_iter=N_ITER).to(dev)
     plan = voc._plan(dev)
 
-    frames = batch_frames(rank)  # config 2 length law; every rank its own batch (weak scaling)
+    frames = batch_frames(0)  # config 2 length law; every rank the same lengths, its own content (weak scaling)
     total = int(sum(frames))
     n_bins = N_FFT // 2 + 1
     audio_s = sum((T - 1) * HOP for T in frames) / SR
