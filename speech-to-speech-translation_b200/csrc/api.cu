@@ -73,6 +73,7 @@ void free_plan_members(s2st_plan* p) {
     cudaFree(p->tw);
     cudaFree(p->vtab);
     cudaFree(p->inv_mel_t);
+    cudaFree(p->inv_mel_tc);
     cudaFree(p->mel_ptr);
     cudaFree(p->mel_idx);
     cudaFree(p->mel_val);
@@ -203,6 +204,11 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         for (int f = 0; f < p->kb; ++f)
             for (int m = 0; m < n_mels; ++m) t[(size_t)m * p->kb_pad + f] = inv_mel_host[(size_t)f * n_mels + m];
         rc = upload(&p->inv_mel_t, t);
+        if (rc == S2ST_OK && p->kb <= 704 && n_mels % 8 == 0 && n_mels <= 80) {
+            std::vector<float> tc(inverse_mel_tc_floats(n_mels));
+            build_inverse_mel_tc(inv_mel_host, p->kb, n_mels, tc.data());
+            rc = upload(&p->inv_mel_tc, tc);
+        }
     }
     if (rc == S2ST_OK && mel_host) {
         std::vector<int> ptr, idx;

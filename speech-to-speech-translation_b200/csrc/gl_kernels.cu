@@ -21,6 +21,8 @@
 // and zeroes the seams of buf[(i+1)%3] for the next pass.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "../../include/s2st_b200.h"
 #include "frame_fft.cuh"
 #include "plan.h"
@@ -496,6 +498,12 @@ int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* l
         return S2ST_EINVAL;
     }
     if (n_frames <= 0) return S2ST_OK;
+    // dense contraction -> tensor cores (tcgen05, 3xTF32) whenever the shape allows; S2ST_INVERSE_MEL=simt
+    // selects the FP32 SIMT kernel (kept for other shapes and for A/B checks)
+    const char* mode_env = getenv("S2ST_INVERSE_MEL");
+    const bool force_simt = mode_env && mode_env[0] == 's';
+    if (!force_simt && inverse_mel_tc_supported(plan) && ((uintptr_t)logmel & 15) == 0)
+        return launch_inverse_mel_tc(plan, n_frames, logmel, is_log, mag, out_stride, n_out, stream);
     const long long blocks = (n_frames + kImFrames - 1) / kImFrames;
     k_inverse_mel<<<(unsigned)blocks, 256, sizeof(float) * kImFrames * plan->n_mels, stream>>>(
         logmel, is_log, n_frames, plan->n_mels, plan->inv_mel_t, plan->kb, plan->kb_pad, mag, out_stride, n_out);

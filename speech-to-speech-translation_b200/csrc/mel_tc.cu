@@ -1,0 +1,235 @@
+// Inverse-mel projection on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+//   mag[t, f] = max(0, sum_m pinv[f, m] * g(mel[t, m]))      g = exp (vocoder.py:141) or identity (vocoder.py:42)
+//
+// is the one dense contraction of the synthesis path: D[M = frames, N = live bins] = A[M, K = n_mels] * B[N, K]^T.
+// The reference runs it as an fp32 matmul and the features must stay within ~1e-6, so single-pass TF32 (10-bit
+// mantissa) is not enough: operands are split into a TF32 head and tail (a = a_hi + a_lo, |a_lo| <= 2^-11 |a|)
+// and three MMAs are accumulated in fp32 in TMEM:  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (the dropped tail*tail
+// term is ~2^-22 relative).
+//
+// One CTA = 128 frames (UMMA M = 128, cta_group::1), 128 threads:
+//   - all threads: exp + hi/lo split of the A tile into shared memory in the canonical K-major, no-swizzle
+//     UMMA layout (8-row x 16-byte core matrices; SBO = 128 B between 8-row groups, LBO between 4-element
+//     K chunks);
+//   - per N chunk of 176 bins: copy the pre-split, pre-laid-out B chunk from global (L2 resident, built once
+//     by the plan), one elected thread issues 3 x (K / 8) tcgen05.mma kind::tf32 into a 176-column fp32
+//     accumulator in TMEM and commits to an mbarrier; then every thread reads its own row (TMEM lane) back
+//     with tcgen05.ld, clamps at zero and stores it.
+#include <stdint.h>
+
+#include <cstring>
+
+#include "../../include/s2st_b200.h"
+#include "plan.h"
+
+namespace s2st {
+
+namespace {
+
+constexpr int kTcM = 128;        // frames per CTA (UMMA M)
+constexpr int kTcNChunk = 176;   // bins per MMA (UMMA N, multiple of 16)
+constexpr int kTcChunks = 4;     // 4 * 176 = 704 >= live bins
+constexpr int kTcTmemCols = 256; // power of two >= kTcNChunk
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // SM100 shared-memory matrix descriptor: start address [0,14), LBO [16,30), SBO [32,46) (all >> 4),
+    // version 1 at [46,48), layout type 0 (no swizzle) at [61,64)
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// canonical K-major / no-swizzle offset (in floats) of element (row, k) of a tile with `groups` 8-row groups
+__host__ __device__ __forceinline__ int canon_off(int row, int k, int groups) {
+    return (((k >> 2) * groups + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
+}
+
+struct TcParams {
+    const float* mel;       // [n_frames, K]
+    const float* b_tc;      // [kTcChunks][2 (hi, lo)][K/4][kTcNChunk/8][8][4]
+    float* mag;             // [n_frames, out_stride]
+    long long n_frames;
+    int K, is_log, out_stride, n_out;
+};
+
+__global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int K = p.K, kc = K >> 2;                      // K chunks of 4 elements (16 bytes)
+    const int a_floats = kTcM * K, b_floats = kTcNChunk * K;
+    float* sA_hi = reinterpret_cast<float*>(smem_raw);
+    float* sA_lo = sA_hi + a_floats;
+    float* sB_hi = sA_lo + a_floats;
+    float* sB_lo = sB_hi + b_floats;
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long t0 = (long long)blockIdx.x * kTcM;
+    const int rows = (int)min((long long)kTcM, p.n_frames - t0);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTcTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // A tile: g(mel) split into TF32 head / tail, canonical layout.  The [rows, K] block is contiguous in global.
+    const float4* src = reinterpret_cast<const float4*>(p.mel + t0 * K);
+    for (int i = tid; i < kTcM * kc; i += 128) {
+        const int row = i / kc, c = i - row * kc;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows) {
+            v = src[i];
+            if (p.is_log) v = make_float4(expf(v.x), expf(v.y), expf(v.z), expf(v.w));
+        }
+        const float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        const int off = canon_off(row, 4 * c, kTcM / 8);
+        *reinterpret_cast<float4*>(sA_hi + off) = hi;
+        *reinterpret_cast<float4*>(sA_lo + off) = lo;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNChunk >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+    const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (kTcNChunk / 8) * 128, sbo = 128;
+    uint32_t phase = 0;
+
+    for (int chunk = 0; chunk < kTcChunks; ++chunk) {
+        // B chunk (head and tail are adjacent in global): straight 16-byte copies
+        const float4* bsrc = reinterpret_cast<const float4*>(p.b_tc + (size_t)chunk * 2 * b_floats);
+        float4* bdst = reinterpret_cast<float4*>(sB_hi);
+        for (int i = tid; i < 2 * b_floats / 4; i += 128) bdst[i] = __ldg(bsrc + i);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {
+                const uint32_t a_base = smem_u32(term == 2 ? sA_lo : sA_hi);
+                const uint32_t b_base = smem_u32(term == 1 ? sB_lo : sB_hi);
+                for (int ks = 0; ks < K / 8; ++ks) {
+                    mma_tf32(tmem, make_desc(a_base + ks * 2 * lbo_a, lbo_a, sbo),
+                             make_desc(b_base + ks * 2 * lbo_b, lbo_b, sbo), idesc, acc);
+                    acc = 1;
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+        }
+        mbar_wait(smem_u32(&s_bar), phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: thread tid owns row tid (TMEM lane tid); 16 columns per tcgen05.ld
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        float* orow = p.mag + (t0 + tid) * (long long)p.out_stride + chunk * kTcNChunk;
+        for (int c0 = 0; c0 < kTcNChunk; c0 += 16) {
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(lane_addr + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (tid < rows) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = chunk * kTcNChunk + c0 + j;
+                    if (col < p.n_out) orow[c0 + j] = fmaxf(__uint_as_float(r[j]), 0.0f);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // TMEM and the B buffers may be overwritten by the next chunk
+    }
+    // columns beyond the live bins are exactly zero
+    if (tid < rows)
+        for (int col = kTcChunks * kTcNChunk; col < p.n_out; ++col) p.mag[(t0 + tid) * (long long)p.out_stride + col] = 0.0f;
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
+}
+
+}  // namespace
+
+// Host: pre-split the pseudo-inverse basis into TF32 head / tail in the canonical per-chunk layout.
+// inv_mel [n_bins_total, K] row-major (K-major), rows >= kb are zero.
+void build_inverse_mel_tc(const float* inv_mel, int kb, int K, float* out /* kTcChunks*2*kTcNChunk*K */) {
+    const int b_floats = kTcNChunk * K;
+    for (int i = 0; i < kTcChunks * 2 * b_floats; ++i) out[i] = 0.0f;
+    for (int n = 0; n < kb && n < kTcChunks * kTcNChunk; ++n) {
+        const int chunk = n / kTcNChunk, row = n % kTcNChunk;
+        for (int k = 0; k < K; ++k) {
+            const float v = inv_mel[(size_t)n * K + k];
+            uint32_t u;
+            memcpy(&u, &v, 4);
+            // round to nearest, ties away (cvt.rna.tf32.f32): add half an ulp of the 13 dropped bits, truncate
+            uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+            if ((u & 0x7F800000u) == 0x7F800000u) h = u;  // inf / nan untouched
+            float hi;
+            memcpy(&hi, &h, 4);
+            const float lo = v - hi;
+            const int off = canon_off(row, k, kTcNChunk / 8);
+            out[(size_t)(chunk * 2 + 0) * b_floats + off] = hi;
+            out[(size_t)(chunk * 2 + 1) * b_floats + off] = lo;
+        }
+    }
+}
+
+size_t inverse_mel_tc_floats(int K) { return (size_t)kTcChunks * 2 * kTcNChunk * K; }
+
+bool inverse_mel_tc_supported(const s2st_plan* plan) {
+    return plan->inv_mel_tc != nullptr && plan->kb <= kTcChunks * kTcNChunk && plan->n_mels % 8 == 0 && plan->n_mels <= 80;
+}
+
+int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float* mel, bool is_log, float* mag,
+                          int out_stride, int n_out, cudaStream_t stream) {
+    if (n_frames <= 0) return S2ST_OK;
+    TcParams p;
+    p.mel = mel;
+    p.b_tc = plan->inv_mel_tc;
+    p.mag = mag;
+    p.n_frames = n_frames;
+    p.K = plan->n_mels;
+    p.is_log = is_log ? 1 : 0;
+    p.out_stride = out_stride;
+    p.n_out = n_out;
+    const size_t smem = sizeof(float) * (size_t)(2 * kTcM * p.K + 2 * kTcNChunk * p.K) + 1024;
+    S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_inverse_mel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long blocks = (n_frames + kTcM - 1) / kTcM;
+    k_inverse_mel_tc<<<(unsigned)blocks, 128, smem, stream>>>(p);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
+
+}  // namespace s2st

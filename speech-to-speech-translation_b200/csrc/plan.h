@@ -19,6 +19,7 @@ struct s2st_plan {
     float2* tw;
     float2* vtab;
     float* inv_mel_t;   // [n_mels, kb_pad] transposed pseudo-inverse (NULL if absent)
+    float* inv_mel_tc;  // the same basis pre-split into TF32 head / tail in UMMA layout (mel_tc.cu), or NULL
     int* mel_ptr;       // CSR of the mel filterbank: [n_mels + 1]
     int* mel_idx;       // [nnz] bin indices, ascending per row
     float* mel_val;     // [nnz]
@@ -54,6 +55,13 @@ int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* l
                        int out_stride, int n_out, cudaStream_t stream);
 int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* out, bool inverse,
                     cudaStream_t stream);
+
+// mel_tc.cu (tcgen05 tensor-core path of the inverse-mel projection)
+void build_inverse_mel_tc(const float* inv_mel, int kb, int K, float* out);
+size_t inverse_mel_tc_floats(int K);
+bool inverse_mel_tc_supported(const s2st_plan* plan);
+int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float* mel, bool is_log, float* mag,
+                          int out_stride, int n_out, cudaStream_t stream);
 
 // frontend_kernels.cu
 int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const int64_t* wave_offsets,

@@ -101,6 +101,29 @@ def test_inverse_mel_matches_oracle(pkg, voc, basis):
     assert ogl.rel_l2(s, ref) < 2e-6
 
 
+def test_inverse_mel_tensor_core_vs_simt_vs_oracle(pkg, voc, basis, monkeypatch):
+    """tcgen05 3xTF32 path against the FP32 SIMT kernel and the oracle, incl. a ragged last 128-frame tile."""
+    import os
+    plan = voc._plan(torch.device("cuda", 0))
+    for n in (1, 127, 128, 300):
+        x = torch.cat([synth_logmel(n, 50 + n), ]).cuda()
+        outs = {}
+        for mode in ("simt", "tc"):
+            monkeypatch.setenv("S2ST_INVERSE_MEL", mode)
+            out = torch.full((n, 1025), -1.0, device="cuda")
+            rc = pkg._lib.load().s2st_inverse_mel(plan.handle, n, pkg._lib.ptr(x), 1, pkg._lib.ptr(out),
+                                                  pkg._lib.stream_ptr(x.device))
+            pkg._lib.check(rc, "s2st_inverse_mel")
+            torch.cuda.synchronize()
+            outs[mode] = out.cpu().numpy()
+        monkeypatch.delenv("S2ST_INVERSE_MEL")
+        ref = ogl.inverse_mel(x.cpu().numpy(), basis).T
+        for mode in ("simt", "tc"):
+            assert np.all(outs[mode] >= 0) and np.all(outs[mode][:, 683:] == 0)
+            assert ogl.rel_l2(outs[mode], ref) < 2e-6, mode
+        assert ogl.rel_l2(outs["tc"], outs["simt"]) < 2e-6
+
+
 @pytest.mark.parametrize("case", ["c0", "c1", "c2", "c3"])
 def test_forward_matches_reference_golden(pkg, voc, basis, case):
     """Drop-in forward(): consumes numpy's global RNG like the reference, so seeding reproduces its output."""
