@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
     const int hop = p.hop, ws = p.ws;
     const int kb = PRUNED ? min(p.kb, 32 * kPrunedRows) : p.kb;
     // fast paths need 16-byte friendly geometry (true for hop 300 / win 1200 / n_fft 2048)
-    const bool geom4 = (hop % 4 == 0) && (ws % hop == 0) && ((p.rot - p.half) % 4 == 0);
+    const bool geom4 = (hop % 4 == 0) && (hop >= 64) && (ws % hop == 0) && ((p.rot - p.half) % 4 == 0);
 
     for (int strip = blockIdx.x * kGlWarps + warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
         const TileDesc td = p.tiles[strip];
@@ -159,10 +159,8 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                     // target magnitudes: requested now, the forward transform hides their latency
                     if constexpr (PRUNED) {
 #pragma unroll
-                        for (int r = 0; r < kPrunedRows; ++r) {
-                            const int k = 32 * r + lane;
-                            mg[r] = (k < kb) ? __ldg(magrow + k) : 0.0f;
-                        }
+                        for (int r = 0; r < kPrunedRows; ++r)
+                            mg[r] = (32 * r < p.mag_stride) ? __ldg(magrow + 32 * r + lane) : 0.0f;  // uniform test
                     }
                 }
                 // pass 0: analysis (frame -> spectrum -> re-imposed magnitude); pass 1: synthesis.  The
@@ -204,9 +202,12 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                                 else m = (k < kb) ? __ldg(magrow + k) : 0.0f;
                                 const float x = a[r].x, yy = a[r].y;
                                 const float r2 = fmaf(x, x, yy * yy);
-                                const float sc = m * rsqrtf(r2);
-                                // |X| == 0: atan2(0, +-0) = 0 / pi  ->  (+-mag, 0)
-                                a[r] = r2 > 0.0f ? make_float2(x * sc, yy * sc) : make_float2(copysignf(m, x), 0.0f);
+                                float rs;
+                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
+                                const float sc = m * rs;
+                                // |X|^2 below the normal range counts as |X| == 0, where the reference's
+                                // atan2(0, +-0) = 0 / pi gives (+-mag, 0)
+                                a[r] = r2 >= 1.1754944e-38f ? make_float2(x * sc, yy * sc) : make_float2(copysignf(m, x), 0.0f);
                             }
                             if (kb > 1024) ynyq = copysignf(__ldg(magrow + 1024), nyq);
                         }
@@ -216,23 +217,38 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                 // a[] holds the synthesis frame with the parts swapped (.y = even sample, .x = odd sample):
                 // window and overlap-add into the private ring
                 const float* w = s_win_s + 2 * lane;
+                if (geom4) {
+                    // samples past the window support have zero weight: they wrap onto a live slot and add
+                    // +0, so every row can accumulate without a bounds test (slots stay even -> 8-byte RMW)
+                    const int first = slot0 + 2 * lane;
+                    const int until_wrap = ws - first;  // rows with 64 r >= until_wrap wrap around once
 #pragma unroll
-                for (int r = 0; r < NZ; ++r) {
-                    const int m = 64 * r + 2 * lane;
-                    if (m < ws) {
-                        int slot = slot0 + m;
-                        if (slot >= ws) slot -= ws;
-                        if (geom4) {
-                            float2 o = *reinterpret_cast<float2*>(ring + slot);
-                            const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
-                            o.x = fmaf(a[r].y, ww.x, o.x);
-                            o.y = fmaf(a[r].x, ww.y, o.y);
-                            *reinterpret_cast<float2*>(ring + slot) = o;
-                        } else {
+                    for (int r = 0; r < NZ; ++r) {
+                        float* dst = ring + first + 64 * r - (64 * r >= until_wrap ? ws : 0);
+                        float2 o = *reinterpret_cast<float2*>(dst);
+                        const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
+                        o.x = fmaf(a[r].y, ww.x, o.x);
+                        o.y = fmaf(a[r].x, ww.y, o.y);
+                        *reinterpret_cast<float2*>(dst) = o;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < NZ; ++r) {
+                        float ex = 0.0f, ey = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < NZ; ++q)
+                            if (q == r) {
+                                ex = a[q].y;
+                                ey = a[q].x;
+                            }
+                        const int m = 64 * r + 2 * lane;
+                        if (m < ws) {
+                            int slot = slot0 + m;
+                            while (slot >= ws) slot -= ws;
                             int slot1 = slot + 1;
                             if (slot1 >= ws) slot1 -= ws;
-                            ring[slot] = fmaf(a[r].y, w[64 * r], ring[slot]);
-                            ring[slot1] = fmaf(a[r].x, w[64 * r + 1], ring[slot1]);
+                            ring[slot] = fmaf(ex, w[64 * r], ring[slot]);
+                            if (m + 1 < ws) ring[slot1] = fmaf(ey, w[64 * r + 1], ring[slot1]);
                         }
                     }
                 }
@@ -430,7 +446,7 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
     };
     w.max_tiles = total_frames / kMinStrip + n_utts;
     w.wave_samples = (total_frames - n_utts) * (long long)plan->hop;
-    w.mag_stride = (int)align_up((size_t)plan->kb, 4);
+    w.mag_stride = (int)align_up((size_t)plan->kb, 32);  // zero padded: row loads need no bounds test
     w.utts = reinterpret_cast<UttDesc*>(take(sizeof(UttDesc) * (size_t)n_utts));
     w.tiles = reinterpret_cast<TileDesc*>(take(sizeof(TileDesc) * (size_t)w.max_tiles));
     w.n_tiles = reinterpret_cast<int*>(take(sizeof(int)));
