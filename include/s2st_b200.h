@@ -69,7 +69,9 @@ int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
  *                   vocoder.py:102, transposed to frame-major), or NULL when logmel_dev is given
  *   init_phase_dev  [total_frames, n_fft/2+1] initial phase in radians, frame-major.  The
  *                   reference draws it from numpy's global RNG on the host (vocoder.py:103-104);
- *                   the host shim does the same and uploads it.
+ *                   the host shim does the same and uploads it.  NULL: the library draws
+ *                   phi ~ U[-pi, pi) on the device from a counter-based generator keyed by
+ *                   phase_seed (same distribution, not numpy's stream; for throughput runs).
  *   n_iter          spec_bwd_max_iter (n_iter forward + n_iter+1 inverse transforms)
  *   wave_out_dev    concatenated waveforms, (total_frames - B) * hop floats
  * Every utterance must have T >= 1; when n_iter > 0, (T-1)*hop must exceed n_fft/2 (the
@@ -78,7 +80,7 @@ int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_fra
 int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
                        const int32_t* frame_offsets_dev, const int32_t* frame_offsets_host,
                        const float* logmel_dev,
-                       const float* mag_dev, const float* init_phase_dev, int n_iter,
+                       const float* mag_dev, const float* init_phase_dev, uint64_t phase_seed, int n_iter,
                        float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream);
 /* Profiling aid (not part of the reference's interface): when enabled, s2st_gl_synthesize / s2st_istft

@@ -296,10 +296,10 @@ int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_fra
 
 int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
                        const int32_t* frame_offsets_dev, const int32_t* frame_offsets_host, const float* logmel_dev,
-                       const float* mag_dev, const float* init_phase_dev, int n_iter,
+                       const float* mag_dev, const float* init_phase_dev, uint64_t phase_seed, int n_iter,
                        float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream) {
-    if (!plan || !frame_offsets_dev || !init_phase_dev || !wave_out_dev || n_iter < 0 ||
+    if (!plan || !frame_offsets_dev || !wave_out_dev || n_iter < 0 ||
         ((logmel_dev == nullptr) == (mag_dev == nullptr))) {
         set_error("bad argument to s2st_gl_synthesize (exactly one of logmel / mag must be given)");
         return S2ST_EINVAL;
@@ -307,7 +307,7 @@ int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
     int rc = check_gl_geometry(plan);
     if (rc != S2ST_OK) return rc;
     return gl_run(plan, n_utts, total_frames, frame_offsets_dev, frame_offsets_host, logmel_dev, mag_dev, kBins,
-                  init_phase_dev, n_iter, wave_out_dev, workspace_dev, workspace_bytes,
+                  init_phase_dev, phase_seed, n_iter, wave_out_dev, workspace_dev, workspace_bytes,
                   static_cast<cudaStream_t>(stream));
 }
 
@@ -360,7 +360,7 @@ int s2st_istft(const s2st_plan* plan, int n_utts, int64_t total_frames, const in
     }
     int rc = check_gl_geometry(plan);
     if (rc != S2ST_OK) return rc;
-    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, nullptr, nullptr, mag_dev, kBins, phase_dev, 0,
+    return gl_run(plan, n_utts, total_frames, frame_offsets_dev, nullptr, nullptr, mag_dev, kBins, phase_dev, 0ull, 0,
                   wave_out_dev, workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

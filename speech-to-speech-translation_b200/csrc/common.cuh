@@ -47,7 +47,8 @@ struct GlParams {
     const int* n_tiles;
     // data
     const float* mag;        // [total_frames, mag_stride]
-    const float* phase;      // [total_frames, phase_stride] (first pass only)
+    const float* phase;      // [total_frames, phase_stride] (first pass only); NULL -> device RNG
+    unsigned long long phase_seed;
     const float* in;         // normalised waveforms written by the previous pass
     float* out;              // waveforms written by this pass (seams pre-zeroed)
     float* zero_next;        // buffer the NEXT pass writes: this pass zeroes its seams

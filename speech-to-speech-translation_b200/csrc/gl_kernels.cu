@@ -34,6 +34,16 @@ namespace {
 constexpr float kTiny = 1.1754944e-38f;  // vocoder.py:69
 constexpr int kGlWarps = kGlThreads / 32;
 
+// Counter-based uniform in [0, 1) for the device-side initial phase (used when the caller passes no phase):
+// two rounds of a 64-bit mix (splitmix64 finaliser) of (seed, element index); 24 random bits.
+__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+}
+
 // Frame load, cold path: reflect padding (audio_utils.py:262-263) at utterance edges / unaligned data.
 template <int NZ>
 __device__ __forceinline__ void load_frame_edge(float2 (&a)[32], const float* __restrict__ y, int j, int L) {
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
         const float* y = p.in + ud.wave_off;
         const bool aligned = geom4 && ((ud.wave_off & 3) == 0);
         const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0) * p.mag_stride;
-        const float* phrow = FIRST ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
+        const float* phrow = (FIRST && p.phase) ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
 
         float2 a[32];
         int slot0 = 0;  // ring slot of strip-relative sample f * hop
@@ -175,7 +185,12 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                                 if (k < kb) {
                                     const float m = __ldg(magrow + k);
                                     float sn, cs, rs, rc;
-                                    sincosf(__ldg(phrow + k), &sn, &cs);
+                                    if (p.phase) {
+                                        sincosf(__ldg(phrow + k), &sn, &cs);
+                                    } else {  // phi = 2 pi u - pi, u ~ U[0, 1): same law as vocoder.py:103
+                                        const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + k;
+                                        sincospif(2.0f * uniform01(p.phase_seed, e) - 1.0f, &sn, &cs);
+                                    }
                                     // the caller's phase refers to the un-rotated frame; frames are processed
                                     // rotated by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048)
                                     sincospif((float)((k * p.rot) & 2047) * (1.0f / 1024.0f), &rs, &rc);
@@ -184,8 +199,11 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                                     a[r] = make_float2(0.0f, 0.0f);
                                 }
                             }
-                            if (kb > 1024) ynyq = __ldg(magrow + 1024) * cosf(__ldg(phrow + 1024));
-                            phrow += p.phase_stride;
+                            if (kb > 1024) {
+                                const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + 1024;
+                                ynyq = __ldg(magrow + 1024) * (p.phase ? cosf(__ldg(phrow + 1024)) : cospif(2.0f * uniform01(p.phase_seed, e) - 1.0f));
+                            }
+                            if (p.phase) phrow += p.phase_stride;
                         }
                         inv_merge<PRUNED, true>(a, ynyq, scratch, s_vtab, lane);
                     }
@@ -544,8 +562,9 @@ int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* 
 }
 
 int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const int32_t* frame_offsets,
-           const int32_t* frame_offsets_host, const float* logmel, const float* mag, int mag_kb, const float* phase, int n_iter,
-           float* wave_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+           const int32_t* frame_offsets_host, const float* logmel, const float* mag, int mag_kb, const float* phase,
+           unsigned long long phase_seed, int n_iter, float* wave_out, void* workspace, size_t workspace_bytes,
+           cudaStream_t stream) {
     s2st_plan* plan = const_cast<s2st_plan*>(plan_c);  // only the profiling state is mutated
     if (n_utts <= 0 || total_frames < n_utts) {
         set_error("bad batch: n_utts=%d total_frames=%lld", n_utts, total_frames);
@@ -580,6 +599,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     p.tiles = w.tiles;
     p.n_tiles = w.n_tiles;
     p.phase = phase;
+    p.phase_seed = phase_seed;
     p.phase_stride = kBins;
     if (logmel) {
         int rc = launch_inverse_mel(plan, total_frames, logmel, true, w.mag, w.mag_stride, w.mag_stride, stream);

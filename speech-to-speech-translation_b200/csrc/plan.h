@@ -49,8 +49,9 @@ namespace s2st {
 // gl_kernels.cu
 size_t gl_workspace_bytes(const s2st_plan* plan, int n_utts, long long total_frames);
 int gl_run(const s2st_plan* plan, int n_utts, long long total_frames, const int32_t* frame_offsets,
-           const int32_t* frame_offsets_host, const float* logmel, const float* mag, int mag_kb, const float* phase, int n_iter,
-           float* wave_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+           const int32_t* frame_offsets_host, const float* logmel, const float* mag, int mag_kb, const float* phase,
+           unsigned long long phase_seed, int n_iter, float* wave_out, void* workspace, size_t workspace_bytes,
+           cudaStream_t stream);
 int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* logmel, bool is_log, float* mag,
                        int out_stride, int n_out, cudaStream_t stream);
 int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* out, bool inverse,

@@ -90,7 +90,7 @@ class GriffinLim(torch.nn.Module):
         ws = plan.workspace(n_utts, total)
         with torch.cuda.device(dev):
             rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo), fo_h.ctypes.data, None, _lib.ptr(mag_fm),
-                                                _lib.ptr(phase_fm), n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
+                                                _lib.ptr(phase_fm), 0, n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_ptr(dev))
         _lib.check(rc, "s2st_gl_synthesize")
         return wave
@@ -188,7 +188,7 @@ class GriffinLimVocoder(nn.Module):
                    window_fn=window_fn, spec_bwd_max_iter=args.spec_bwd_max_iter, fp16=args.fp16)
 
     # -- the data-parallel entry ----------------------------------------------------------------
-    def _synthesize_flat(self, logmel_flat, frames: Sequence[int], phase_fm, n_iter, dev):
+    def _synthesize_flat(self, logmel_flat, frames: Sequence[int], phase_fm, n_iter, dev, seed=0):
         plan = self._plan(dev)
         n_utts, total = len(frames), int(sum(frames))
         fo = np.zeros(n_utts + 1, np.int32)
@@ -201,7 +201,7 @@ class GriffinLimVocoder(nn.Module):
         ws = plan.workspace(n_utts, total)
         with torch.cuda.device(dev):
             rc = _lib.load().s2st_gl_synthesize(plan.handle, n_utts, total, _lib.ptr(fo_d), fo.ctypes.data, _lib.ptr(logmel_flat), None,
-                                                _lib.ptr(phase_fm), n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
+                                                _lib.ptr(phase_fm), int(seed) & 0xFFFFFFFFFFFFFFFF, n_iter, _lib.ptr(wave), _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_ptr(dev))
         _lib.check(rc, "s2st_gl_synthesize")
         return wave
@@ -238,14 +238,21 @@ class GriffinLimVocoder(nn.Module):
         lens = [(T - 1) * g.hop_length for T in frames]
         return list(torch.split(wave, lens))
 
-    def synthesize_flat(self, logmel_flat: torch.Tensor, frames: Sequence[int], phase_fm: torch.Tensor,
-                        n_iter: Optional[int] = None) -> torch.Tensor:
+    def synthesize_flat(self, logmel_flat: torch.Tensor, frames: Sequence[int], phase_fm: Optional[torch.Tensor],
+                        n_iter: Optional[int] = None, seed: int = 0) -> torch.Tensor:
         """Lowest-overhead entry: everything already resident and frame-major on one CUDA device:
-        logmel_flat [sum T, n_mels], phase_fm [sum T, F] -> concatenated waveforms [sum (T_i-1)*hop]."""
+        logmel_flat [sum T, n_mels], phase_fm [sum T, F] -> concatenated waveforms [sum (T_i-1)*hop].
+        phase_fm=None draws the initial phase on the device (U[-pi, pi), counter-based generator keyed by
+        ``seed``): same distribution as the reference's numpy draw, no 4 KB/frame upload."""
         n_iter = self.gl_transform.n_iter if n_iter is None else n_iter
         dev = require_cuda(logmel_flat.device)
-        assert logmel_flat.is_cuda and phase_fm.is_cuda and logmel_flat.dtype == phase_fm.dtype == torch.float32
-        return self._synthesize_flat(logmel_flat.contiguous(), frames, phase_fm.contiguous(), n_iter, dev)
+        assert logmel_flat.is_cuda and logmel_flat.dtype == torch.float32
+        if phase_fm is not None:
+            assert phase_fm.is_cuda and phase_fm.dtype == torch.float32
+            phase_fm = phase_fm.contiguous()
+        for T in frames:
+            _check_length(T, self.gl_transform.hop_length, self.gl_transform.n_fft, n_iter)
+        return self._synthesize_flat(logmel_flat.contiguous(), frames, phase_fm, n_iter, dev, seed)
 
 
 def get_vocoder(args, data_cfg):

@@ -205,6 +205,33 @@ def test_full_size_properties_long_form(pkg, voc, basis):
     assert sc[0] > sc[1] > sc[2]
 
 
+def test_device_drawn_initial_phase(pkg, voc, basis):
+    """phase_fm=None: U[-pi, pi) drawn on the device.  Deterministic per seed, different across seeds, and
+    statistically equivalent to the host draw: same spectral convergence after the iterations (it is a
+    different random start, so waveforms are not compared sample by sample)."""
+    frames = [60, 75, 133]
+    feats = [synth_logmel(T, 300 + i) for i, T in enumerate(frames)]
+    flat = torch.cat(feats).cuda()
+    a = voc.synthesize_flat(flat, frames, None, n_iter=32, seed=7)
+    b = voc.synthesize_flat(flat, frames, None, n_iter=32, seed=7)
+    c = voc.synthesize_flat(flat, frames, None, n_iter=32, seed=8)
+    assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
+    host = voc.synthesize_batch([f.cuda() for f in feats], init_phase=[seeded_phase(40 + i, T) for i, T in enumerate(frames)], n_iter=32)
+    off = 0
+    for f, T, h in zip(feats, frames, host):
+        L = (T - 1) * 300
+        mag = ogl.inverse_mel(f.numpy(), basis)
+        sc_dev = ogl.spectral_convergence(a[off: off + L].cpu().numpy(), mag, **CFG)
+        sc_host = ogl.spectral_convergence(h.cpu().numpy(), mag, **CFG)
+        assert abs(sc_dev - sc_host) < 0.25 * sc_host, (sc_dev, sc_host)  # two random starts: same ballpark
+        off += L
+    # the n_iter = 0 output has the statistics of a uniform phase: compare its energy with the host draw's
+    e_dev = float(voc.synthesize_flat(flat, frames, None, n_iter=0, seed=3).pow(2).mean())
+    ph = torch.from_numpy(np.concatenate([seeded_phase(60 + i, T).T for i, T in enumerate(frames)])).cuda()
+    e_host = float(voc.synthesize_flat(flat, frames, ph.contiguous(), n_iter=0).pow(2).mean())
+    assert abs(e_dev - e_host) < 0.1 * e_host
+
+
 def test_half_precision_io(pkg, voc):
     x = synth_logmel(20, 3).cuda()
     voc.gl_transform.n_iter = 2
