@@ -59,18 +59,16 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU through NVML from a thread of this process
-    (equivalent to the nvidia-smi --query-gpu clocks line, without a polling subprocess)."""
+    """SM clock and throttle reasons of one GPU through NVML (what the nvidia-smi --query-gpu clocks line
+    reports).  sample() is called by the benchmark loop itself between steps of the timed region, while
+    the GPU still has a deep queue of launches -- a polling thread or subprocess was measurably delaying
+    kernel launches on this driver."""
 
-    def __init__(self, gpu_index, period_s=0.25):
-        import threading
-        self.samples, self.reasons, self.err = [], set(), None
-        self.sm_max = None
-        self._stop = threading.Event()
+    def __init__(self, gpu_index):
+        self.samples, self.reasons, self.err, self.sm_max = [], set(), None, None
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = gpu_index
             if vis:
@@ -82,39 +80,30 @@ class ClockSampler:
             self.nv = pynvml
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception as e:  # noqa: BLE001
-            self.err = repr(e)
-            self.nv = None
-            return
-        self.period = period_s
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+            self.err, self.nv = repr(e), None
 
-    def _run(self):
+    def sample(self):
         nv = self.nv
-        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
-                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
-                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for n, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(n)
-            except Exception as e:  # noqa: BLE001
-                self.err = repr(e)
-                return
-            self._stop.wait(self.period)
+        if nv is None:
+            return
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for n, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                           ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                           ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                           ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+                if mask & bit:
+                    self.reasons.add(n)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self):
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
-        self._stop.set()
-        self.t.join(2)
         sm = self.samples
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
-                "reasons": sorted(self.reasons), "source": "NVML, sampled in-process during the timed region"}
+                "reasons": sorted(self.reasons), "source": "NVML, sampled between steps inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,8 +223,10 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_CLOCKS")) else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for step in range(args.steps):
         wave_d = voc.synthesize_flat(logmel_d, frames, phase_d)
+        if sampler and step % 8 == 4:  # the GPU is several steps behind the host here: it stays busy
+            sampler.sample()
     ev1.record()
     barrier()
     clocks = sampler.stop() if sampler else None

@@ -16,10 +16,15 @@ struct UttDesc {
     int n_frames;        // T
 };
 
+// One strip = nf consecutive frames of one utterance, with everything a warp needs to run it (32 bytes,
+// fetched with two 16-byte loads, no dependent lookup).
 struct TileDesc {
-    int utt;  // utterance index
-    int f0;   // first frame (utterance-local) of the strip
-    int nf;   // frames in the strip (1..S)
+    long long wave_off;  // first sample of the utterance in the concatenated waveform buffers
+    int frame_off;       // first row of the utterance in the frame-major tensors
+    int n_frames;        // T of the utterance
+    int f0;              // first frame (utterance-local) of the strip
+    int nf;              // frames in the strip (1..S)
+    int utt;             // utterance index
     int pad;
 };
 

@@ -138,7 +138,10 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
 
     for (int strip = blockIdx.x * kGlWarps + warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
         const TileDesc td = p.tiles[strip];
-        const UttDesc ud = p.utts[td.utt];
+        UttDesc ud;
+        ud.wave_off = td.wave_off;
+        ud.frame_off = td.frame_off;
+        ud.n_frames = td.n_frames;
         const int T = ud.n_frames, L = (T - 1) * hop;
         const int j_base = td.f0 * hop + p.rot - p.half;  // output sample index of strip-relative sample 0
         float* out = p.out + ud.wave_off;
@@ -352,6 +355,9 @@ __global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict_
             utts[u] = d;
             for (int k = 0; k < nt; ++k) {
                 TileDesc t;
+                t.wave_off = d.wave_off;
+                t.frame_off = d.frame_off;
+                t.n_frames = T;
                 t.utt = u;
                 t.f0 = k * S;
                 t.nf = min(S, T - k * S);
