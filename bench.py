@@ -51,6 +51,21 @@ def synth_logmel_np(T, seed):
     return np.clip(x, np.log(1e-5), 2.0).astype(np.float32)
 
 
+def measured_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_pass launch on this workload, from the
+    committed `ncu --set full` capture (profiles/r01_glpass_final_ncu_summary.txt); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_glpass_final_ncu_summary.txt")
+    try:
+        tot = 0.0
+        for line in open(path):
+            if line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum"):
+                val, unit = line.split("=")[1].split()[:2]
+                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot or None
+    except (OSError, KeyError, ValueError, IndexError):
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -313,7 +328,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_gl_pass<19,false> (fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
+                     "traffic": measured_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
                      "launch_ms": iter_ms, "launches_per_step": N_ITER,
                      "share_of_step": float(np.sum(last_pass_ms[1:]) / ms_step) if len(last_pass_ms) > 1 else None,
                      "first_pass_ms": float(last_pass_ms[0])},
