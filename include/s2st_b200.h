@@ -83,6 +83,12 @@ int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
                        const float* mag_dev, const float* init_phase_dev, uint64_t phase_seed, int n_iter,
                        float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream);
+/* Work decomposition of the Griffin-Lim kernel: a "strip" of `frames` consecutive frames is run by one warp.
+ * 0 (default) lets every call pick the length that fills the GPU best for that batch.  Results are bitwise
+ * reproducible for a given batch either way; pinning the length additionally makes each utterance's waveform
+ * bitwise independent of what else is in the batch (the few samples shared by two strips are rounded slightly
+ * differently from the others, so moving strip boundaries moves last-bit differences). */
+int s2st_plan_set_strip_frames(s2st_plan* plan, int frames);
 /* Profiling aid (not part of the reference's interface): when enabled, s2st_gl_synthesize / s2st_istft
  * record a CUDA event on the caller's stream before every Griffin-Lim pass and after the last one;
  * s2st_plan_get_pass_times waits for the last event and returns the device time of each pass of the

@@ -32,6 +32,7 @@ SIGNATURES = {
     "s2st_gl_synthesize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "s2st_plan_set_strip_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "s2st_plan_set_pass_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "s2st_plan_get_pass_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_int)]),

@@ -249,6 +249,15 @@ int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out) {
     return S2ST_OK;
 }
 
+int s2st_plan_set_strip_frames(s2st_plan* plan, int frames) {
+    if (!plan || frames < 0 || frames > 4096) {
+        set_error("bad argument to s2st_plan_set_strip_frames");
+        return S2ST_EINVAL;
+    }
+    plan->strip_frames = frames;
+    return S2ST_OK;
+}
+
 int s2st_plan_set_pass_timing(s2st_plan* plan, int enabled) {
     if (!plan) {
         set_error("null plan");

@@ -584,7 +584,9 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
         return S2ST_EWORKSPACE;
     }
     if (w.wave_samples <= 0) return S2ST_OK;  // every utterance has a single frame: nothing to write
-    const int S = choose_strip(plan, n_utts, total_frames, frame_offsets_host);
+    const int s_floor = plan->nphase > kMinStrip ? plan->nphase : kMinStrip;
+    const int S = plan->strip_frames > 0 ? (plan->strip_frames < s_floor ? s_floor : plan->strip_frames)
+                                         : choose_strip(plan, n_utts, total_frames, frame_offsets_host);
     k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, S, w.utts, w.tiles, w.n_tiles);
     S2ST_CUDA_CHECK(cudaGetLastError());
 
@@ -619,7 +621,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
         p.kb = mag_kb;
     }
     const size_t smem = gl_pass_smem(plan);
-    const long long strips_ub = total_frames / S + n_utts;
+    const long long strips_ub = total_frames / S + n_utts;  // <= w.max_tiles because S >= kMinStrip
     const int grid = (int)min((long long)plan->num_sms * 2, (strips_ub + kGlWarps - 1) / kGlWarps);
     const bool pruned = p.kb <= 32 * kPrunedRows;
     // three rotating waveform buffers; the one the last pass writes is the caller's output

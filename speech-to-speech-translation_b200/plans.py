@@ -76,6 +76,10 @@ class StftPlan:
                    "s2st_gl_launch_count")
         return n.value
 
+    def set_strip_frames(self, frames):
+        """0 = automatic strip length per call; > 0 pins it (bitwise batch-invariant results)."""
+        _lib.check(_lib.load().s2st_plan_set_strip_frames(self.handle, int(frames)), "s2st_plan_set_strip_frames")
+
     def set_pass_timing(self, enabled):
         _lib.check(_lib.load().s2st_plan_set_pass_timing(self.handle, int(enabled)), "s2st_plan_set_pass_timing")
 

@@ -154,8 +154,33 @@ def test_batched_dense_forward_matches_reference(pkg, voc):
         assert ogl.rel_l2(y[b].cpu().numpy(), g["wave"][b]) < 1e-3
 
 
+def test_batch_invariance_with_pinned_and_automatic_strips(pkg, voc, basis):
+    """With a pinned strip length an utterance's waveform is bitwise independent of the rest of the batch;
+    with the automatic choice (which depends on the batch) it moves by rounding noise only."""
+    plan = voc._plan(torch.device("cuda", 0))
+    frames = [300, 301, 64, 400] + [200] * 60
+    feats = [synth_logmel(T, 500 + i) for i, T in enumerate(frames)]
+    phases = [seeded_phase(600 + i, T) for i, T in enumerate(frames)]
+    cu = [f.cuda() for f in feats]
+    try:
+        plan.set_strip_frames(12)
+        full = voc.synthesize_batch(cu, init_phase=phases, n_iter=16)
+        for i in (0, 1, 3):
+            alone = voc.synthesize_batch([cu[i]], init_phase=[phases[i]], n_iter=16)[0]
+            assert torch.equal(alone, full[i])
+    finally:
+        plan.set_strip_frames(0)
+    auto_full = voc.synthesize_batch(cu, init_phase=phases, n_iter=16)
+    auto_alone = voc.synthesize_batch([cu[3]], init_phase=[phases[3]], n_iter=16)[0]
+    assert ogl.rel_l2(auto_alone.cpu().numpy(), auto_full[3].cpu().numpy()) < 1e-4
+    assert ogl.rel_l2(auto_full[3].cpu().numpy(), full[3].cpu().numpy()) < 1e-4
+    ref = ogl.vocoder_forward(feats[3].numpy(), phases[3], 16, basis=basis)
+    assert ogl.rel_l2(auto_full[3].cpu().numpy(), ref) < 1e-3
+
+
 def test_ragged_batch_equals_per_utterance_and_oracle(pkg, voc, basis):
-    """The data-parallel entry: ragged lengths incl. tile-boundary cases; bitwise equal to one-at-a-time."""
+    """The data-parallel entry: ragged lengths incl. strip-boundary cases; these small batches all get the same
+    (minimum) strip length, so they are also bitwise equal to one-at-a-time runs."""
     frames = [5, 8, 9, 31, 56, 64, 65, 100]
     feats = [synth_logmel(T, 100 + i, "smooth" if i % 2 else "iid") for i, T in enumerate(frames)]
     phases = [seeded_phase(200 + i, T) for i, T in enumerate(frames)]
