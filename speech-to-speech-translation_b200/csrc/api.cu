@@ -161,7 +161,8 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         int imax = -1;
         for (int i = 0; r + i * hop_length < p->ws; ++i) imax = i;
         for (int i = imax; i >= 0; --i) acc += w2[r + i * hop_length];
-        inv_wss[r] = acc > 1.1754944e-38f ? (float)(1.0 / (double)acc) : 1.0f;
+        // 1 / n_fft (the inverse transform's scale, a power of two) is folded in here
+        inv_wss[r] = (acc > 1.1754944e-38f ? (float)(1.0 / (double)acc) : 1.0f) / (float)n_fft;
     }
     std::vector<float2> tw(1024), vtab(1024);
     const double pi = 3.14159265358979323846;

@@ -8,7 +8,7 @@ namespace s2st {
 constexpr int kNfft = 2048;
 constexpr int kBins = kNfft / 2 + 1;  // 1025
 constexpr int kMinStrip = 4;          // shortest strip (frames a warp runs in sequence); must cover the overlap
-constexpr int kGlThreads = 256;       // 8 warps per CTA, 2 CTAs per SM
+constexpr int kGlThreads = 512;       // 16 warps per CTA, 1 CTA per SM (128 registers per thread = the whole file)
 
 struct UttDesc {
     long long wave_off;  // first sample of this utterance in the concatenated waveform buffers
@@ -40,10 +40,10 @@ struct GlParams {
     int kb;        // bins >= kb have zero target magnitude
     int mag_stride, phase_stride;
     // constants (device global memory, owned by the plan)
-    const float* win_a;      // [wp] analysis window, rotated
-    const float* win_s;      // [wp] synthesis window / n_fft, rotated
+    const float* win_a;      // [wp] window, rotated (analysis and synthesis; 1 / n_fft is folded into inv_wss)
     const float* w2;         // [ws] squared window, rotated (edge window-sum-square)
-    const float* inv_wss;    // [hop] 1 / steady-state window-sum-square by (q mod hop)
+    const float* inv_wss;    // [hop] 1 / (n_fft * steady-state window-sum-square) by (q mod hop)
+    float inv_nfft;          // 1 / n_fft (a power of two: the scaling is exact wherever it is applied)
     const float2* tw;        // [32*32] exp(-2 pi i r l / 1024)
     const float2* vtab;      // [1024]  -i exp(-2 pi i k / 2048)
     // batch tables (workspace)

@@ -2,8 +2,12 @@
 //
 // Radix-2 decimation-in-time, written as a template recursion so that every index is a
 // compile-time constant: the arrays live entirely in registers and the twiddle constants
-// become FFMA immediates.  Twiddled butterflies use the 6-FMA "factor out the cosine" form
-//     e +- w*o = e +- c * (o + i*tau*o'),  tau = s/c  (or the sine form when |s| > |c|).
+// become instruction immediates.  Twiddled butterflies use the 6-FMA "factor out the cosine" form
+//     e +- w*o = e +- c * (o + tau * (-i o)),  tau = s/c  (or the sine form when |s| > |c|).
+// All complex arithmetic is issued as Blackwell packed-pair instructions (FFMA2 / FADD2 / FMUL2 on a
+// (re, im) register pair): one issue slot per complex operation instead of two.  The "-i o" operand
+// (swap the halves, negate one) is an operand modifier of those instructions (.LO_HI.NP in SASS), so
+// it costs nothing; ptxas folds it from the make_float2(o.y, -o.x) expression below.
 // NZ = number of leading non-zero inputs: Griffin-Lim frames are a 1200-sample window inside a
 // 2048-point transform, so 13 of the 32 strided inputs each lane sees are structurally zero and
 // the leaf butterflies that only copy are never emitted.
@@ -11,6 +15,17 @@
 #include <cuda_runtime.h>
 
 namespace s2st {
+
+// Packed-pair helpers (sm_100a: fma/add/mul.rn.f32x2).  Results are bit-identical to the scalar fmaf forms.
+__device__ __forceinline__ float2 bcast2(const float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 neg2(const float2 o) { return make_float2(-o.x, -o.y); }
+__device__ __forceinline__ float2 conj2(const float2 o) { return make_float2(o.x, -o.y); }
+__device__ __forceinline__ float2 swap2(const float2 o) { return make_float2(o.y, o.x); }
+__device__ __forceinline__ float2 mul_mi(const float2 o) { return make_float2(o.y, -o.x); }  // -i * o
+__device__ __forceinline__ float2 mul_pi(const float2 o) { return make_float2(-o.y, o.x); }  // +i * o
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) { return __fmul2_rn(a, b); }
 
 // cos(2*pi*j/32), j = 0..8
 __host__ __device__ constexpr float quarter_cos32(int j) {
@@ -37,32 +52,30 @@ template <int J, bool INV>
 __device__ __forceinline__ void bfly(const float2 e, const float2 o, float2& lo, float2& hi) {
     static_assert(J >= 0 && J < 16, "twiddle index");
     if constexpr (J == 0) {
-        lo = make_float2(e.x + o.x, e.y + o.y);
-        hi = make_float2(e.x - o.x, e.y - o.y);
+        lo = add2(e, o);
+        hi = add2(e, neg2(o));
     } else if constexpr (J == 8) {
         // w = -+ i  ->  w*o = (+-o.y, -+o.x)
         if constexpr (!INV) {
-            lo = make_float2(e.x + o.y, e.y - o.x);
-            hi = make_float2(e.x - o.y, e.y + o.x);
+            lo = add2(e, mul_mi(o));
+            hi = add2(e, mul_pi(o));
         } else {
-            lo = make_float2(e.x - o.y, e.y + o.x);
-            hi = make_float2(e.x + o.y, e.y - o.x);
+            lo = add2(e, mul_pi(o));
+            hi = add2(e, mul_mi(o));
         }
     } else {
         constexpr float c = cos32(J);
         constexpr float s = INV ? -sin32(J) : sin32(J);  // w*o = (o.x c + o.y s, o.y c - o.x s)
         if constexpr ((c < 0 ? -c : c) >= (s < 0 ? -s : s)) {
             constexpr float tau = s / c;
-            const float tx = fmaf(o.y, tau, o.x);
-            const float ty = fmaf(-o.x, tau, o.y);
-            lo = make_float2(fmaf(c, tx, e.x), fmaf(c, ty, e.y));
-            hi = make_float2(fmaf(-c, tx, e.x), fmaf(-c, ty, e.y));
+            const float2 t = fma2(mul_mi(o), bcast2(tau), o);  // (o.x + tau o.y, o.y - tau o.x)
+            lo = fma2(t, bcast2(c), e);
+            hi = fma2(t, bcast2(-c), e);
         } else {
             constexpr float kap = c / s;
-            const float tx = fmaf(o.x, kap, o.y);
-            const float ty = fmaf(o.y, kap, -o.x);
-            lo = make_float2(fmaf(s, tx, e.x), fmaf(s, ty, e.y));
-            hi = make_float2(fmaf(-s, tx, e.x), fmaf(-s, ty, e.y));
+            const float2 t = fma2(o, bcast2(kap), mul_mi(o));  // (kap o.x + o.y, kap o.y - o.x)
+            lo = fma2(t, bcast2(s), e);
+            hi = fma2(t, bcast2(-s), e);
         }
     }
 }
@@ -100,6 +113,31 @@ struct FftDit {
         }
     }
 };
+
+// ---- in-place variant on bit-reversed input --------------------------------------------------------------
+// brev5(p): 5-bit bit reversal.
+__host__ __device__ constexpr int brev5(int p) {
+    return ((p & 1) << 4) | ((p & 2) << 2) | (p & 4) | ((p & 8) >> 2) | ((p & 16) >> 4);
+}
+
+// Butterfly I of the 80 of a 32-point radix-2 DIT run in place: stage s = I / 16 has half-span m = 2^s.
+template <int I, bool INV>
+struct InplaceStep {
+    static __device__ __forceinline__ void run(float2 (&b)[32]) {
+        constexpr int s = I / 16, idx = I % 16, m = 1 << s;
+        constexpr int k = idx % m, blk = idx / m, i = blk * 2 * m + k;
+        bfly<k*(16 / m), INV>(b[i], b[i + m], b[i], b[i + m]);
+        if constexpr (I + 1 < 80) InplaceStep<I + 1, INV>::run(b);
+    }
+};
+
+// 32-point FFT in place: in b[p] = x[brev5(p)], out b[k] = X[k].  Every value stays in the array slot (register)
+// it was computed into, so a loop that runs this code several times carries no register permutation: producers
+// write their values to the bit-reversed slot (a compile-time renaming), consumers read natural order.
+template <bool INV>
+__device__ __forceinline__ void fft32_inplace_br(float2 (&b)[32]) {
+    InplaceStep<0, INV>::run(b);
+}
 
 // In-place (from the caller's point of view) 32-point FFT, natural order in and out.
 template <int NZ, bool INV>

@@ -10,9 +10,10 @@
 //   time      a[n2] = z[lane + 32*n2]        (samples 2*lane + 64*n2 and +1)
 //   frequency a[k1] = X[32*k1 + lane],  plus the Nyquist bin X[1024] (real) in lane 0
 //
-// Scratch per warp: kScratchFloats floats (5648 B).  To stay that small the transposes move the real
-// and imaginary parts one after the other (rows of 36 floats: 4-byte column writes and 16-byte row
-// reads are both bank-conflict free), and the pair exchange only moves the rows that are needed:
+// Scratch per warp: kScratchFloats floats (8 KB) = one 32 x 32 tile of complex values.  The transposes move whole
+// (re, im) pairs -- the packed-pair arithmetic wants them in adjacent registers -- with 8-byte column writes
+// and 16-byte row reads; instead of padding, the 16-byte chunks of row j are XOR-swizzled with (j & 7),
+// which makes both directions bank-conflict free.  The pair exchange only moves the rows that are needed:
 //   PRUNED (all live bins < 704, the f_max = 8 kHz vocoder case): one round, rows 10..31 forward /
 //          rows 0..21 inverse, 704 complex values + the bin-1024 alias;
 //   generic: two rounds of 16 rows with the first round's partners parked in registers.
@@ -21,55 +22,64 @@
 
 namespace s2st {
 
-constexpr int kScratchPitch = 36;       // floats per transpose row (144 B)
 constexpr int kPrunedRows = 22;         // rows (of 32 bins) that can be live in PRUNED mode
-constexpr int kScratchFloats = 1412;    // >= 32*36 (transpose), 2*705 (pruned exchange), 2*513 (generic)
+constexpr int kScratchFloats = 2048;    // 32*32 complex (transpose) >= 2*705 (pruned exchange), 2*513 (generic)
 
+// Complex products as two packed-pair instructions (FMUL2 + FFMA2).  "Swap the halves / negate one half" is a
+// free modifier of the FIRST source operand only (SASS .LO_HI.NP); ptxas does not commute it past a broadcast
+// scalar, so the modified operand is always written first.
 __device__ __forceinline__ float2 cmul(const float2 a, const float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+    return fma2(mul_pi(b), bcast2(a.y), mul2(b, bcast2(a.x)));
 }
 __device__ __forceinline__ float2 cmul_conj(const float2 a, const float2 b) {  // a * conj(b)
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+    return fma2(swap2(b), bcast2(a.y), mul2(conj2(b), bcast2(a.x)));
 }
 
 // 32x32 transpose of the per-lane register arrays: out a[r] = (lane r's) a[lane].
+// Element (row j, column l) lives in 16-byte chunk ((l >> 1) ^ (j & 7)) of row j (256 B per row), half (l & 1).
+template <bool BR = false>  // BR: deliver element r into slot brev5(r) (input order of fft32_inplace_br)
 __device__ __forceinline__ void warp_transpose(float2 (&a)[32], float* scratch, int lane) {
-    const float4* row = reinterpret_cast<const float4*>(scratch + lane * kScratchPitch);
+    char* base = reinterpret_cast<char*>(scratch);
+    const int wofs = lane * 8;  // ((lane >> 1) << 4) | ((lane & 1) << 3)
 #pragma unroll
-    for (int r = 0; r < 32; ++r) scratch[r * kScratchPitch + lane] = a[r].x;
+    for (int j = 0; j < 32; ++j)
+        *reinterpret_cast<float2*>(base + j * 256 + (wofs ^ ((j & 7) << 4))) = a[j];
     __syncwarp();
+    const char* row = base + lane * 256;
+    const int sw = (lane & 7) << 4;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float4 v = row[c];
-        a[4 * c].x = v.x;
-        a[4 * c + 1].x = v.y;
-        a[4 * c + 2].x = v.z;
-        a[4 * c + 3].x = v.w;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; ++r) scratch[r * kScratchPitch + lane] = a[r].y;
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float4 v = row[c];
-        a[4 * c].y = v.x;
-        a[4 * c + 1].y = v.y;
-        a[4 * c + 2].y = v.z;
-        a[4 * c + 3].y = v.w;
+    for (int c = 0; c < 16; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(row + ((((c & 7) << 4) ^ sw) | ((c & 8) << 4)));
+        a[BR ? brev5(2 * c) : 2 * c] = make_float2(v.x, v.y);
+        a[BR ? brev5(2 * c + 1) : 2 * c + 1] = make_float2(v.z, v.w);
     }
     __syncwarp();
 }
 
 // X2 = (Z + conj P) + V (Z - conj P)     (V = -i exp(-2 pi i k / 2048): forward split)
 __device__ __forceinline__ float2 split_fwd(const float2 z, const float2 p, const float2 v) {
-    const float sx = z.x + p.x, sy = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
-    return make_float2(fmaf(v.x, dx, fmaf(-v.y, dy, sx)), fmaf(v.x, dy, fmaf(v.y, dx, sy)));
+    const float2 s = add2(z, conj2(p)), d = add2(z, neg2(conj2(p)));
+    return fma2(d, bcast2(v.x), fma2(mul_pi(d), bcast2(v.y), s));
 }
-// Z' = (Y + conj P) + conj(V) (Y - conj P)   (inverse merge)
+// Z' = (Y + conj P) + conj(V) (Y - conj P)   (inverse merge).  SW: return Z' with its halves exchanged; the
+// exchange is pushed down to the operands (where it is a free operand modifier) instead of moving registers.
+template <bool SW>
+__device__ __forceinline__ float2 sw2(const float2 o) { return SW ? swap2(o) : o; }
+template <bool SW>
 __device__ __forceinline__ float2 merge_inv(const float2 y, const float2 p, const float2 v) {
-    const float sx = y.x + p.x, sy = y.y - p.y, dx = y.x - p.x, dy = y.y + p.y;
-    return make_float2(fmaf(v.x, dx, fmaf(v.y, dy, sx)), fmaf(v.x, dy, fmaf(-v.y, dx, sy)));
+    const float2 s = add2(sw2<SW>(y), sw2<SW>(conj2(p))), d = add2(sw2<SW>(y), sw2<SW>(neg2(conj2(p))));
+    return fma2(d, bcast2(v.x), fma2(SW ? mul_pi(d) : mul_mi(d), bcast2(v.y), s));
+}
+// the same with P = 0  (Z' = Y + conj(V) Y)  and with Y = 0  (Z' = conj(P) - conj(V) conj(P))
+template <bool SW>
+__device__ __forceinline__ float2 merge_inv_y(const float2 y, const float2 v) {
+    const float2 d = sw2<SW>(y);
+    return fma2(d, bcast2(v.x), fma2(SW ? mul_pi(d) : mul_mi(d), bcast2(v.y), d));
+}
+template <bool SW>
+__device__ __forceinline__ float2 merge_inv_p(const float2 p, const float2 v) {
+    const float2 s = sw2<SW>(conj2(p)), d = sw2<SW>(neg2(conj2(p)));
+    return fma2(d, bcast2(v.x), fma2(SW ? mul_pi(d) : mul_mi(d), bcast2(v.y), s));
 }
 
 // Forward, first half: in-lane FFT over n2, twiddle, transpose.  In: a[n2] for n2 < NZ (others ignored).
@@ -149,10 +159,11 @@ __device__ __forceinline__ void frame_fwd(float2 (&a)[32], float& nyq, float* sc
 // ignored; PRUNED: rows >= 22 are taken as zero whatever they hold), ynyq = Y[1024] (real, from lane 0).
 // Out: a[k1] = Z'[32*k1+lane], the packed 1024-point spectrum; SWAP: real and imaginary parts exchanged,
 // which turns the inverse transform into a forward one (IDFT(Z) = swap(DFT(swap(Z)))).
-template <bool PRUNED, bool SWAP>
+template <bool PRUNED, bool SWAP, bool BR = false>  // BR: Z' row r goes to slot brev5(r)
 __device__ __forceinline__ void inv_merge(float2 (&a)[32], float ynyq, float* scratch,
                                           const float2* __restrict__ vtab, int lane) {
     if (lane == 0) a[0].y = 0.0f;
+    float2 z[32];
     float2* sc = reinterpret_cast<float2*>(scratch);
     if constexpr (PRUNED) {
 #pragma unroll
@@ -165,24 +176,19 @@ __device__ __forceinline__ void inv_merge(float2 (&a)[32], float ynyq, float* sc
         for (int r = 0; r < 32; ++r) {
             const int k = 32 * r + lane;
             const float2 v = vtab[k];
-            float2 z;
             if (r < 10) {
                 float2 p = make_float2(0.0f, 0.0f);
                 if (r == 0 && lane == 0) p = sc[704];
-                z = (r == 0) ? merge_inv(a[r], p, v)
-                             : make_float2(fmaf(v.x, a[r].x, fmaf(v.y, a[r].y, a[r].x)), fmaf(v.x, a[r].y, fmaf(-v.y, a[r].x, a[r].y)));
+                z[r] = (r == 0) ? merge_inv<SWAP>(a[r], p, v) : merge_inv_y<SWAP>(a[r], v);
             } else if (r == 10) {
                 float2 p = make_float2(0.0f, 0.0f);
                 if (lane > 0) p = sc[1024 - k];
-                z = merge_inv(a[r], p, v);
+                z[r] = merge_inv<SWAP>(a[r], p, v);
             } else if (r < kPrunedRows) {
-                z = merge_inv(a[r], sc[1024 - k], v);
+                z[r] = merge_inv<SWAP>(a[r], sc[1024 - k], v);
             } else {
-                // Y = 0: Z' = conj(P) - conj(V) conj(P)
-                const float2 p = sc[1024 - k];
-                z = make_float2(fmaf(-v.x, p.x, fmaf(v.y, p.y, p.x)), fmaf(v.x, p.y, fmaf(v.y, p.x, -p.y)));
+                z[r] = merge_inv_p<SWAP>(sc[1024 - k], v);
             }
-            a[r] = SWAP ? make_float2(z.y, z.x) : z;
         }
         __syncwarp();
     } else {
@@ -201,29 +207,30 @@ __device__ __forceinline__ void inv_merge(float2 (&a)[32], float ynyq, float* sc
         for (int r = 16; r < 32; ++r) {
             const int k = 32 * r + lane;
             const float2 p = (k == 512) ? a[r] : sc[1024 - k];
-            const float2 z = merge_inv(a[r], p, vtab[k]);
-            a[r] = SWAP ? make_float2(z.y, z.x) : z;
+            z[r] = merge_inv<SWAP>(a[r], p, vtab[k]);
         }
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-            const float2 z = merge_inv(a[r], t[r], vtab[32 * r + lane]);
-            a[r] = SWAP ? make_float2(z.y, z.x) : z;
+            z[r] = merge_inv<SWAP>(a[r], t[r], vtab[32 * r + lane]);
         }
         __syncwarp();
     }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) a[BR ? brev5(r) : r] = z[r];
 }
 
-// The 1024-point complex forward DFT of the per-lane arrays, in place: in a[j] = z[lane + 32*j], out
-// a[j] = Z[lane + 32*j] -- input and output use the same (index mod 32, index div 32) layout, which is
-// what lets one routine serve both directions.  The in-lane FFT is emitted once and run twice.
+// The 1024-point complex forward DFT of the per-lane arrays, in place: in a[brev5(j)] = z[lane + 32*j] (the
+// bit-reversed slots fft32_inplace_br wants), out a[j] = Z[lane + 32*j] -- input and output use the same
+// (index mod 32, index div 32) layout, which is what lets one routine serve both directions.  The in-lane FFT
+// is emitted once and run twice; it works in place, so the loop carries no register shuffling.
 __device__ __forceinline__ void fwd1024(float2 (&a)[32], float* scratch, const float2* __restrict__ tw, int lane) {
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
-        fft32<32, false>(a);
+        fft32_inplace_br<false>(a);
         if (h == 0) {
 #pragma unroll
             for (int r = 1; r < 32; ++r) a[r] = cmul(a[r], tw[r * 32 + lane]);
-            warp_transpose(a, scratch, lane);
+            warp_transpose<true>(a, scratch, lane);
         }
     }
 }

@@ -58,14 +58,14 @@ __device__ __forceinline__ void load_frame_edge(float2 (&a)[32], const float* __
         // registers cannot be indexed dynamically: scatter through a switch-free unrolled select
 #pragma unroll
         for (int q = 0; q < NZ; ++q)
-            if (q == r) a[q] = v;
+            if (q == r) a[brev5(q)] = v;  // frame row q lives in slot brev5(q) (fwd1024's input order)
     }
 }
 
 // Generic (cold) write-out of strip samples [i0, i0 + n): seams, utterance edges, unaligned layouts.
 // Kept out of line; everything it needs is passed by value.
 __device__ __noinline__ void emit_generic(float* __restrict__ ring, const float* __restrict__ s_inv_wss,
-                                          const float* __restrict__ w2, float* __restrict__ out,
+                                          const float* __restrict__ w2, float inv_nfft, float* __restrict__ out,
                                           float* __restrict__ znext, int hop, int ws, int f0, int nf, int T, int L,
                                           int j_base, int i0, int n, int slot0, int lane) {
     const bool has_prev = f0 > 0, has_next = f0 + nf < T;
@@ -89,7 +89,7 @@ __device__ __noinline__ void emit_generic(float* __restrict__ ring, const float*
             const int qq = f0 * hop + i;
             float w = 0.0f;
             for (int t = max(t_lo, 0); t <= min(t_hi, T - 1); ++t) w += __ldg(w2 + (qq - t * hop));
-            inv = w > kTiny ? 1.0f / w : 1.0f;
+            inv = (w > kTiny ? 1.0f / w : 1.0f) * inv_nfft;
         } else {
             inv = s_inv_wss[i % hop];
         }
@@ -104,16 +104,20 @@ __device__ __noinline__ void emit_generic(float* __restrict__ ring, const float*
 // One Griffin-Lim pass.  FIRST: spectra come from (mag, initial phase) -> inverse only.
 // PRUNED: every live bin is below 704 (kb <= 704): magnitudes are prefetched into registers and the
 // pair exchanges move 22 rows instead of 32.
-template <int NZ, bool FIRST, bool PRUNED>
-__global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant__ GlParams p) {
+// STD: the vocoder's standard geometry (hop 300, window support 1200 starting at sample 424 of the 2048-point
+// frame, magnitude rows at least 704 wide) as compile-time constants: no geometry tests in the frame loop.
+constexpr int kStdHop = 300, kStdWs = 1200, kStdRot = 424;
+template <int NZ, bool FIRST, bool PRUNED, bool STD>
+__global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant__ GlParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);            // 1024
     float2* s_vtab = s_tw + 1024;                                  // 1024
     float* s_win_a = reinterpret_cast<float*>(s_vtab + 1024);
-    float* s_win_s = s_win_a + 64 * NZ;
-    float* s_inv_wss = s_win_s + 64 * NZ;                          // hop (rounded up to 4)
-    float* s_warp = s_inv_wss + ((p.hop + 3) & ~3);                // per warp: scratch + ring
-    const int ring_floats = (p.ws + 3) & ~3;
+    float* s_inv_wss = s_win_a + 64 * NZ;                          // hop (rounded up to 4)
+    const int hop = STD ? kStdHop : p.hop, ws = STD ? kStdWs : p.ws;
+    const int rot_half = STD ? kStdRot - kNfft / 2 : p.rot - p.half;
+    float* s_warp = s_inv_wss + ((hop + 3) & ~3);                  // per warp: scratch + ring
+    const int ring_floats = (ws + 3) & ~3;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* scratch = s_warp + warp * (kScratchFloats + ring_floats);
@@ -122,19 +126,15 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
         s_tw[i] = p.tw[i];
         s_vtab[i] = p.vtab[i];
     }
-    for (int i = tid; i < 64 * NZ; i += kGlThreads) {
-        s_win_a[i] = p.win_a[i];
-        s_win_s[i] = p.win_s[i];
-    }
-    for (int i = tid; i < p.hop; i += kGlThreads) s_inv_wss[i] = p.inv_wss[i];
+    for (int i = tid; i < 64 * NZ; i += kGlThreads) s_win_a[i] = p.win_a[i];
+    for (int i = tid; i < hop; i += kGlThreads) s_inv_wss[i] = p.inv_wss[i];
     for (int i = lane; i < ring_floats; i += 32) ring[i] = 0.0f;
     __syncthreads();  // the only block-wide barrier: constant tables are in place
 
     const int n_strips = *p.n_tiles;
-    const int hop = p.hop, ws = p.ws;
     const int kb = PRUNED ? min(p.kb, 32 * kPrunedRows) : p.kb;
     // fast paths need 16-byte friendly geometry (true for hop 300 / win 1200 / n_fft 2048)
-    const bool geom4 = (hop % 4 == 0) && (hop >= 64) && (ws % hop == 0) && ((p.rot - p.half) % 4 == 0);
+    const bool geom4 = STD || ((hop % 4 == 0) && (hop >= 64) && (ws % hop == 0) && (rot_half % 4 == 0));
 
     for (int strip = blockIdx.x * kGlWarps + warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
         const TileDesc td = p.tiles[strip];
@@ -143,11 +143,11 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
         ud.frame_off = td.frame_off;
         ud.n_frames = td.n_frames;
         const int T = ud.n_frames, L = (T - 1) * hop;
-        const int j_base = td.f0 * hop + p.rot - p.half;  // output sample index of strip-relative sample 0
+        const int j_base = td.f0 * hop + rot_half;  // output sample index of strip-relative sample 0
         float* out = p.out + ud.wave_off;
         float* znext = p.zero_next + ud.wave_off;
         const float* y = p.in + ud.wave_off;
-        const bool aligned = geom4 && ((ud.wave_off & 3) == 0);
+        const bool aligned = STD || (geom4 && ((ud.wave_off & 3) == 0));  // STD: wave_off is a multiple of hop
         const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0) * p.mag_stride;
         const float* phrow = (FIRST && p.phase) ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
 
@@ -165,15 +165,15 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
 #pragma unroll
                     for (int r = 0; r < NZ; ++r) {
                         const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
-                        a[r] = make_float2(a[r].x * ww.x, a[r].y * ww.y);
+                        a[brev5(r)] = mul2(a[brev5(r)], ww);  // frame row r lives in slot brev5(r)
                     }
 #pragma unroll
-                    for (int r = NZ; r < 32; ++r) a[r] = make_float2(0.0f, 0.0f);
+                    for (int r = NZ; r < 32; ++r) a[brev5(r)] = make_float2(0.0f, 0.0f);
                     // target magnitudes: requested now, the forward transform hides their latency
                     if constexpr (PRUNED) {
 #pragma unroll
                         for (int r = 0; r < kPrunedRows; ++r)
-                            mg[r] = (32 * r < p.mag_stride) ? __ldg(magrow + 32 * r + lane) : 0.0f;  // uniform test
+                            mg[r] = (STD || 32 * r < p.mag_stride) ? __ldcs(magrow + 32 * r + lane) : 0.0f;  // uniform test; read once per pass
                     }
                 }
                 // pass 0: analysis (frame -> spectrum -> re-imposed magnitude); pass 1: synthesis.  The
@@ -208,27 +208,60 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                             }
                             if (p.phase) phrow += p.phase_stride;
                         }
-                        inv_merge<PRUNED, true>(a, ynyq, scratch, s_vtab, lane);
+                        inv_merge<PRUNED, true, true>(a, ynyq, scratch, s_vtab, lane);
                     }
                     fwd1024(a, scratch, s_tw, lane);
                     if constexpr (!FIRST) {
                         if (pass == 0) {
                             float nyq;
                             fwd_split<PRUNED>(a, nyq, scratch, s_vtab, lane);
+                            if constexpr (PRUNED) {
+                                // scale factors first (into mg[]); spectra whose |X|^2 is below the normal range
+                                // (where the reference's atan2(0, +-0) = 0 / pi gives (+-mag, 0)) are only flagged
+                                bool degenerate = false;
 #pragma unroll
-                            for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
-                                const int k = 32 * r + lane;
-                                float m;
-                                if constexpr (PRUNED) m = mg[r];
-                                else m = (k < kb) ? __ldg(magrow + k) : 0.0f;
-                                const float x = a[r].x, yy = a[r].y;
-                                const float r2 = fmaf(x, x, yy * yy);
-                                float rs;
-                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
-                                const float sc = m * rs;
-                                // |X|^2 below the normal range counts as |X| == 0, where the reference's
-                                // atan2(0, +-0) = 0 / pi gives (+-mag, 0)
-                                a[r] = r2 >= 1.1754944e-38f ? make_float2(x * sc, yy * sc) : make_float2(copysignf(m, x), 0.0f);
+                                for (int r = 0; r < kPrunedRows; ++r) {
+                                    const float r2 = fmaf(a[r].x, a[r].x, a[r].y * a[r].y);
+                                    float rs;
+                                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
+                                    mg[r] *= rs;
+                                    degenerate |= !(r2 >= 1.1754944e-38f);
+                                }
+                                if (__builtin_expect(__any_sync(0xffffffffu, degenerate), 0)) {
+#pragma unroll 1
+                                    for (int r = 0; r < kPrunedRows; ++r) {
+                                        const float m = __ldg(magrow + 32 * r + lane);
+                                        float2 v = make_float2(0.0f, 0.0f);
+                                        float sc = 0.0f;
+#pragma unroll
+                                        for (int q = 0; q < kPrunedRows; ++q)
+                                            if (q == r) {
+                                                v = a[q];
+                                                sc = mg[q];
+                                            }
+                                        const float r2 = fmaf(v.x, v.x, v.y * v.y);
+                                        v = r2 >= 1.1754944e-38f ? mul2(v, bcast2(sc)) : make_float2(copysignf(m, v.x), 0.0f);
+#pragma unroll
+                                        for (int q = 0; q < kPrunedRows; ++q)
+                                            if (q == r) a[q] = v;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int r = 0; r < kPrunedRows; ++r) a[r] = mul2(a[r], bcast2(mg[r]));
+                                }
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 32; ++r) {
+                                    const int k = 32 * r + lane;
+                                    const float m = (k < kb) ? __ldg(magrow + k) : 0.0f;
+                                    const float x = a[r].x, yy = a[r].y;
+                                    const float r2 = fmaf(x, x, yy * yy);
+                                    float rs;
+                                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
+                                    const float sc = m * rs;
+                                    const float2 sa = mul2(a[r], bcast2(sc));
+                                    a[r] = r2 >= 1.1754944e-38f ? sa : make_float2(copysignf(m, x), 0.0f);
+                                }
                             }
                             if (kb > 1024) ynyq = copysignf(__ldg(magrow + 1024), nyq);
                         }
@@ -237,7 +270,7 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                 magrow += p.mag_stride;
                 // a[] holds the synthesis frame with the parts swapped (.y = even sample, .x = odd sample):
                 // window and overlap-add into the private ring
-                const float* w = s_win_s + 2 * lane;
+                const float* w = s_win_a + 2 * lane;
                 if (geom4) {
                     // samples past the window support have zero weight: they wrap onto a live slot and add
                     // +0, so every row can accumulate without a bounds test (slots stay even -> 8-byte RMW)
@@ -248,9 +281,7 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                         float* dst = ring + first + 64 * r - (64 * r >= until_wrap ? ws : 0);
                         float2 o = *reinterpret_cast<float2*>(dst);
                         const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
-                        o.x = fmaf(a[r].y, ww.x, o.x);
-                        o.y = fmaf(a[r].x, ww.y, o.y);
-                        *reinterpret_cast<float2*>(dst) = o;
+                        *reinterpret_cast<float2*>(dst) = fma2(swap2(a[r]), ww, o);
                     }
                 } else {
 #pragma unroll 1
@@ -281,7 +312,10 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                     if (aligned && jf >= 0 && jf + 64 * NZ <= L) {
                         const float2* src = reinterpret_cast<const float2*>(y + jf) + lane;
 #pragma unroll
-                        for (int r = 0; r < NZ; ++r) a[r] = src[32 * r];
+                        for (int r = 0; r < NZ; ++r) a[brev5(r)] = src[32 * r];
+                        // the hop the frame after that adds is not in cache yet: ask L2 for it now (11 lines)
+                        const int jp = jf + 64 * NZ - 16 + 32 * lane;
+                        if (lane < 11 && jp < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + jp));
                     } else {
                         load_frame_edge<NZ>(a, y, jf + 2 * lane, L);
                     }
@@ -300,10 +334,12 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
                     for (int q = lane; q < (hop >> 2); q += 32) {
                         const float4 v = rg[q], wv = iw[q];
                         rg[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        dst[q] = make_float4(v.x * wv.x, v.y * wv.y, v.z * wv.z, v.w * wv.w);
+                        const float2 lo = mul2(make_float2(v.x, v.y), make_float2(wv.x, wv.y));
+                        const float2 hi = mul2(make_float2(v.z, v.w), make_float2(wv.z, wv.w));
+                        dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
                     }
                 } else {
-                    emit_generic(ring, s_inv_wss, p.w2, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, i0, hop, slot0, lane);
+                    emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, i0, hop, slot0, lane);
                 }
                 slot0 += hop;
                 if (slot0 >= ws) slot0 -= ws;
@@ -311,7 +347,7 @@ __global__ void __launch_bounds__(kGlThreads, 2) k_gl_pass(const __grid_constant
             }
         }
         // the tail of the last frame: [nf*hop, (nf-1)*hop + ws)
-        emit_generic(ring, s_inv_wss, p.w2, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
+        emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
         __syncwarp();
     }
 }
@@ -483,14 +519,14 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
 
 size_t gl_pass_smem(const s2st_plan* plan) {
     return sizeof(float2) * 2048 +
-           sizeof(float) * (2 * plan->wp + ((plan->hop + 3) & ~3) + kGlWarps * (kScratchFloats + ((plan->ws + 3) & ~3)));
+           sizeof(float) * (plan->wp + ((plan->hop + 3) & ~3) + kGlWarps * (kScratchFloats + ((plan->ws + 3) & ~3)));
 }
 
 // Strip length: all strips cost the same, warps take them round-robin, so the pass lasts
 // ceil(n_strips / n_warps) strip times.  Pick the S that minimises that (exactly when the host knows the
 // utterance lengths, from the average otherwise).
 int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, const int32_t* fo_host) {
-    const long long n_warps = (long long)plan->num_sms * 2 * kGlWarps;
+    const long long n_warps = (long long)plan->num_sms * kGlWarps;
     const int s_min = plan->nphase > kMinStrip ? plan->nphase : kMinStrip;
     int best = s_min;
     double best_cost = 1e300;
@@ -511,10 +547,10 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
     return best;
 }
 
-template <int NZ, bool FIRST, bool PRUNED>
+template <int NZ, bool FIRST, bool PRUNED, bool STD = false>
 int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream) {
-    S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_gl_pass<NZ, FIRST, PRUNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gl_pass<NZ, FIRST, PRUNED><<<grid, kGlThreads, smem, stream>>>(p);
+    S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_gl_pass<NZ, FIRST, PRUNED, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gl_pass<NZ, FIRST, PRUNED, STD><<<grid, kGlThreads, smem, stream>>>(p);
     S2ST_CUDA_CHECK(cudaGetLastError());
     return S2ST_OK;
 }
@@ -598,7 +634,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     p.wp = plan->wp;
     p.nphase = plan->nphase;
     p.win_a = plan->win_a;
-    p.win_s = plan->win_s;
+    p.inv_nfft = 1.0f / (float)plan->n_fft;
     p.w2 = plan->w2;
     p.inv_wss = plan->inv_wss;
     p.tw = plan->tw;
@@ -622,7 +658,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     }
     const size_t smem = gl_pass_smem(plan);
     const long long strips_ub = total_frames / S + n_utts;  // <= w.max_tiles because S >= kMinStrip
-    const int grid = (int)min((long long)plan->num_sms * 2, (strips_ub + kGlWarps - 1) / kGlWarps);
+    const int grid = (int)min((long long)plan->num_sms, (strips_ub + kGlWarps - 1) / kGlWarps);
     const bool pruned = p.kb <= 32 * kPrunedRows;
     // three rotating waveform buffers; the one the last pass writes is the caller's output
     float* ring[3];
@@ -639,8 +675,12 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
             if (!plan->timing_events[it]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[it]));
             S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[it], stream));
         }
-        int rc = (plan->nz == 19) ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
-                                  : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
+        // the iteration kernel specialised for the vocoder's standard geometry, else the generic one
+        const bool std_geom = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
+                              plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
+        int rc = (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
+                 : (plan->nz == 19)   ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
+                                      : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
         if (rc != S2ST_OK) return rc;
     }
     if (timed) {
