@@ -11,7 +11,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libs2st_b200.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+# S2ST_B200_LIB points the loader at another build of the same library (kernel A/B experiments in tools/)
+LIB_PATH = os.environ.get("S2ST_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "s2st_b200.h")
 
 S2ST_OK = 0

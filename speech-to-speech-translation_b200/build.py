@@ -29,17 +29,22 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=OUT, defines=()):
+    """out / defines: experiment builds (tools/), e.g. build(out="/tmp/x.so", defines=["S2ST_GL_UNROLL_H=2"])."""
+    if not force and out == OUT and not is_stale():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] +
+           ["-o", out] + SOURCES)
     res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libs2st_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv or bool(defs), verbose="-v" in sys.argv,
+                out=os.path.abspath(outs[0]) if outs else OUT, defines=defs))

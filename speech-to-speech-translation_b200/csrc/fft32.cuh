@@ -121,22 +121,39 @@ __host__ __device__ constexpr int brev5(int p) {
 }
 
 // Butterfly I of the 80 of a 32-point radix-2 DIT run in place: stage s = I / 16 has half-span m = 2^s.
-template <int I, bool INV>
+// NZ_IN: only input rows < NZ_IN are non-zero (slot p holds row brev5(p)): first-stage butterflies whose odd
+// operand is structurally zero are copies.  NZ_OUT: only outputs k < NZ_OUT are used: last-stage butterflies
+// skip the unused half.  LOOPED: the array is carried around a loop, so the last stage must leave its results
+// in the operand slots without a spare register (hi overwrites o, then lo = 2e - hi overwrites e).
+template <int I, bool INV, int NZ_IN, int NZ_OUT, bool LOOPED>
 struct InplaceStep {
     static __device__ __forceinline__ void run(float2 (&b)[32]) {
         constexpr int s = I / 16, idx = I % 16, m = 1 << s;
         constexpr int k = idx % m, blk = idx / m, i = blk * 2 * m + k;
-        bfly<k*(16 / m), INV>(b[i], b[i + m], b[i], b[i + m]);
-        if constexpr (I + 1 < 80) InplaceStep<I + 1, INV>::run(b);
+        if constexpr (s == 0 && brev5(i + m) >= NZ_IN) {
+            b[i + m] = b[i];
+        } else if constexpr (s == 4 && k + 16 >= NZ_OUT) {
+            float2 hi;
+            bfly<k*(16 / m), INV>(b[i], b[i + m], b[i], hi);
+        } else if constexpr (s == 4 && LOOPED) {
+            float2 lo, hi;
+            bfly<k*(16 / m), INV>(b[i], b[i + m], lo, hi);
+            b[i + m] = hi;
+            b[i] = fma2(b[i], bcast2(2.0f), neg2(hi));
+        } else {
+            bfly<k*(16 / m), INV>(b[i], b[i + m], b[i], b[i + m]);
+        }
+        if constexpr (I + 1 < 80) InplaceStep<I + 1, INV, NZ_IN, NZ_OUT, LOOPED>::run(b);
     }
 };
 
 // 32-point FFT in place: in b[p] = x[brev5(p)], out b[k] = X[k].  Every value stays in the array slot (register)
-// it was computed into, so a loop that runs this code several times carries no register permutation: producers
-// write their values to the bit-reversed slot (a compile-time renaming), consumers read natural order.
-template <bool INV>
+// it was computed into; producers write their values to the bit-reversed slot (a compile-time renaming),
+// consumers read natural order.
+template <bool INV, int NZ_IN = 32, int NZ_OUT = 32, bool LOOPED = false>
 __device__ __forceinline__ void fft32_inplace_br(float2 (&b)[32]) {
-    InplaceStep<0, INV>::run(b);
+    static_assert(NZ_IN > 16 && NZ_OUT > 16, "pruning only covers the upper half");
+    InplaceStep<0, INV, NZ_IN, NZ_OUT, LOOPED>::run(b);
 }
 
 // In-place (from the caller's point of view) 32-point FFT, natural order in and out.

@@ -223,15 +223,27 @@ __device__ __forceinline__ void inv_merge(float2 (&a)[32], float ynyq, float* sc
 // bit-reversed slots fft32_inplace_br wants), out a[j] = Z[lane + 32*j] -- input and output use the same
 // (index mod 32, index div 32) layout, which is what lets one routine serve both directions.  The in-lane FFT
 // is emitted once and run twice; it works in place, so the loop carries no register shuffling.
+// NZ_IN: input rows >= NZ_IN are zero (their slots need not be initialised); NZ_OUT: only output rows
+// < NZ_OUT are needed (the others are left undefined).  SHARED_FFT: emit the in-lane FFT once and run it twice
+// (smaller code, but the array becomes loop-carried and no pruning is possible).
+template <int NZ_IN = 32, int NZ_OUT = 32, bool SHARED_FFT = false>
 __device__ __forceinline__ void fwd1024(float2 (&a)[32], float* scratch, const float2* __restrict__ tw, int lane) {
+    if constexpr (SHARED_FFT) {
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        fft32_inplace_br<false>(a);
-        if (h == 0) {
+        for (int h = 0; h < 2; ++h) {
+            fft32_inplace_br<false, 32, 32, true>(a);
+            if (h == 0) {
 #pragma unroll
-            for (int r = 1; r < 32; ++r) a[r] = cmul(a[r], tw[r * 32 + lane]);
-            warp_transpose<true>(a, scratch, lane);
+                for (int r = 1; r < 32; ++r) a[r] = cmul(a[r], tw[r * 32 + lane]);
+                warp_transpose<true>(a, scratch, lane);
+            }
         }
+    } else {
+        fft32_inplace_br<false, NZ_IN, 32>(a);
+#pragma unroll
+        for (int r = 1; r < 32; ++r) a[r] = cmul(a[r], tw[r * 32 + lane]);
+        warp_transpose<true>(a, scratch, lane);
+        fft32_inplace_br<false, 32, NZ_OUT>(a);
     }
 }
 
