@@ -499,6 +499,30 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
     } else {
         p->num_sms = prop.multiProcessorCount;
     }
+    // tables of the register-resident kernel (FFT 512 / 256 with at most 13 * 16 window samples per transform)
+    p->fast_mode = -1;
+    if (padded == 512 && win <= 13 * 32) p->fast_mode = 0;
+    if (padded == 256 && win <= 13 * 16) p->fast_mode = 1;
+    if (p->fast_mode >= 0) {
+        std::vector<float2> tw16(256), vsplit(256);
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const double a = -2.0 * pi * (double)(k1 * n2) / 256.0;
+                tw16[k1 * 16 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
+            }
+        for (int k = 0; k < 256; ++k) {
+            const double a = 2.0 * pi * (double)k / 512.0;  // -i * exp(-i a) = (-sin a, -cos a)
+            vsplit[k] = make_float2((float)(-std::sin(a)), (float)(-std::cos(a)));
+        }
+        vsplit[0] = make_float2(0.0f, -1.0f);
+        vsplit[128] = make_float2(-1.0f, 0.0f);
+        const int per_row = p->fast_mode == 0 ? 32 : 16;
+        std::vector<float> winp(13 * per_row, 0.0f);
+        for (int i = 0; i < win; ++i) winp[i] = window[i];
+        if (rc == S2ST_OK) rc = upload(&p->tw16, tw16);
+        if (rc == S2ST_OK) rc = upload(&p->vsplit, vsplit);
+        if (rc == S2ST_OK) rc = upload(&p->winp, winp);
+    }
     if (rc == S2ST_OK) rc = upload(&p->window, window);
     if (rc == S2ST_OK) rc = upload(&p->tw, tw);
     if (rc == S2ST_OK) rc = upload(&p->mel_ptr, ptr);
@@ -517,6 +541,9 @@ int s2st_fbank_plan_destroy(s2st_fbank_plan* plan) {
     DeviceGuard guard(plan->device);
     cudaFree(plan->window);
     cudaFree(plan->tw);
+    cudaFree(plan->tw16);
+    cudaFree(plan->vsplit);
+    cudaFree(plan->winp);
     cudaFree(plan->mel_ptr);
     cudaFree(plan->mel_idx);
     cudaFree(plan->mel_val);

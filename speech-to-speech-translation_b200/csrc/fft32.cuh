@@ -114,28 +114,36 @@ struct FftDit {
     }
 };
 
-// ---- in-place variant on bit-reversed input --------------------------------------------------------------
-// brev5(p): 5-bit bit reversal.
+// ---- in-place variants on bit-reversed input ------------------------------------------------------------
+// brev5(p) / brev4(p): 5- and 4-bit bit reversal.
 __host__ __device__ constexpr int brev5(int p) {
     return ((p & 1) << 4) | ((p & 2) << 2) | (p & 4) | ((p & 8) >> 2) | ((p & 16) >> 4);
 }
+__host__ __device__ constexpr int brev4(int p) { return ((p & 1) << 3) | ((p & 2) << 1) | ((p & 4) >> 1) | ((p & 8) >> 3); }
+template <int N>
+__host__ __device__ constexpr int brev_n(int p) {
+    static_assert(N == 16 || N == 32, "sizes in use");
+    return N == 32 ? brev5(p) : brev4(p);
+}
 
-// Butterfly I of the 80 of a 32-point radix-2 DIT run in place: stage s = I / 16 has half-span m = 2^s.
-// NZ_IN: only input rows < NZ_IN are non-zero (slot p holds row brev5(p)): first-stage butterflies whose odd
+// Butterfly I of the (N/2) log2(N) of an N-point radix-2 DIT run in place: stage s = I / (N/2) has half-span
+// m = 2^s and twiddle exp(-+2 pi i k / (2m)) = W_32^(k * 16 / m) for every N.
+// NZ_IN: only input rows < NZ_IN are non-zero (slot p holds row brev(p)): first-stage butterflies whose odd
 // operand is structurally zero are copies.  NZ_OUT: only outputs k < NZ_OUT are used: last-stage butterflies
 // skip the unused half.  LOOPED: the array is carried around a loop, so the last stage must leave its results
 // in the operand slots without a spare register (hi overwrites o, then lo = 2e - hi overwrites e).
-template <int I, bool INV, int NZ_IN, int NZ_OUT, bool LOOPED>
+template <int N, int I, bool INV, int NZ_IN, int NZ_OUT, bool LOOPED>
 struct InplaceStep {
-    static __device__ __forceinline__ void run(float2 (&b)[32]) {
-        constexpr int s = I / 16, idx = I % 16, m = 1 << s;
+    static __device__ __forceinline__ void run(float2 (&b)[N]) {
+        constexpr int H = N / 2, LAST = (N == 32 ? 4 : 3), TOTAL = H * (LAST + 1);
+        constexpr int s = I / H, idx = I % H, m = 1 << s;
         constexpr int k = idx % m, blk = idx / m, i = blk * 2 * m + k;
-        if constexpr (s == 0 && brev5(i + m) >= NZ_IN) {
+        if constexpr (s == 0 && brev_n<N>(i + m) >= NZ_IN) {
             b[i + m] = b[i];
-        } else if constexpr (s == 4 && k + 16 >= NZ_OUT) {
+        } else if constexpr (s == LAST && k + H >= NZ_OUT) {
             float2 hi;
             bfly<k*(16 / m), INV>(b[i], b[i + m], b[i], hi);
-        } else if constexpr (s == 4 && LOOPED) {
+        } else if constexpr (s == LAST && LOOPED) {
             float2 lo, hi;
             bfly<k*(16 / m), INV>(b[i], b[i + m], lo, hi);
             b[i + m] = hi;
@@ -143,17 +151,22 @@ struct InplaceStep {
         } else {
             bfly<k*(16 / m), INV>(b[i], b[i + m], b[i], b[i + m]);
         }
-        if constexpr (I + 1 < 80) InplaceStep<I + 1, INV, NZ_IN, NZ_OUT, LOOPED>::run(b);
+        if constexpr (I + 1 < TOTAL) InplaceStep<N, I + 1, INV, NZ_IN, NZ_OUT, LOOPED>::run(b);
     }
 };
 
-// 32-point FFT in place: in b[p] = x[brev5(p)], out b[k] = X[k].  Every value stays in the array slot (register)
-// it was computed into; producers write their values to the bit-reversed slot (a compile-time renaming),
-// consumers read natural order.
+// N-point FFT in place (N = 32 or 16): in b[p] = x[brev(p)], out b[k] = X[k].  Every value stays in the array
+// slot (register) it was computed into; producers write their values to the bit-reversed slot (a compile-time
+// renaming), consumers read natural order.
 template <bool INV, int NZ_IN = 32, int NZ_OUT = 32, bool LOOPED = false>
 __device__ __forceinline__ void fft32_inplace_br(float2 (&b)[32]) {
     static_assert(NZ_IN > 16 && NZ_OUT > 16, "pruning only covers the upper half");
-    InplaceStep<0, INV, NZ_IN, NZ_OUT, LOOPED>::run(b);
+    InplaceStep<32, 0, INV, NZ_IN, NZ_OUT, LOOPED>::run(b);
+}
+template <int NZ_IN = 16, int NZ_OUT = 16>
+__device__ __forceinline__ void fft16_inplace_br(float2 (&b)[16]) {
+    static_assert(NZ_IN > 8 && NZ_OUT > 8, "pruning only covers the upper half");
+    InplaceStep<16, 0, false, NZ_IN, NZ_OUT, false>::run(b);
 }
 
 // In-place (from the caller's point of view) 32-point FFT, natural order in and out.

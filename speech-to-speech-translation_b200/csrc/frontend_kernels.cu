@@ -12,6 +12,8 @@
 // written, so the HBM traffic is the hop of new samples in and the feature row out.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "../../include/s2st_b200.h"
 #include "frame_fft.cuh"
 #include "plan.h"
@@ -245,6 +247,233 @@ __global__ void __launch_bounds__(32 * kFbankWarps) k_fbank(const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Kaldi fbank, register-resident version for the two speech rates of the recipe: 16 kHz (25 ms = 400 samples,
+// FFT 512) and 8 kHz (200 samples, FFT 256).  A half-warp (16 lanes) owns a frame; everything between the
+// waveform read and the feature row stays in registers / 2 KB of shared memory per half-warp:
+//   MODE 0 (FFT 512): the real frame is packed as 256 complex points z[n] = y[2n] + i y[2n+1];
+//   MODE 1 (FFT 256): TWO frames share one transform, z[n] = yA[n] + i yB[n] (two-for-one real FFT);
+// either way a 256-point complex DFT = in-lane FFT-16 (fft32.cuh, packed f32x2 arithmetic), twiddle,
+// 16 x 16 transpose through the swizzled scratch, in-lane FFT-16, then the Hermitian split, |X|^2,
+// sparse mel, log, optional CMVN.  A half-warp walks kFbChunk consecutive frames of the ragged batch, so
+// the utterance lookup is one binary search per chunk.
+constexpr int kFbWarps = 8;
+constexpr int kFbChunk = 16;
+constexpr int kFbRows = 13;                 // rows of 16 elements that can hold window samples (13 * 16 >= 200)
+constexpr int kFbScratchBytes = 2048;       // per half-warp: 16 x 16 complex
+
+struct FbankFastParams {
+    int win, shift, n_bins, n_utts, mel_nnz;
+    long long total_frames;
+    const float2* tw16;    // [256] exp(-2 pi i k1 n2 / 256) at [k1 * 16 + n2]
+    const float2* vsplit;  // [256] -i exp(-2 pi i k / 512)            (MODE 0)
+    const float* winp;     // MODE 0: [13 * 16 * 2] (w[2n], w[2n+1]) zero padded; MODE 1: [13 * 16] w[n] zero padded
+    const int64_t* wave_offsets;
+    const int32_t* frame_offsets;
+    const float* wave;
+    const float* cmvn_mean;
+    const float* cmvn_std;
+    const int* mel_ptr;
+    const int* mel_idx;
+    const float* mel_val;
+    float* out;
+};
+
+// 16 x 16 transpose inside a half-warp: out a[brev4(r)] = (sub-lane r's) a[sub].  Same XOR swizzle as
+// warp_transpose: element (row j, column l) sits in 16-byte chunk ((l >> 1) ^ (j & 7)) of its 128-byte row.
+__device__ __forceinline__ void group_transpose16(float2 (&a)[16], char* scratch, int sub) {
+    const int wofs = sub * 8;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) *reinterpret_cast<float2*>(scratch + j * 128 + (wofs ^ ((j & 7) << 4))) = a[j];
+    __syncwarp();
+    const char* row = scratch + sub * 128;
+    const int sw = (sub & 7) << 4;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(row + ((c << 4) ^ sw));
+        a[brev4(2 * c)] = make_float2(v.x, v.y);
+        a[brev4(2 * c + 1)] = make_float2(v.z, v.w);
+    }
+    __syncwarp();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32 * kFbWarps, 4) k_fbank_fast(const __grid_constant__ FbankFastParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);                 // 256
+    float2* s_vs = s_tw + 256;                                          // 256
+    float* s_win = reinterpret_cast<float*>(s_vs + 256);                // 13 * 16 * 2
+    int2* s_mel = reinterpret_cast<int2*>(s_win + kFbRows * 32);        // mel_nnz entries (idx, val bits)
+    int* s_ptr = reinterpret_cast<int*>(s_mel + ((p.mel_nnz + 1) & ~1));  // n_bins + 1
+    char* s_scr = reinterpret_cast<char*>(s_ptr + ((p.n_bins + 1 + 3) & ~3));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & 15, grp = lane >> 4;
+    for (int i = tid; i < 256; i += blockDim.x) {
+        s_tw[i] = p.tw16[i];
+        if (MODE == 0) s_vs[i] = p.vsplit[i];
+    }
+    for (int i = tid; i < kFbRows * 16 * (MODE == 0 ? 2 : 1); i += blockDim.x) s_win[i] = p.winp[i];
+    for (int i = tid; i < p.mel_nnz; i += blockDim.x) s_mel[i] = make_int2(p.mel_idx[i], __float_as_int(p.mel_val[i]));
+    for (int i = tid; i <= p.n_bins; i += blockDim.x) s_ptr[i] = p.mel_ptr[i];
+    __syncthreads();
+    char* scratch = s_scr + (warp * 2 + grp) * kFbScratchBytes;
+    float* pwr = reinterpret_cast<float*>(scratch);
+    const int prev_lane = (lane & 16) | ((sub + 15) & 15);
+    const int n_mel_iter = (p.n_bins + 15) >> 4;
+
+    const long long n_chunks = (p.total_frames + kFbChunk - 1) / kFbChunk;
+    for (long long cp = (long long)blockIdx.x * kFbWarps + warp; 2 * cp < n_chunks; cp += (long long)gridDim.x * kFbWarps) {
+        long long f = (2 * cp + grp) * kFbChunk;
+        int u = find_utt(p.frame_offsets, p.n_utts, f < p.total_frames ? f : p.total_frames - 1);
+#pragma unroll 1
+        for (int it = 0; it < kFbChunk / (MODE + 1); ++it) {
+            // ---- resolve the frame(s) of this step
+            const float* src[MODE + 1];
+            bool valid[MODE + 1];
+#pragma unroll
+            for (int q = 0; q <= MODE; ++q) {
+                valid[q] = f < p.total_frames;
+                if (valid[q]) {
+                    while (u + 1 < p.n_utts && f >= __ldg(p.frame_offsets + u + 1)) ++u;
+                    src[q] = p.wave + __ldg(p.wave_offsets + u) + (f - __ldg(p.frame_offsets + u)) * p.shift;
+                } else {
+                    src[q] = p.wave;  // a readable address; nothing is stored for this frame
+                }
+                ++f;
+            }
+            // ---- load, frame mean
+            float2 a[16];
+            if constexpr (MODE == 0) {
+                const bool al = (reinterpret_cast<uintptr_t>(src[0]) & 7) == 0;
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) {
+                    const int j = 32 * r + 2 * sub;
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (valid[0] && j + 1 < p.win) {
+                        if (al) v = __ldg(reinterpret_cast<const float2*>(src[0] + j));
+                        else v = make_float2(__ldg(src[0] + j), __ldg(src[0] + j + 1));
+                    } else if (valid[0] && j < p.win) {
+                        v.x = __ldg(src[0] + j);
+                    }
+                    a[r] = v;
+                }
+                float sum = 0.0f;
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) sum += a[r].x + a[r].y;
+#pragma unroll
+                for (int d = 8; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                const float mean = sum / (float)p.win;
+                // DC removal, pre-emphasis 0.97 with replicate padding, povey window.  The previous sample of
+                // an element's first half is the second half of the element one sub-lane to the left.
+                float carry = 0.0f;
+                float2 y[kFbRows];
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) {
+                    const float2 c = make_float2(a[r].x - mean, a[r].y - mean);
+                    const float left = __shfl_sync(0xffffffffu, c.y, prev_lane);
+                    const float prev = sub > 0 ? left : (r == 0 ? c.x : carry);
+                    carry = left;  // for sub == 0: the last element of the row above
+                    const float2 w = *reinterpret_cast<const float2*>(s_win + 32 * r + 2 * sub);
+                    y[r] = make_float2(fmaf(-0.97f, prev, c.x) * w.x, fmaf(-0.97f, c.x, c.y) * w.y);
+                }
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) a[brev4(r)] = y[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) {
+                    const int j = 16 * r + sub;
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (j < p.win) {
+                        if (valid[0]) v.x = __ldg(src[0] + j);
+                        if (valid[1]) v.y = __ldg(src[1] + j);
+                    }
+                    a[r] = v;
+                }
+                float2 sum = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) sum = add2(sum, a[r]);
+#pragma unroll
+                for (int d = 8; d > 0; d >>= 1) {
+                    sum.x += __shfl_xor_sync(0xffffffffu, sum.x, d);
+                    sum.y += __shfl_xor_sync(0xffffffffu, sum.y, d);
+                }
+                const float2 nmean = make_float2(-(sum.x / (float)p.win), -(sum.y / (float)p.win));
+                float2 carry = make_float2(0.0f, 0.0f);
+                float2 y[kFbRows];
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) {
+                    const float2 c = add2(a[r], nmean);
+                    const float2 left = make_float2(__shfl_sync(0xffffffffu, c.x, prev_lane),
+                                                    __shfl_sync(0xffffffffu, c.y, prev_lane));
+                    const float2 prev = sub > 0 ? left : (r == 0 ? c : carry);
+                    carry = left;
+                    y[r] = mul2(fma2(prev, bcast2(-0.97f), c), bcast2(s_win[16 * r + sub]));
+                }
+#pragma unroll
+                for (int r = 0; r < kFbRows; ++r) a[brev4(r)] = y[r];
+            }
+            // ---- 256-point complex DFT (rows >= 13 of the input are the zero padding)
+            fft16_inplace_br<kFbRows, 16>(a);
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) a[k1] = cmul(a[k1], s_tw[k1 * 16 + sub]);
+            group_transpose16(a, scratch, sub);
+            fft16_inplace_br<16, 16>(a);
+            // ---- Hermitian split through the scratch (linear in k = sub + 16 * k2), power spectrum
+            float2* sc = reinterpret_cast<float2*>(scratch);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) sc[16 * k2 + sub] = a[k2];
+            __syncwarp();
+            float pw[16];
+            if constexpr (MODE == 0) {
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    const int k = 16 * k2 + sub;
+                    const float2 x2 = split_fwd(a[k2], sc[(256 - k) & 255], s_vs[k]);  // 2 X[k]
+                    pw[k2] = 0.25f * fmaf(x2.x, x2.x, x2.y * x2.y);
+                }
+            } else {
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) {
+                    const int k = 16 * k2 + sub;
+                    const float2 pz = sc[(256 - k) & 255];
+                    const float2 sa = add2(a[k2], conj2(pz)), sb = add2(a[k2], neg2(conj2(pz)));  // 2 XA, 2i XB
+                    pw[k2] = 0.25f * fmaf(sa.x, sa.x, sa.y * sa.y);
+                    pw[k2 + 8] = 0.25f * fmaf(sb.x, sb.x, sb.y * sb.y);
+                }
+            }
+            __syncwarp();
+            // power spectrum to shared memory: MODE 0 bins 0..255; MODE 1 frame A at [0, 128), frame B at [128, 256)
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) pwr[16 * k2 + sub] = pw[k2];
+            __syncwarp();
+            // ---- sparse mel, log, CMVN, store: sub-lane s owns bins s, s + 16, ...
+            for (int i = 0; i < n_mel_iter; ++i) {
+                const int m = sub + 16 * i;
+                if (m < p.n_bins) {
+                    float acc0 = 0.0f, acc1 = 0.0f;
+                    const int e1 = s_ptr[m + 1];
+                    for (int e = s_ptr[m]; e < e1; ++e) {
+                        const int2 ent = s_mel[e];
+                        const float w = __int_as_float(ent.y);
+                        acc0 = fmaf(w, pwr[ent.x], acc0);
+                        if (MODE == 1) acc1 = fmaf(w, pwr[128 + ent.x], acc1);
+                    }
+                    float v0 = logf(fmaxf(acc0, 1.1920928955078125e-07f));
+                    float v1 = MODE == 1 ? logf(fmaxf(acc1, 1.1920928955078125e-07f)) : 0.0f;
+                    if (p.cmvn_mean) {
+                        const float mu = __ldg(p.cmvn_mean + m), sd = __ldg(p.cmvn_std + m);
+                        v0 = (v0 - mu) / sd;
+                        v1 = (v1 - mu) / sd;
+                    }
+                    const long long f0 = f - (MODE + 1);
+                    if (valid[0]) p.out[f0 * p.n_bins + m] = v0;
+                    if (MODE == 1 && valid[MODE]) p.out[(f0 + 1) * p.n_bins + m] = v1;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <bool DENORM>
 __global__ void __launch_bounds__(256) k_cmvn(long long n, int n_cols, const float* __restrict__ x,
                                                const float* __restrict__ mean, const float* __restrict__ std,
@@ -381,6 +610,40 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
     p.mel_idx = plan->mel_idx;
     p.mel_val = plan->mel_val;
     p.out = out;
+    if (plan->fast_mode >= 0 && !getenv("S2ST_FBANK_GENERIC")) {
+        FbankFastParams q;
+        q.win = plan->win;
+        q.shift = plan->shift;
+        q.n_bins = plan->n_bins;
+        q.n_utts = n_utts;
+        q.mel_nnz = plan->mel_nnz;
+        q.total_frames = total_frames;
+        q.tw16 = plan->tw16;
+        q.vsplit = plan->vsplit;
+        q.winp = plan->winp;
+        q.wave_offsets = wave_offsets;
+        q.frame_offsets = frame_offsets;
+        q.wave = wave;
+        q.cmvn_mean = cmvn_mean;
+        q.cmvn_std = cmvn_std;
+        q.mel_ptr = plan->mel_ptr;
+        q.mel_idx = plan->mel_idx;
+        q.mel_val = plan->mel_val;
+        q.out = out;
+        const size_t fsmem = sizeof(float2) * 512 + sizeof(float) * kFbRows * 32 + sizeof(int2) * ((plan->mel_nnz + 1) & ~1) +
+                             sizeof(int) * ((plan->n_bins + 1 + 3) & ~3) + (size_t)kFbWarps * 2 * kFbScratchBytes;
+        const long long pair_chunks = ((total_frames + kFbChunk - 1) / kFbChunk + 1) / 2;
+        const int fgrid = (int)min((long long)plan->num_sms * 4, (pair_chunks + kFbWarps - 1) / kFbWarps);
+        if (plan->fast_mode == 0) {
+            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k_fbank_fast<0><<<fgrid, 32 * kFbWarps, fsmem, stream>>>(q);
+        } else {
+            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k_fbank_fast<1><<<fgrid, 32 * kFbWarps, fsmem, stream>>>(q);
+        }
+        S2ST_CUDA_CHECK(cudaGetLastError());
+        return S2ST_OK;
+    }
     const size_t smem = sizeof(float2) * (size_t)plan->padded * kFbankWarps;  // 2 * half per warp
     S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)200 * 1024 / smem));

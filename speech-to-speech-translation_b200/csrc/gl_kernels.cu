@@ -354,6 +354,17 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                         const float2 hi = mul2(make_float2(v.z, v.w), make_float2(wv.z, wv.w));
                         dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
                     }
+                } else if (STD && td.f0 > 0 && i0 < ws - hop && j0 + hop <= L && i0 + hop <= (T - td.f0) * hop) {
+                    // left seam of an interior strip, steady-state window sum: the previous strip adds the other
+                    // part of these samples; two contributions onto a zeroed location commute -> deterministic
+                    float4* dst = reinterpret_cast<float4*>(out + j0);
+                    float4* rg = reinterpret_cast<float4*>(ring + slot0);
+                    const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
+                    for (int q = lane; q < (hop >> 2); q += 32) {
+                        const float4 v = rg[q], wv = iw[q];
+                        rg[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        atomicAdd(dst + q, make_float4(v.x * wv.x, v.y * wv.y, v.z * wv.z, v.w * wv.w));
+                    }
                 } else {
                     emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, i0, hop, slot0, lane);
                 }
@@ -363,7 +374,28 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
             }
         }
         // the tail of the last frame: [nf*hop, (nf-1)*hop + ws)
-        emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
+        if (STD && T - td.f0 - td.nf >= 3) {
+            // right seam of an interior strip (the next strip has at least three frames, so the window sum is the
+            // steady one): add our part, and clear the same samples of the buffer the NEXT pass accumulates into
+            const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
+#pragma unroll 1
+            for (int h = 0; h < (kStdWs - kStdHop) / kStdHop; ++h) {
+                const int j0 = j_base + (td.nf + h) * hop;
+                float4* dst = reinterpret_cast<float4*>(out + j0);
+                float4* zn = reinterpret_cast<float4*>(znext + j0);
+                float4* rg = reinterpret_cast<float4*>(ring + slot0);
+                for (int q = lane; q < (hop >> 2); q += 32) {
+                    const float4 v = rg[q], wv = iw[q];
+                    rg[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    atomicAdd(dst + q, make_float4(v.x * wv.x, v.y * wv.y, v.z * wv.z, v.w * wv.w));
+                    zn[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                slot0 += hop;
+                if (slot0 >= ws) slot0 -= ws;
+            }
+        } else {
+            emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
+        }
         __syncwarp();
     }
 }

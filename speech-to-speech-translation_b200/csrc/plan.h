@@ -43,6 +43,12 @@ struct s2st_fbank_plan {
     int* mel_idx;
     float* mel_val;
     int mel_nnz;
+    // register-resident kernel (k_fbank_fast): -1 = not available for this rate, 0 = FFT 512 (one frame per
+    // 256-point complex transform), 1 = FFT 256 (two frames per transform)
+    int fast_mode;
+    float2* tw16;       // [256] exp(-2 pi i k1 n2 / 256) at [k1 * 16 + n2]
+    float2* vsplit;     // [256] -i exp(-2 pi i k / 512)
+    float* winp;        // window in the kernel's register layout, zero padded (see FbankFastParams)
 };
 
 namespace s2st {
