@@ -519,9 +519,33 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
         const int per_row = p->fast_mode == 0 ? 32 : 16;
         std::vector<float> winp(13 * per_row, 0.0f);
         for (int i = 0; i < win; ++i) winp[i] = window[i];
+        // column view of the mel bank: every FFT bin must feed at most two adjacent mel bins (true for Kaldi's
+        // pairwise-overlapping triangles); the table is stored in the order the kernel's sub-lanes read it
+        const int kpl = p->fast_mode == 0 ? 16 : 8;  // FFT bins per sub-lane
+        std::vector<float4> col(256, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        bool ok = n_bins + 1 <= 4096;
+        for (int k = 0; k < nfb && ok; ++k) {
+            int first = -1, count = 0, last = -1;
+            for (int b = 0; b < n_bins; ++b)
+                if (dense[(size_t)b * (nfb + 1) + k] != 0.0f) {
+                    if (first < 0) first = b;
+                    last = b;
+                    ++count;
+                }
+            if (count > 2 || (count == 2 && last != first + 1)) ok = false;
+            const int b = first < 0 ? 0 : first;
+            const float w0 = first < 0 ? 0.0f : dense[(size_t)b * (nfb + 1) + k];
+            const float w1 = (count == 2) ? dense[(size_t)(b + 1) * (nfb + 1) + k] : 0.0f;
+            int bi = b;
+            float bf;
+            std::memcpy(&bf, &bi, sizeof(float));
+            col[(k % kpl) * 16 + k / kpl] = make_float4(w0, w1, bf, 0.0f);
+        }
+        if (!ok) p->fast_mode = -1;
         if (rc == S2ST_OK) rc = upload(&p->tw16, tw16);
         if (rc == S2ST_OK) rc = upload(&p->vsplit, vsplit);
         if (rc == S2ST_OK) rc = upload(&p->winp, winp);
+        if (rc == S2ST_OK) rc = upload(&p->mel_col, col);
     }
     if (rc == S2ST_OK) rc = upload(&p->window, window);
     if (rc == S2ST_OK) rc = upload(&p->tw, tw);
@@ -544,6 +568,7 @@ int s2st_fbank_plan_destroy(s2st_fbank_plan* plan) {
     cudaFree(plan->tw16);
     cudaFree(plan->vsplit);
     cudaFree(plan->winp);
+    cudaFree(plan->mel_col);
     cudaFree(plan->mel_ptr);
     cudaFree(plan->mel_idx);
     cudaFree(plan->mel_val);

@@ -257,6 +257,11 @@ __global__ void __launch_bounds__(32 * kFbankWarps) k_fbank(const __grid_constan
 // 16 x 16 transpose through the swizzled scratch, in-lane FFT-16, then the Hermitian split, |X|^2,
 // sparse mel, log, optional CMVN.  A half-warp walks kFbChunk consecutive frames of the ragged batch, so
 // the utterance lookup is one binary search per chunk.
+// Mel projection: Kaldi's triangles overlap pairwise, so every FFT bin k feeds at most two ADJACENT mel bins
+// (checked when the plan is built).  Each sub-lane walks a contiguous run of bins with a column table
+// (weight into bin b, weight into bin b + 1, b), accumulates in registers while b stays the same and adds
+// the partial sums to a small shared-memory accumulator when it changes: balanced across lanes (the row-wise
+// gather is not: high mel bins are ten times wider than low ones) and free of dependent index loads.
 constexpr int kFbWarps = 8;
 constexpr int kFbChunk = 16;
 constexpr int kFbRows = 13;                 // rows of 16 elements that can hold window samples (13 * 16 >= 200)
@@ -273,7 +278,8 @@ struct FbankFastParams {
     const float* wave;
     const float* cmvn_mean;
     const float* cmvn_std;
-    const int* mel_ptr;
+    const float4* mel_col;  // MODE 0: [256] (w into bin b, w into bin b + 1, b, 0) in the order the sub-lanes read it
+    const int* mel_ptr;     // MODE 1: CSR rows of the mel bank (its 128-bin rows are short: the row gather wins)
     const int* mel_idx;
     const float* mel_val;
     float* out;
@@ -298,25 +304,33 @@ __device__ __forceinline__ void group_transpose16(float2 (&a)[16], char* scratch
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(32 * kFbWarps, 4) k_fbank_fast(const __grid_constant__ FbankFastParams p) {
+__global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast(const __grid_constant__ FbankFastParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);                 // 256
     float2* s_vs = s_tw + 256;                                          // 256
     float* s_win = reinterpret_cast<float*>(s_vs + 256);                // 13 * 16 * 2
-    int2* s_mel = reinterpret_cast<int2*>(s_win + kFbRows * 32);        // mel_nnz entries (idx, val bits)
-    int* s_ptr = reinterpret_cast<int*>(s_mel + ((p.mel_nnz + 1) & ~1));  // n_bins + 1
-    char* s_scr = reinterpret_cast<char*>(s_ptr + ((p.n_bins + 1 + 3) & ~3));
+    float4* s_col = reinterpret_cast<float4*>(s_win + kFbRows * 32);    // MODE 0: 256 column entries
+    int2* s_mel = reinterpret_cast<int2*>(s_col);                       // MODE 1: mel_nnz CSR entries (idx, val bits)
+    int* s_ptr = reinterpret_cast<int*>(s_mel + ((p.mel_nnz + 1) & ~1));  //         n_bins + 1 row pointers
+    char* s_scr = MODE == 0 ? reinterpret_cast<char*>(s_col + 256)
+                            : reinterpret_cast<char*>(s_ptr + ((p.n_bins + 1 + 3) & ~3));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & 15, grp = lane >> 4;
     for (int i = tid; i < 256; i += blockDim.x) {
         s_tw[i] = p.tw16[i];
         if (MODE == 0) s_vs[i] = p.vsplit[i];
     }
     for (int i = tid; i < kFbRows * 16 * (MODE == 0 ? 2 : 1); i += blockDim.x) s_win[i] = p.winp[i];
-    for (int i = tid; i < p.mel_nnz; i += blockDim.x) s_mel[i] = make_int2(p.mel_idx[i], __float_as_int(p.mel_val[i]));
-    for (int i = tid; i <= p.n_bins; i += blockDim.x) s_ptr[i] = p.mel_ptr[i];
+    if constexpr (MODE == 0) {
+        for (int i = tid; i < 256; i += blockDim.x) s_col[i] = p.mel_col[i];
+    } else {
+        for (int i = tid; i < p.mel_nnz; i += blockDim.x) s_mel[i] = make_int2(p.mel_idx[i], __float_as_int(p.mel_val[i]));
+        for (int i = tid; i <= p.n_bins; i += blockDim.x) s_ptr[i] = p.mel_ptr[i];
+    }
     __syncthreads();
-    char* scratch = s_scr + (warp * 2 + grp) * kFbScratchBytes;
+    const int acc_floats = ((MODE + 1) * (p.n_bins + 1) + 3) & ~3;
+    char* scratch = s_scr + (size_t)(warp * 2 + grp) * (kFbScratchBytes + 4 * acc_floats);
     float* pwr = reinterpret_cast<float*>(scratch);
+    float* macc = reinterpret_cast<float*>(scratch + kFbScratchBytes);
     const int prev_lane = (lane & 16) | ((sub + 15) & 15);
     const int n_mel_iter = (p.n_bins + 15) >> 4;
 
@@ -441,24 +455,62 @@ __global__ void __launch_bounds__(32 * kFbWarps, 4) k_fbank_fast(const __grid_co
                 }
             }
             __syncwarp();
-            // power spectrum to shared memory: MODE 0 bins 0..255; MODE 1 frame A at [0, 128), frame B at [128, 256)
+            if constexpr (MODE == 0) {
+                // power spectrum to shared memory, bin k at [(k & 15) * 17 + (k >> 4)] (conflict-free for this write
+                // and for the run-per-lane read below)
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) pwr[16 * k2 + sub] = pw[k2];
+                for (int k2 = 0; k2 < 16; ++k2) pwr[sub * 17 + k2] = pw[k2];
+                for (int i = sub; i < acc_floats; i += 16) macc[i] = 0.0f;
+                __syncwarp();
+                // mel: sub-lane s owns FFT bins [16 s, 16 s + 16)
+                float lo = 0.0f, hi = 0.0f;
+                int cur = -1;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 c = s_col[j * 16 + sub];
+                    const int b = __float_as_int(c.z);
+                    if (b != cur) {
+                        if (cur >= 0) {
+                            atomicAdd(macc + cur, lo);
+                            atomicAdd(macc + cur + 1, hi);
+                        }
+                        cur = b;
+                        lo = hi = 0.0f;
+                    }
+                    const float p0 = pwr[j * 17 + sub];  // bin k = 16 sub + j
+                    lo = fmaf(c.x, p0, lo);
+                    hi = fmaf(c.y, p0, hi);
+                }
+                atomicAdd(macc + cur, lo);
+                atomicAdd(macc + cur + 1, hi);
+            } else {
+                // frame A at [0, 128), frame B at [128, 256); row gather: sub-lane s owns mel bins s, s + 16, ...
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) pwr[16 * k2 + sub] = pw[k2];
+                __syncwarp();
+                for (int i = 0; i < n_mel_iter; ++i) {
+                    const int m = sub + 16 * i;
+                    if (m < p.n_bins) {
+                        float acc0 = 0.0f, acc1 = 0.0f;
+                        const int e1 = s_ptr[m + 1];
+                        for (int e = s_ptr[m]; e < e1; ++e) {
+                            const int2 ent = s_mel[e];
+                            const float w = __int_as_float(ent.y);
+                            acc0 = fmaf(w, pwr[ent.x], acc0);
+                            acc1 = fmaf(w, pwr[128 + ent.x], acc1);
+                        }
+                        macc[m] = acc0;
+                        macc[p.n_bins + 1 + m] = acc1;
+                    }
+                }
+            }
             __syncwarp();
-            // ---- sparse mel, log, CMVN, store: sub-lane s owns bins s, s + 16, ...
+            // ---- log, CMVN, store: sub-lane s owns bins s, s + 16, ...
             for (int i = 0; i < n_mel_iter; ++i) {
                 const int m = sub + 16 * i;
                 if (m < p.n_bins) {
-                    float acc0 = 0.0f, acc1 = 0.0f;
-                    const int e1 = s_ptr[m + 1];
-                    for (int e = s_ptr[m]; e < e1; ++e) {
-                        const int2 ent = s_mel[e];
-                        const float w = __int_as_float(ent.y);
-                        acc0 = fmaf(w, pwr[ent.x], acc0);
-                        if (MODE == 1) acc1 = fmaf(w, pwr[128 + ent.x], acc1);
-                    }
-                    float v0 = logf(fmaxf(acc0, 1.1920928955078125e-07f));
-                    float v1 = MODE == 1 ? logf(fmaxf(acc1, 1.1920928955078125e-07f)) : 0.0f;
+                    float v0 = logf(fmaxf(macc[m], 1.1920928955078125e-07f));
+                    float v1 = MODE == 1 ? logf(fmaxf(macc[p.n_bins + 1 + m], 1.1920928955078125e-07f)) : 0.0f;
                     if (p.cmvn_mean) {
                         const float mu = __ldg(p.cmvn_mean + m), sd = __ldg(p.cmvn_std + m);
                         v0 = (v0 - mu) / sd;
@@ -616,7 +668,6 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
         q.shift = plan->shift;
         q.n_bins = plan->n_bins;
         q.n_utts = n_utts;
-        q.mel_nnz = plan->mel_nnz;
         q.total_frames = total_frames;
         q.tw16 = plan->tw16;
         q.vsplit = plan->vsplit;
@@ -626,14 +677,19 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
         q.wave = wave;
         q.cmvn_mean = cmvn_mean;
         q.cmvn_std = cmvn_std;
+        q.mel_col = plan->mel_col;
         q.mel_ptr = plan->mel_ptr;
         q.mel_idx = plan->mel_idx;
         q.mel_val = plan->mel_val;
+        q.mel_nnz = plan->mel_nnz;
         q.out = out;
-        const size_t fsmem = sizeof(float2) * 512 + sizeof(float) * kFbRows * 32 + sizeof(int2) * ((plan->mel_nnz + 1) & ~1) +
-                             sizeof(int) * ((plan->n_bins + 1 + 3) & ~3) + (size_t)kFbWarps * 2 * kFbScratchBytes;
+        const size_t acc_floats = (size_t)(((plan->fast_mode + 1) * (plan->n_bins + 1) + 3) & ~3);
+        const size_t tab = plan->fast_mode == 0 ? sizeof(float4) * 256
+                                                : sizeof(int2) * ((plan->mel_nnz + 1) & ~1) + sizeof(int) * ((plan->n_bins + 1 + 3) & ~3);
+        const size_t fsmem = sizeof(float2) * 512 + sizeof(float) * kFbRows * 32 + tab +
+                             (size_t)kFbWarps * 2 * (kFbScratchBytes + 4 * acc_floats);
         const long long pair_chunks = ((total_frames + kFbChunk - 1) / kFbChunk + 1) / 2;
-        const int fgrid = (int)min((long long)plan->num_sms * 4, (pair_chunks + kFbWarps - 1) / kFbWarps);
+        const int fgrid = (int)min((long long)plan->num_sms * (plan->fast_mode == 0 ? 4 : 3), (pair_chunks + kFbWarps - 1) / kFbWarps);
         if (plan->fast_mode == 0) {
             S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
             k_fbank_fast<0><<<fgrid, 32 * kFbWarps, fsmem, stream>>>(q);

@@ -49,6 +49,7 @@ struct s2st_fbank_plan {
     float2* tw16;       // [256] exp(-2 pi i k1 n2 / 256) at [k1 * 16 + n2]
     float2* vsplit;     // [256] -i exp(-2 pi i k / 512)
     float* winp;        // window in the kernel's register layout, zero padded (see FbankFastParams)
+    float4* mel_col;    // [256] per FFT bin: (weight into mel bin b, weight into b + 1, b as int bits, 0)
 };
 
 namespace s2st {
