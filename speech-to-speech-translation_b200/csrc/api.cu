@@ -77,6 +77,7 @@ void free_plan_members(s2st_plan* p) {
     cudaFree(p->mel_ptr);
     cudaFree(p->mel_idx);
     cudaFree(p->mel_val);
+    cudaFree(p->mel_col);
 }
 
 }  // namespace
@@ -223,6 +224,29 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         rc = upload(&p->mel_ptr, ptr);
         if (rc == S2ST_OK) rc = upload(&p->mel_idx, idx);
         if (rc == S2ST_OK) rc = upload(&p->mel_val, val);
+        // column view (k_logmel_fast)
+        std::vector<float4> col(704, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        bool ok = true;
+        for (int k = 0; k < kBins && ok; ++k) {
+            int first = -1, last = -1, count = 0;
+            for (int m = 0; m < n_mels; ++m)
+                if (mel_host[(size_t)m * kBins + k] != 0.0f) {
+                    if (first < 0) first = m;
+                    last = m;
+                    ++count;
+                }
+            if (count == 0) continue;
+            if (k >= 704 || count > 2 || (count == 2 && last != first + 1)) {
+                ok = false;
+                break;
+            }
+            int bi = first;
+            float bf;
+            std::memcpy(&bf, &bi, sizeof(float));
+            col[(k % 22) * 32 + k / 22] = make_float4(mel_host[(size_t)first * kBins + k],
+                                                      count == 2 ? mel_host[(size_t)last * kBins + k] : 0.0f, bf, 0.0f);
+        }
+        if (ok && rc == S2ST_OK) rc = upload(&p->mel_col, col);
     }
     if (rc != S2ST_OK) {
         free_plan_members(p);

@@ -22,6 +22,27 @@ namespace s2st {
 
 namespace {
 
+// One step of the column-wise mel accumulation (see k_fbank_fast): FFT bin with table entry c = (weight into mel
+// bin b, weight into b + 1, b) and value v.  While b stays the same the two partial sums stay in registers; when it
+// changes they are added to the shared accumulator.  Branch-free (predicated red.shared), because the lanes of a
+// warp change bins at different steps and a divergent flush block would run at almost every step.
+__device__ __forceinline__ void mel_col_step(float& lo, float& hi, int& cur, const float4 c, const float v, float* macc) {
+    const int b = __float_as_int(c.z);
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(macc + cur);
+    asm volatile(
+        "{ .reg .pred q; setp.ne.s32 q, %0, %1; @q red.shared.add.f32 [%2], %3; @q red.shared.add.f32 [%2+4], %4; }" ::"r"(b),
+        "r"(cur), "r"(addr), "f"(lo), "f"(hi)
+        : "memory");
+    const bool changed = b != cur;
+    lo = fmaf(c.x, v, changed ? 0.0f : lo);
+    hi = fmaf(c.y, v, changed ? 0.0f : hi);
+    cur = b;
+}
+__device__ __forceinline__ void mel_col_flush(const float lo, const float hi, const int cur, float* macc) {
+    atomicAdd(macc + cur, lo);
+    atomicAdd(macc + cur + 1, hi);
+}
+
 __device__ __forceinline__ int find_utt(const int32_t* __restrict__ fo, int n_utts, long long f) {
     int lo = 0, hi = n_utts - 1;  // last u with fo[u] <= f (utterances with zero frames are skipped)
     while (lo < hi) {
@@ -49,6 +70,7 @@ struct StftParams {
     const int* mel_ptr;
     const int* mel_idx;
     const float* mel_val;
+    const float4* mel_col;  // k_logmel_fast: [22 * 32] column view of the mel bank (see s2st_plan::mel_col)
 };
 
 // MODE 0: magnitude (+ optional phase) [F,] rows; MODE 1: log-mel (+ optional CMVN) rows.
@@ -122,6 +144,106 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
                 for (int e = __ldg(p.mel_ptr + m); e < e1; ++e)
                     acc = fmaf(__ldg(p.mel_val + e), spec[__ldg(p.mel_idx + e)], acc);
                 float v = logf(fmaxf(acc, p.eps));
+                if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
+                p.logmel_out[f * p.n_mels + m] = v;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// logmelspec80, fast path (mel bank confined to bins < 704 with pairwise-overlapping triangles, i.e. the
+// recipe's f_max = 8 kHz Slaney bank): a warp walks kLmChunk consecutive frames of the ragged batch (one
+// utterance lookup per chunk); per frame: window -> in-place pruned 1024-point transform (fwd1024) -> pruned
+// Hermitian split (22 rows) -> |X| -> column-wise mel (each lane owns 22 consecutive bins, see k_fbank_fast) ->
+// log(max(., eps)) -> optional CMVN -> one 320-byte row.
+constexpr int kLmChunk = 8;
+constexpr int kLmCols = 32 * kPrunedRows;      // 704 spectrum bins
+constexpr int kLmAccFloats = 132;              // n_mels + 1 <= 129 accumulators, padded
+template <int NZ>
+__global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ StftParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+    float2* s_vtab = s_tw + 1024;
+    float4* s_col = reinterpret_cast<float4*>(s_vtab + 1024);            // [22][32]: entry of bin 22 * lane + j at [j][lane]
+    float* s_win = reinterpret_cast<float*>(s_col + kLmCols);
+    float* s_warp = s_win + 64 * NZ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 1024; i += blockDim.x) {
+        s_tw[i] = p.tw[i];
+        s_vtab[i] = p.vtab[i];
+    }
+    for (int i = tid; i < kLmCols; i += blockDim.x) s_col[i] = p.mel_col[i];
+    for (int i = tid; i < 64 * NZ; i += blockDim.x) s_win[i] = p.win_a[i];
+    __syncthreads();
+    float* scratch = s_warp + warp * (kScratchFloats + kLmAccFloats);
+    float* macc = scratch + kScratchFloats;
+    const long long n_chunks = (p.total_frames + kLmChunk - 1) / kLmChunk;
+    for (long long chunk = (long long)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (long long)gridDim.x * 8) {
+        long long f = chunk * kLmChunk;
+        int u = find_utt(p.frame_offsets, p.n_utts, f);
+        {
+            // the chunk's frames are (mostly) consecutive hops of one utterance: ask L2 for their samples now
+            const long long woff = __ldg(p.wave_offsets + u);
+            const long long n = __ldg(p.wave_offsets + u + 1) - woff;
+            const long long b0 = (f - __ldg(p.frame_offsets + u)) * p.hop + p.rot - p.half;
+            const long long span = (long long)(kLmChunk - 1) * p.hop + 64 * NZ;
+            for (long long j = b0 + 32 * lane; j < b0 + span; j += 32 * 32)
+                if (j >= 0 && j < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wave + woff + j));
+        }
+#pragma unroll 1
+        for (int it = 0; it < kLmChunk && f < p.total_frames; ++it, ++f) {
+            while (u + 1 < p.n_utts && f >= __ldg(p.frame_offsets + u + 1)) ++u;
+            const int t = (int)(f - __ldg(p.frame_offsets + u));
+            const long long woff = __ldg(p.wave_offsets + u);
+            const int n = (int)(__ldg(p.wave_offsets + u + 1) - woff);
+            const float* src = p.wave + woff;
+            const int base0 = t * p.hop + p.rot - p.half;
+            float2 a[32];
+            if (base0 >= 0 && base0 + 64 * NZ <= n && (((woff + base0) & 1) == 0)) {
+                const float2* s2 = reinterpret_cast<const float2*>(src + base0) + lane;
+#pragma unroll
+                for (int r = 0; r < NZ; ++r) a[brev5(r)] = __ldg(s2 + 32 * r);
+            } else {
+                const int base = base0 + 2 * lane;
+#pragma unroll
+                for (int r = 0; r < NZ; ++r) {
+                    int j0 = base + 64 * r, j1 = j0 + 1;
+                    j0 = j0 < 0 ? -j0 : j0;
+                    j1 = j1 < 0 ? -j1 : j1;
+                    j0 = j0 >= n ? 2 * (n - 1) - j0 : j0;
+                    j1 = j1 >= n ? 2 * (n - 1) - j1 : j1;
+                    j0 = min(max(j0, 0), n - 1);  // only reachable where the window is zero
+                    j1 = min(max(j1, 0), n - 1);
+                    a[brev5(r)] = make_float2(__ldg(src + j0), __ldg(src + j1));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NZ; ++r)
+                a[brev5(r)] = mul2(a[brev5(r)], *reinterpret_cast<const float2*>(s_win + 64 * r + 2 * lane));
+            fwd1024<(NZ > 16 ? NZ : 32), 32>(a, scratch, s_tw, lane);
+            float nyq;
+            fwd_split<true>(a, nyq, scratch, s_vtab, lane);
+            // |X| (the split returns 2 X) to shared memory, linear in k; clear the mel accumulators
+#pragma unroll
+            for (int r = 0; r < kPrunedRows; ++r) {
+                float mag;  // |2 X|: MUFU.SQRT (2 ulp) instead of the IEEE sequence; the features are compared at 1e-5
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(a[r].x, a[r].x, a[r].y * a[r].y)));
+                scratch[32 * r + lane] = 0.5f * mag;
+            }
+            for (int i = lane; i < kLmAccFloats; i += 32) macc[i] = 0.0f;
+            __syncwarp();
+            {
+                float lo = 0.0f, hi = 0.0f;
+                int cur = __float_as_int(s_col[lane].z);
+                const float* sp = scratch + kPrunedRows * lane;
+#pragma unroll
+                for (int j = 0; j < kPrunedRows; ++j) mel_col_step(lo, hi, cur, s_col[j * 32 + lane], sp[j], macc);
+                mel_col_flush(lo, hi, cur, macc);
+            }
+            __syncwarp();
+            for (int m = lane; m < p.n_mels; m += 32) {
+                float v = logf(fmaxf(macc[m], p.eps));
                 if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
                 p.logmel_out[f * p.n_mels + m] = v;
             }
@@ -464,25 +586,10 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast
                 __syncwarp();
                 // mel: sub-lane s owns FFT bins [16 s, 16 s + 16)
                 float lo = 0.0f, hi = 0.0f;
-                int cur = -1;
+                int cur = __float_as_int(s_col[sub].z);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 c = s_col[j * 16 + sub];
-                    const int b = __float_as_int(c.z);
-                    if (b != cur) {
-                        if (cur >= 0) {
-                            atomicAdd(macc + cur, lo);
-                            atomicAdd(macc + cur + 1, hi);
-                        }
-                        cur = b;
-                        lo = hi = 0.0f;
-                    }
-                    const float p0 = pwr[j * 17 + sub];  // bin k = 16 sub + j
-                    lo = fmaf(c.x, p0, lo);
-                    hi = fmaf(c.y, p0, hi);
-                }
-                atomicAdd(macc + cur, lo);
-                atomicAdd(macc + cur + 1, hi);
+                for (int j = 0; j < 16; ++j) mel_col_step(lo, hi, cur, s_col[j * 16 + sub], pwr[j * 17 + sub], macc);  // bin 16 sub + j
+                mel_col_flush(lo, hi, cur, macc);
             } else {
                 // frame A at [0, 128), frame B at [128, 256); row gather: sub-lane s owns mel bins s, s + 16, ...
 #pragma unroll
@@ -608,6 +715,22 @@ int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const
     p.mel_ptr = plan->mel_ptr;
     p.mel_idx = plan->mel_idx;
     p.mel_val = plan->mel_val;
+    p.mel_col = plan->mel_col;
+    if (logmel_out && plan->mel_col && plan->n_mels + 1 <= kLmAccFloats && !getenv("S2ST_LOGMEL_GENERIC")) {
+        const size_t fsmem = sizeof(float2) * 2048 + sizeof(float4) * kLmCols +
+                             sizeof(float) * (plan->wp + 8 * (kScratchFloats + kLmAccFloats));
+        const long long chunks = (total_frames + kLmChunk - 1) / kLmChunk;
+        const int fgrid = (int)min((long long)plan->num_sms * 2, (chunks + 7) / 8);
+        if (plan->nz == 19) {
+            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_logmel_fast<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k_logmel_fast<19><<<fgrid, 256, fsmem, stream>>>(p);
+        } else {
+            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_logmel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k_logmel_fast<32><<<fgrid, 256, fsmem, stream>>>(p);
+        }
+        S2ST_CUDA_CHECK(cudaGetLastError());
+        return S2ST_OK;
+    }
     const size_t smem = sizeof(float2) * 2048 + sizeof(float) * (8 * kScratchFloats + plan->wp);
     const int grid = (int)min((long long)plan->num_sms * 2, (total_frames + 7) / 8);
 #define S2ST_LAUNCH_STFT(NZV, MODEV)                                                                          \

@@ -25,6 +25,9 @@ struct s2st_plan {
     float* mel_val;     // [nnz]
     int mel_nnz;
     int mel_max_row;    // longest CSR row
+    float4* mel_col;    // column view for k_logmel_fast, or NULL when the bank does not qualify: every bin < 704
+                        // feeds at most two adjacent mel bins, bins >= 704 feed none; entry of bin 22 * l + j at
+                        // [j * 32 + l] = (weight into mel bin b, weight into b + 1, b as int bits, 0)
     // profiling aid (s2st_plan_set_pass_timing): CUDA events around every Griffin-Lim pass of the LAST call
     int strip_frames;             // 0 = choose per call (s2st_plan_set_strip_frames)
     int timing_enabled;
