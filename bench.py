@@ -53,8 +53,8 @@ def synth_logmel_np(T, seed):
 
 def measured_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_pass launch on this workload, from the
-    committed `ncu --set full` capture (profiles/r01_glpass_final_ncu_summary.txt); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_glpass_final_ncu_summary.txt")
+    committed `ncu --set full` capture (profiles/r01_glpass_current_ncu_summary.txt); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_glpass_current_ncu_summary.txt")
     try:
         tot = 0.0
         for line in open(path):
@@ -75,9 +75,9 @@ def peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons of one GPU through NVML (what the nvidia-smi --query-gpu clocks line
-    reports).  sample() is called by the benchmark loop itself between steps of the timed region, while
-    the GPU still has a deep queue of launches -- a polling thread or subprocess was measurably delaying
-    kernel launches on this driver."""
+    reports).  sample() is called by the benchmark itself once every step of the timed region is enqueued and
+    the GPU is still executing them -- a polling thread, a subprocess, or calls between steps were measurably
+    delaying kernel launches on this driver."""
 
     def __init__(self, gpu_index):
         self.samples, self.reasons, self.err, self.sm_max = [], set(), None, None
@@ -118,7 +118,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
         sm = self.samples
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
-                "reasons": sorted(self.reasons), "source": "NVML, sampled between steps inside the timed region"}
+                "samples_under_load": getattr(self, "under_load", len(sm)), "reasons": sorted(self.reasons),
+                "source": "NVML, sampled inside the timed region while the GPU drains the enqueued steps"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,9 +241,17 @@ def run_ours(args):
     ev0.record()
     for step in range(args.steps):
         wave_d = voc.synthesize_flat(logmel_d, frames, phase_d)
-        if sampler and step % 8 == 4:  # the GPU is several steps behind the host here: it stays busy
-            sampler.sample()
     ev1.record()
+    # Clocks / throttle reasons are sampled NOW: everything of the timed region is enqueued, the GPU is still
+    # working through the queue (the host runs up to ~15 steps ahead), and no launch can be delayed by a slow
+    # NVML call (on some boxes one call takes tens of ms and, issued between steps, drained the launch queue).
+    if sampler:
+        while not ev1.query() and len(sampler.samples) < 8:
+            sampler.sample()
+            time.sleep(0.005)
+        sampler.under_load = len(sampler.samples)
+        if not sampler.samples:
+            sampler.sample()
     barrier()
     clocks = sampler.stop() if sampler else None
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
@@ -265,11 +274,20 @@ def run_ours(args):
     # initial phase is drawn inside the timed call in both arms: the reference draws it with numpy on the
     # host (vocoder.py:103), the library draws the same distribution on the device (phase_fm=None).  The
     # variant that uploads a host-drawn phase (4.1 KB per frame, what the parity tests use) is reported too.
+    # Steps are fed back to back like generate_waveform.py feeds batches: synthesize_host() downloads on a copy stream,
+    # so step i's D2H overlaps step i+1's H2D and kernels; two host output buffers alternate, and the timed region ends
+    # only when every download has landed (barrier() synchronises the whole device).
+    wave_h2 = torch.empty_like(wave_h).pin_memory()
+    e2e_bufs, e2e_events = [wave_h, wave_h2], [None, None]
+    e2e_count = [0]
+
     def e2e_step(host_phase):
-        lm = logmel_h.to(dev, non_blocking=True)
-        ph = phase_h.to(dev, non_blocking=True) if host_phase else None
-        w = voc.synthesize_flat(lm, frames, ph, seed=1234)
-        wave_h.copy_(w, non_blocking=True)
+        i = e2e_count[0] % 2
+        e2e_count[0] += 1
+        if e2e_events[i] is not None:
+            e2e_events[i].synchronize()  # the buffer's previous download must be complete before it is reused
+        e2e_events[i] = voc.synthesize_host(logmel_h, frames, e2e_bufs[i], device=dev,
+                                            phase_host=phase_h if host_phase else None, seed=1234)
 
     def time_e2e(host_phase):
         for _ in range(min(args.warmup, 3)):
@@ -287,7 +305,8 @@ def run_ours(args):
 
     e2e_host_ms = time_e2e(True)
     e2e_ms = time_e2e(False)
-    assert torch.isfinite(wave_h).all()
+    assert torch.isfinite(wave_h).all() and torch.isfinite(wave_h2).all()
+    e2e_count[0] = 0
     e2e_step(True)  # leave the host-phase result in wave_h for the parity spot check below
     torch.cuda.synchronize()
 
@@ -321,12 +340,12 @@ def run_ours(args):
         "e2e": {"value": world * audio_s / (e2e_ms * 1e-3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": int(logmel_h.numel() * 4),
                 "d2h_bytes_per_step": int(wave_h.numel() * 4), "ms_per_step": e2e_ms,
-                "api": "GriffinLimVocoder.synthesize_flat(logmel from pinned host memory, phase_fm=None: initial "
-                       "phase drawn on the device) + D2H of the waveforms",
+                "api": "GriffinLimVocoder.synthesize_host(pinned log-mel in, pinned waveforms out; initial phase drawn on "
+                       "the device; the D2H of step i runs on a copy stream and overlaps step i+1)",
                 "with_host_drawn_phase": {"value": world * audio_s / (e2e_host_ms * 1e-3), "ms_per_step": e2e_host_ms,
                                           "h2d_bytes_per_step": int(logmel_h.numel() * 4 + phase_h.numel() * 4)}},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_gl_pass<19,false> (fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
+        "roofline": {"bound": "hbm", "kernel": "k_gl_pass<19,false,true,true> (fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": measured_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
                      "launch_ms": iter_ms, "launches_per_step": N_ITER,

@@ -255,6 +255,35 @@ class GriffinLimVocoder(nn.Module):
         return self._synthesize_flat(logmel_flat.contiguous(), frames, phase_fm, n_iter, dev, seed)
 
 
+    def synthesize_host(self, logmel_host: torch.Tensor, frames: Sequence[int], wave_host: torch.Tensor,
+                        device=None, phase_host: Optional[torch.Tensor] = None, n_iter: Optional[int] = None,
+                        seed: int = 0) -> torch.cuda.Event:
+        """Host buffers in, host buffer out, pipelined: uploads ``logmel_host`` [sum T, n_mels] (pinned), synthesises
+        on ``device`` and downloads the concatenated waveforms into ``wave_host`` (pinned, sum (T_i-1)*hop floats).
+
+        The download runs on a private copy stream, so the next call's upload and kernels overlap it (this is how
+        generate_waveform.py would feed batch after batch).  Returns the CUDA event that marks ``wave_host`` complete;
+        callers that reuse ``wave_host`` must synchronise on it (or on the device) first."""
+        dev = require_cuda(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        assert logmel_host.dtype == torch.float32 and wave_host.dtype == torch.float32
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = {}
+        cs = self._copy_streams.get(dev.index)
+        if cs is None:
+            cs = self._copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+        lm = logmel_host.to(dev, non_blocking=True)
+        ph = phase_host.to(dev, non_blocking=True) if phase_host is not None else None
+        wave = self.synthesize_flat(lm, frames, ph, n_iter=n_iter, seed=seed)
+        main = torch.cuda.current_stream(dev)
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            wave_host[: wave.numel()].copy_(wave, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+        wave.record_stream(cs)  # keep the device buffer alive until the download has read it
+        return done
+
+
 def get_vocoder(args, data_cfg):
     if args.vocoder == "griffin_lim":
         return GriffinLimVocoder.from_data_cfg(args, data_cfg)

@@ -297,3 +297,20 @@ def test_griffin_lim_module_forward_on_magnitudes(pkg, voc, basis):
     gl.n_iter = 64
     ref = ogl.griffin_lim(mag, seeded_phase(9, T), 3, **CFG)
     assert ogl.rel_l2(y, ref) < 1e-4
+
+
+def test_host_pipeline_matches_flat_and_overlaps_buffers(pkg, voc):
+    """synthesize_host (pinned in, pinned out, download on a copy stream) == synthesize_flat, also when calls are
+    issued back to back into alternating host buffers."""
+    frames = [40, 57, 33]
+    x = torch.from_numpy(np.concatenate([synth_logmel(T, 50 + i) for i, T in enumerate(frames)]))
+    ph = torch.from_numpy(np.concatenate([seeded_phase(60 + i, T).T for i, T in enumerate(frames)]).astype(np.float32))
+    want = voc.synthesize_flat(x.cuda(), frames, ph.cuda().contiguous(), n_iter=6).cpu()
+    xh, phh = x.pin_memory(), ph.contiguous().pin_memory()
+    outs = [torch.zeros(want.numel() + 7).pin_memory() for _ in range(2)]
+    events = [voc.synthesize_host(xh, frames, outs[i % 2], phase_host=phh, n_iter=6) for i in range(4)]
+    for e in events:
+        e.synchronize()
+    for o in outs:
+        assert torch.equal(o[: want.numel()], want)
+        assert float(o[want.numel():].abs().max()) == 0.0
