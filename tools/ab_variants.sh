@@ -3,4 +3,5 @@
 for so in build_variants/*.so; do
   echo "== $so"
   S2ST_B200_LIB=$PWD/$so timeout 300 python tools/time_pass.py 0 2>&1 | tail -1
+  [ -n "$SMALL" ] && S2ST_B200_LIB=$PWD/$so timeout 300 python tools/time_small.py 2>&1 | tail -3
 done
