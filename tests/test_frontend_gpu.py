@@ -118,3 +118,36 @@ def test_cmvn_stats(pkg, built_lib):
     st = pkg.global_cmvn_stats([torch.from_numpy(f).cuda() for f in feats])
     ref = ofe.global_cmvn_stats(feats)
     assert np.allclose(st["mean"], ref["mean"], atol=1e-5) and np.allclose(st["std"], ref["std"], atol=1e-5)
+
+
+def test_fast_kernels_ragged_chunks_match_oracle_and_generic(pkg, built_lib, monkeypatch):
+    """The chunked kernels (k_fbank_fast: 16 frames per half-warp, two frames per transform at 8 kHz; k_logmel_fast:
+    8 frames per warp) on batches whose utterances end inside chunks, have odd sample offsets (unaligned loads), odd
+    frame counts and single frames -- against the oracle, and against the one-warp-per-frame kernels they replace."""
+    rng = np.random.RandomState(11)
+    for sr, lens in ((8000, [200, 281, 8000, 199, 1000, 2763, 4001, 360]), (16000, [401, 7777, 400, 12345, 3001, 561])):
+        waves = [(rng.randn(n) * 2000).astype(np.float32) for n in lens]
+        mean, std = rng.randn(80).astype(np.float32), rng.uniform(0.5, 2, 80).astype(np.float32)
+        outs = pkg.fbank_batch([torch.from_numpy(w) for w in waves], sr)
+        fused = pkg.fbank_batch([torch.from_numpy(w) for w in waves], sr, cmvn_mean=mean, cmvn_std=std)
+        monkeypatch.setenv("S2ST_FBANK_GENERIC", "1")
+        generic = pkg.fbank_batch([torch.from_numpy(w) for w in waves], sr)
+        monkeypatch.delenv("S2ST_FBANK_GENERIC")
+        for w, o, fo, g in zip(waves, outs, fused, generic):
+            ref = ofe.kaldi_fbank(w, sr)
+            assert o.shape == ref.shape == g.shape
+            if ref.shape[0]:
+                assert ogl.rel_l2(o.cpu().numpy(), ref) < 1e-5
+                assert ogl.rel_l2(o.cpu().numpy(), g.cpu().numpy()) < 1e-5
+                assert np.abs(fo.cpu().numpy() - (o.cpu().numpy() - mean) / std).max() < 2e-5
+    lens = [1025, 3000, 1500, 24000, 2047, 7001, 1201]
+    waves = [synth_audio(n, 24000, 30 + i) for i, n in enumerate(lens)]
+    outs = pkg.logmel_batch([torch.from_numpy(w) for w in waves], f_min=20.0)
+    monkeypatch.setenv("S2ST_LOGMEL_GENERIC", "1")
+    generic = pkg.logmel_batch([torch.from_numpy(w) for w in waves], f_min=20.0)
+    monkeypatch.delenv("S2ST_LOGMEL_GENERIC")
+    for w, o, g in zip(waves, outs, generic):
+        ref = ofe.logmel_spectrogram(w)
+        assert o.shape == ref.shape
+        assert ogl.rel_l2(o.cpu().numpy(), ref) < 1e-5
+        assert ogl.rel_l2(o.cpu().numpy(), g.cpu().numpy()) < 1e-5
