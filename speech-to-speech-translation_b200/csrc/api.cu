@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -78,6 +79,7 @@ void free_plan_members(s2st_plan* p) {
     cudaFree(p->mel_idx);
     cudaFree(p->mel_val);
     cudaFree(p->mel_col);
+    cudaFree(p->mel_gather);
 }
 
 }  // namespace
@@ -224,29 +226,68 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         rc = upload(&p->mel_ptr, ptr);
         if (rc == S2ST_OK) rc = upload(&p->mel_idx, idx);
         if (rc == S2ST_OK) rc = upload(&p->mel_val, val);
-        // column view (k_logmel_fast)
-        std::vector<float4> col(704, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-        bool ok = true;
-        for (int k = 0; k < kBins && ok; ++k) {
-            int first = -1, last = -1, count = 0;
+        // column view (k_logmel_fast): lane l owns bins 22 l .. 22 l + 21 and keeps one pair of partial sums per run
+        // of bins that feed the same mel bin b ("slot"); see plan.h
+        constexpr int kpl = 22, lanes = 32, max_slots = 17, max_terms = 8;
+        std::vector<float4> col(kpl * lanes, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        std::vector<std::vector<int>> terms(n_mels);
+        bool ok = n_mels <= 128;
+        for (int k = 704; k < kBins && ok; ++k)
             for (int m = 0; m < n_mels; ++m)
-                if (mel_host[(size_t)m * kBins + k] != 0.0f) {
-                    if (first < 0) first = m;
-                    last = m;
-                    ++count;
+                if (mel_host[(size_t)m * kBins + k] != 0.0f) ok = false;
+        for (int l = 0; l < lanes && ok; ++l) {
+            int cur = -1, slot = -1;
+            for (int j = 0; j < kpl && ok; ++j) {
+                const int k = kpl * l + j;
+                int first = -1, last = -1, count = 0;
+                for (int m = 0; m < n_mels; ++m)
+                    if (mel_host[(size_t)m * kBins + k] != 0.0f) {
+                        if (first < 0) first = m;
+                        last = m;
+                        ++count;
+                    }
+                if (count > 2 || (count == 2 && last != first + 1)) {
+                    ok = false;
+                    break;
                 }
-            if (count == 0) continue;
-            if (k >= 704 || count > 2 || (count == 2 && last != first + 1)) {
-                ok = false;
-                break;
+                int b = count ? first : (cur < 0 ? 0 : cur);  // an empty column continues the current run
+                if (count == 1 && cur >= 0 && first == cur + 1) b = cur;  // only the upper bin of the run: stay in it
+                const bool keep = (b == cur);
+                if (!keep) {
+                    ++slot;
+                    cur = b;
+                    if (slot >= max_slots) {
+                        ok = false;
+                        break;
+                    }
+                    terms[b].push_back((l * max_slots + slot) * 2);
+                    if (b + 1 < n_mels) terms[b + 1].push_back((l * max_slots + slot) * 2 + 1);
+                }
+                float w0 = 0.0f, w1 = 0.0f;
+                if (count) {
+                    if (first == b) w0 = mel_host[(size_t)first * kBins + k];
+                    else w1 = mel_host[(size_t)first * kBins + k];
+                    if (count == 2) w1 = mel_host[(size_t)last * kBins + k];
+                }
+                float sf;
+                std::memcpy(&sf, &slot, sizeof(float));
+                col[j * lanes + l] = make_float4(w0, w1, keep ? 1.0f : 0.0f, sf);
             }
-            int bi = first;
-            float bf;
-            std::memcpy(&bf, &bi, sizeof(float));
-            col[(k % 22) * 32 + k / 22] = make_float4(mel_host[(size_t)first * kBins + k],
-                                                      count == 2 ? mel_host[(size_t)last * kBins + k] : 0.0f, bf, 0.0f);
         }
-        if (ok && rc == S2ST_OK) rc = upload(&p->mel_col, col);
+        int n_terms = 1;
+        for (int m = 0; m < n_mels && ok; ++m) {
+            if ((int)terms[m].size() > max_terms) ok = false;
+            n_terms = std::max(n_terms, (int)terms[m].size());
+        }
+        if (ok && rc == S2ST_OK) {
+            // unused gather entries point at a float the kernel keeps at zero (index 2 * 32 * 17)
+            std::vector<int> gather((size_t)n_mels * max_terms, 2 * lanes * max_slots);
+            for (int m = 0; m < n_mels; ++m)
+                for (size_t q = 0; q < terms[m].size(); ++q) gather[(size_t)m * max_terms + q] = terms[m][q];
+            p->mel_terms = n_terms;
+            rc = upload(&p->mel_col, col);
+            if (rc == S2ST_OK) rc = upload(&p->mel_gather, gather);
+        }
     }
     if (rc != S2ST_OK) {
         free_plan_members(p);

@@ -71,6 +71,8 @@ struct StftParams {
     const int* mel_idx;
     const float* mel_val;
     const float4* mel_col;  // k_logmel_fast: [22 * 32] column view of the mel bank (see s2st_plan::mel_col)
+    const int* mel_gather;  //                [n_mels * 8] slab floats per mel bin
+    int mel_terms;
 };
 
 // MODE 0: magnitude (+ optional phase) [F,] rows; MODE 1: log-mel (+ optional CMVN) rows.
@@ -159,14 +161,17 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
 // log(max(., eps)) -> optional CMVN -> one 320-byte row.
 constexpr int kLmChunk = 8;
 constexpr int kLmCols = 32 * kPrunedRows;      // 704 spectrum bins
-constexpr int kLmAccFloats = 132;              // n_mels + 1 <= 129 accumulators, padded
+constexpr int kLmSlots = 17;                   // partial-sum slots per lane (pitch of the slab: conflict-free 8-byte stores)
+constexpr int kLmSlabFloats = 2 * 32 * kLmSlots + 4;  // + the always-zero float unused gather entries point at
+static_assert(kLmCols + kLmSlabFloats <= kScratchFloats, "spectrum + slab live in the warp scratch");
 template <int NZ>
 __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ StftParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float2* s_vtab = s_tw + 1024;
     float4* s_col = reinterpret_cast<float4*>(s_vtab + 1024);            // [22][32]: entry of bin 22 * lane + j at [j][lane]
-    float* s_win = reinterpret_cast<float*>(s_col + kLmCols);
+    int* s_gather = reinterpret_cast<int*>(s_col + kLmCols);            // [n_mels][8]
+    float* s_win = reinterpret_cast<float*>(s_gather + 8 * 128);
     float* s_warp = s_win + 64 * NZ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += blockDim.x) {
@@ -174,10 +179,11 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
         s_vtab[i] = p.vtab[i];
     }
     for (int i = tid; i < kLmCols; i += blockDim.x) s_col[i] = p.mel_col[i];
+    for (int i = tid; i < 8 * p.n_mels; i += blockDim.x) s_gather[i] = p.mel_gather[i];
     for (int i = tid; i < 64 * NZ; i += blockDim.x) s_win[i] = p.win_a[i];
+    float* scratch = s_warp + warp * kScratchFloats;
+    float* slab = scratch + kLmCols;  // [32][17] (lo, hi) pairs, then the zero float unused gather entries read
     __syncthreads();
-    float* scratch = s_warp + warp * (kScratchFloats + kLmAccFloats);
-    float* macc = scratch + kScratchFloats;
     const long long n_chunks = (p.total_frames + kLmChunk - 1) / kLmChunk;
     for (long long chunk = (long long)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (long long)gridDim.x * 8) {
         long long f = chunk * kLmChunk;
@@ -224,26 +230,35 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
             fwd1024<(NZ > 16 ? NZ : 32), 32>(a, scratch, s_tw, lane);
             float nyq;
             fwd_split<true>(a, nyq, scratch, s_vtab, lane);
-            // |X| (the split returns 2 X) to shared memory, linear in k; clear the mel accumulators
+            // |X| (the split returns 2 X) to shared memory, linear in k
 #pragma unroll
             for (int r = 0; r < kPrunedRows; ++r) {
                 float mag;  // |2 X|: MUFU.SQRT (2 ulp) instead of the IEEE sequence; the features are compared at 1e-5
                 asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(a[r].x, a[r].x, a[r].y * a[r].y)));
                 scratch[32 * r + lane] = 0.5f * mag;
             }
-            for (int i = lane; i < kLmAccFloats; i += 32) macc[i] = 0.0f;
             __syncwarp();
             {
+                // column-wise mel: running (lo, hi) partial sums per run of bins that feed the same mel bin, written
+                // to the run's slot after every step (the last write of a run is its total): no branches, no atomics
                 float lo = 0.0f, hi = 0.0f;
-                int cur = __float_as_int(s_col[lane].z);
                 const float* sp = scratch + kPrunedRows * lane;
+                float2* my = reinterpret_cast<float2*>(slab) + kLmSlots * lane;
 #pragma unroll
-                for (int j = 0; j < kPrunedRows; ++j) mel_col_step(lo, hi, cur, s_col[j * 32 + lane], sp[j], macc);
-                mel_col_flush(lo, hi, cur, macc);
+                for (int j = 0; j < kPrunedRows; ++j) {
+                    const float4 c = s_col[j * 32 + lane];
+                    const float v = sp[j];
+                    lo = fmaf(c.x, v, lo * c.z);
+                    hi = fmaf(c.y, v, hi * c.z);
+                    my[__float_as_int(c.w)] = make_float2(lo, hi);
+                }
+                if (lane == 0) slab[2 * 32 * kLmSlots] = 0.0f;  // (the transposes use the whole scratch)
             }
             __syncwarp();
             for (int m = lane; m < p.n_mels; m += 32) {
-                float v = logf(fmaxf(macc[m], p.eps));
+                float acc = 0.0f;
+                for (int q = 0; q < p.mel_terms; ++q) acc += slab[s_gather[8 * m + q]];
+                float v = logf(fmaxf(acc, p.eps));
                 if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
                 p.logmel_out[f * p.n_mels + m] = v;
             }
@@ -716,9 +731,11 @@ int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const
     p.mel_idx = plan->mel_idx;
     p.mel_val = plan->mel_val;
     p.mel_col = plan->mel_col;
-    if (logmel_out && plan->mel_col && plan->n_mels + 1 <= kLmAccFloats && !getenv("S2ST_LOGMEL_GENERIC")) {
-        const size_t fsmem = sizeof(float2) * 2048 + sizeof(float4) * kLmCols +
-                             sizeof(float) * (plan->wp + 8 * (kScratchFloats + kLmAccFloats));
+    p.mel_gather = plan->mel_gather;
+    p.mel_terms = plan->mel_terms;
+    if (logmel_out && plan->mel_col && plan->mel_gather && !getenv("S2ST_LOGMEL_GENERIC")) {
+        const size_t fsmem = sizeof(float2) * 2048 + sizeof(float4) * kLmCols + sizeof(int) * 8 * 128 +
+                             sizeof(float) * (plan->wp + 8 * kScratchFloats);
         const long long chunks = (total_frames + kLmChunk - 1) / kLmChunk;
         const int fgrid = (int)min((long long)plan->num_sms * 2, (chunks + 7) / 8);
         if (plan->nz == 19) {

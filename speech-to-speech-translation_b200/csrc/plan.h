@@ -25,9 +25,14 @@ struct s2st_plan {
     float* mel_val;     // [nnz]
     int mel_nnz;
     int mel_max_row;    // longest CSR row
-    float4* mel_col;    // column view for k_logmel_fast, or NULL when the bank does not qualify: every bin < 704
-                        // feeds at most two adjacent mel bins, bins >= 704 feed none; entry of bin 22 * l + j at
-                        // [j * 32 + l] = (weight into mel bin b, weight into b + 1, b as int bits, 0)
+    // column view for k_logmel_fast, or NULL when the bank does not qualify (every bin < 704 must feed at most two
+    // adjacent mel bins, bins >= 704 none).  Lane l owns bins 22 l + j; entry [j * 32 + l] = (weight into mel bin b,
+    // weight into b + 1, 1 if b is the same as for j - 1 else 0, slot as int bits): the lane keeps (lo, hi) partial
+    // sums per run of equal b and writes them to slot (l * 17 + slot) of a per-warp slab.  mel_gather[m * 8 + q] are
+    // the slab floats that add up to mel bin m (mel_terms = longest list; unused entries point at a zero).
+    float4* mel_col;
+    int* mel_gather;
+    int mel_terms;
     // profiling aid (s2st_plan_set_pass_timing): CUDA events around every Griffin-Lim pass of the LAST call
     int strip_frames;             // 0 = choose per call (s2st_plan_set_strip_frames)
     int timing_enabled;
