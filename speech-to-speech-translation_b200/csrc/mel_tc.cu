@@ -213,11 +213,11 @@ bool inverse_mel_tc_supported(const s2st_plan* plan) {
 }
 
 int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float* mel, bool is_log, float* mag,
-                          int out_stride, int n_out, cudaStream_t stream) {
+                          int out_stride, int n_out, cudaStream_t stream, const float* basis_tc) {
     if (n_frames <= 0) return S2ST_OK;
     TcParams p;
     p.mel = mel;
-    p.b_tc = plan->inv_mel_tc;
+    p.b_tc = basis_tc ? basis_tc : plan->inv_mel_tc;
     p.mag = mag;
     p.n_frames = n_frames;
     p.K = plan->n_mels;

@@ -18,6 +18,12 @@ struct s2st_plan {
     float* inv_wss;
     float2* tw;
     float2* vtab;
+    float2* tw64;       // real-FFT-64 formulation (frame_r64.cuh): exp(-2 pi i m l / 2048) at [m * 32 + l]
+    float2* vp64;       // r64_column_mid split factors
+    float2* win_pair;   // rotated window as (w[l + 64 r], w[l + 32 + 64 r]) at [r * 32 + l]; NULL unless nz == 19
+    int* mag_perm;          // [704] bin -> position in the slot-ordered magnitude rows of k_gl_pass_r64 (or NULL)
+    float* inv_mel_t_perm;  // inv_mel_t / inv_mel_tc with the basis rows in that order ([n_mels, 704]), or NULL
+    float* inv_mel_tc_perm;
     float* inv_mel_t;   // [n_mels, kb_pad] transposed pseudo-inverse (NULL if absent)
     float* inv_mel_tc;  // the same basis pre-split into TF32 head / tail in UMMA layout (mel_tc.cu), or NULL
     int* mel_ptr;       // CSR of the mel filterbank: [n_mels + 1]
@@ -69,7 +75,7 @@ int gl_run(const s2st_plan* plan, int n_utts, long long total_frames, const int3
            unsigned long long phase_seed, int n_iter, float* wave_out, void* workspace, size_t workspace_bytes,
            cudaStream_t stream);
 int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* logmel, bool is_log, float* mag,
-                       int out_stride, int n_out, cudaStream_t stream);
+                       int out_stride, int n_out, cudaStream_t stream, bool slot_order = false);
 int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* out, bool inverse,
                     cudaStream_t stream);
 
@@ -78,7 +84,7 @@ void build_inverse_mel_tc(const float* inv_mel, int kb, int K, float* out);
 size_t inverse_mel_tc_floats(int K);
 bool inverse_mel_tc_supported(const s2st_plan* plan);
 int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float* mel, bool is_log, float* mag,
-                          int out_stride, int n_out, cudaStream_t stream);
+                          int out_stride, int n_out, cudaStream_t stream, const float* basis_tc = nullptr);
 
 // frontend_kernels.cu
 int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const int64_t* wave_offsets,

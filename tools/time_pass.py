@@ -20,5 +20,7 @@ for S in [int(a) for a in sys.argv[1:]] or [0]:
     torch.cuda.synchronize()
     t = np.asarray(plan.pass_times_ms())
     algo = 6500.0 * total
+    if os.environ.get("ALL_PASSES"):
+        print(" ".join(f"{v:.4f}" for v in t))
     print(f"S={S:3d}  first {t[0]:.4f} ms  iteration median {np.median(t[1:]):.4f} ms  min {t[1:].min():.4f}  "
           f"-> {algo / np.median(t[1:]) / 1e6:.0f} GB/s algorithmic, {total / np.median(t[1:]) * 1e-3:.1f} M frame-iter/s")
