@@ -8,6 +8,8 @@
                           its default (dither 0, povey window, pre-emphasis 0.97,
                           DC removal, snip_edges, power spectrum, log, 20 Hz..Nyquist)
 * ``global_cmvn``         feature_transforms/global_cmvn.py:26-29
+* ``utterance_cmvn``      feature_transforms/utterance_cmvn.py:29-40
+* ``specaugment``         feature_transforms/specaugment.py:79-131 (masking; no time warp)
 * ``global_cmvn_stats``   examples/speech_synthesis/data_utils.py:190-220
 * ``gcmvn_denormalize``   fairseq/speech_generator_for_s2st.py:21-29
 """
@@ -84,3 +86,43 @@ def global_cmvn_stats(feature_list):
     mean = sx / n
     var = sx2 / n - mean ** 2
     return {"mean": mean, "std": np.sqrt(np.maximum(var, 1e-10))}
+
+
+def utterance_cmvn(x, norm_means=True, norm_vars=True):
+    """feature_transforms/utterance_cmvn.py:29-40, statement for statement (numpy float32 arithmetic)."""
+    mean = x.mean(axis=0)
+    square_sums = (x ** 2).sum(axis=0)
+    if norm_means:
+        x = np.subtract(x, mean)
+    if norm_vars:
+        var = square_sums / x.shape[0] - mean ** 2
+        std = np.sqrt(np.maximum(var, 1e-10))
+        x = np.divide(x, std)
+    return x
+
+
+def specaugment(spectrogram, freq_mask_n=0, freq_mask_f=0, time_mask_n=0, time_mask_t=0, time_mask_p=0.0,
+                mask_value=0.0):
+    """feature_transforms/specaugment.py:79-131 without time warping (time_warp_W = 0): same RNG call sequence on
+    numpy's global generator."""
+    import math
+    distorted = spectrogram.copy()
+    num_frames, num_freqs = spectrogram.shape
+    if mask_value is None:
+        mask_value = spectrogram.mean()
+    if num_frames == 0 or num_freqs < freq_mask_f:
+        return spectrogram
+    for _ in range(freq_mask_n):
+        f = np.random.randint(0, freq_mask_f)
+        f0 = np.random.randint(0, num_freqs - f)
+        if f != 0:
+            distorted[:, f0:f0 + f] = mask_value
+    max_time_mask_t = min(time_mask_t, math.floor(num_frames * time_mask_p))
+    if max_time_mask_t < 1:
+        return distorted
+    for _ in range(time_mask_n):
+        t = np.random.randint(0, max_time_mask_t)
+        t0 = np.random.randint(0, num_frames - t)
+        if t != 0:
+            distorted[t0:t0 + t, :] = mask_value
+    return distorted

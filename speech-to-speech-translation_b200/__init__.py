@@ -15,6 +15,8 @@ from .audio_utils import (TTSMelScale, TTSSpectrogram, fbank_batch, get_fbank, g
 from .feature_transforms import (AudioFeatureTransform, CompositeAudioFeatureTransform,  # noqa: F401
                                  get_audio_feature_transform, register_audio_feature_transform)
 from .feature_transforms.global_cmvn import GlobalCMVN, SRCGlobalCMVN, TGTGlobalCMVN  # noqa: F401
+from .feature_transforms.specaugment import SpecAugmentTransform  # noqa: F401
+from .feature_transforms.utterance_cmvn import UtteranceCMVN  # noqa: F401
 from .features import (extract_fbank_features, extract_logmel_spectrogram, gcmvn_denormalize,  # noqa: F401
                        global_cmvn_stats, logmel_batch)
 from .vocoder import GriffinLim, GriffinLimVocoder, PseudoInverseMelScale, get_vocoder  # noqa: F401

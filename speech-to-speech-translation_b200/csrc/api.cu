@@ -737,4 +737,36 @@ int s2st_cmvn_accumulate(int64_t n_rows, int n_cols, const float* x_dev, double*
     return launch_cmvn_accumulate(n_rows, n_cols, x_dev, sums_dev, static_cast<cudaStream_t>(stream));
 }
 
+int s2st_utterance_cmvn(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev, int norm_means,
+                        int norm_vars, float* out_dev, void* stream) {
+    if (n_utts < 0 || n_cols < 1 || (n_utts > 0 && (!frame_offsets_dev || !x_dev || !out_dev))) {
+        set_error("bad argument to s2st_utterance_cmvn");
+        return S2ST_EINVAL;
+    }
+    return launch_utterance_cmvn(n_utts, frame_offsets_dev, n_cols, x_dev, out_dev, norm_means != 0, norm_vars != 0,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int s2st_utterance_sum(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev, double* sums_dev,
+                       void* stream) {
+    if (n_utts < 0 || n_cols < 1 || (n_utts > 0 && (!frame_offsets_dev || !x_dev || !sums_dev))) {
+        set_error("bad argument to s2st_utterance_sum");
+        return S2ST_EINVAL;
+    }
+    return launch_utterance_sum(n_utts, frame_offsets_dev, n_cols, x_dev, sums_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_fill_rects(int n_rects, const int32_t* rects_dev, const float* values_dev, int n_cols, float* x_dev,
+                    void* stream) {
+    if (n_rects < 0 || n_cols < 1 || (n_rects > 0 && (!rects_dev || !values_dev || !x_dev))) {
+        set_error("bad argument to s2st_fill_rects");
+        return S2ST_EINVAL;
+    }
+    if (((uintptr_t)rects_dev & 15) != 0) {
+        set_error("s2st_fill_rects: rects_dev must be 16-byte aligned");
+        return S2ST_EINVAL;
+    }
+    return launch_fill_rects(n_rects, rects_dev, values_dev, n_cols, x_dev, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

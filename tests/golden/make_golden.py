@@ -206,6 +206,30 @@ def main():
     np.savez_compressed(os.path.join(HERE, "cmvn.npz"), x=x, mean=mean, std=std, denorm=den[0].numpy(), **outs)
     print("cmvn ok", {k: v.dtype for k, v in outs.items()})
 
+    # ---- per-utterance transforms of the registry: utterance_cmvn, specaugment ----------------------
+    tr = {}
+    rng = np.random.RandomState(11)
+    for name, T in (("a", 1), ("b", 7), ("c", 333), ("d", 1998)):
+        xu = (rng.randn(T, 80) * rng.uniform(0.2, 3.0, 80) + rng.uniform(-8, 2, 80)).astype(np.float32)
+        tr[f"ucmvn_{name}_x"] = xu
+        for nm in (0, 1):
+            for nv in (0, 1):
+                t = reg["utterance_cmvn"].from_config_dict({"norm_means": bool(nm), "norm_vars": bool(nv)})
+                tr[f"ucmvn_{name}_m{nm}v{nv}"] = t(xu)
+    cfgs = {"ld": {"freq_mask_N": 2, "freq_mask_F": 27, "time_mask_N": 2, "time_mask_T": 100, "time_mask_p": 1.0},
+            "zero": {"freq_mask_N": 1, "freq_mask_F": 10, "time_mask_N": 3, "time_mask_T": 40, "time_mask_p": 0.2,
+                     "mask_value": 0.0},
+            "fonly": {"freq_mask_N": 3, "freq_mask_F": 15}}
+    for cname, cfg in cfgs.items():
+        t = reg["specaugment"].from_config_dict(cfg)
+        for name, T in (("s", 9), ("m", 250), ("l", 1203)):
+            xs = (rng.randn(T, 80) * 2 - 4).astype(np.float32)
+            np.random.seed(1000 + T)
+            tr[f"spec_{cname}_{name}_x"] = xs
+            tr[f"spec_{cname}_{name}_y"] = t(xs)
+    np.savez_compressed(os.path.join(HERE, "transforms.npz"), **tr)
+    print("transforms ok", len(tr))
+
 
 if __name__ == "__main__":
     main()

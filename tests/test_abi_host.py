@@ -84,8 +84,23 @@ def test_from_data_cfg_and_get_vocoder(pkg):
 
 def test_registry_semantics(pkg):
     ft = pkg.feature_transforms
-    for name in ("global_cmvn", "src_global_cmvn", "tgt_global_cmvn"):
+    # every name the reference registers (feature_transforms/*.py) resolves here as well
+    for name in ("global_cmvn", "src_global_cmvn", "tgt_global_cmvn", "utterance_cmvn", "specaugment"):
         assert issubclass(ft.get_audio_feature_transform(name), ft.AudioFeatureTransform)
+    u = ft.get_audio_feature_transform("utterance_cmvn").from_config_dict({"norm_vars": False})
+    assert (u.norm_means, u.norm_vars) == (True, False) and repr(u) == "UtteranceCMVN(norm_means=True, norm_vars=False)"
+    sa = ft.get_audio_feature_transform("specaugment").from_config_dict(
+        {"freq_mask_N": 2, "freq_mask_F": 27, "time_mask_N": 2, "time_mask_T": 100, "time_mask_p": 1.0})
+    assert sa.mask_value is None and "freq_mask_f=27" in repr(sa)
+    with pytest.raises(AssertionError, match="freq_mask_F"):
+        ft.get_audio_feature_transform("specaugment").from_config_dict({"freq_mask_N": 1})
+    # mask drawing is host logic: same numpy RNG call sequence as specaugment.py:111-129
+    np.random.seed(5)
+    rects = sa.draw_masks(300, 80)
+    np.random.seed(5)
+    f = np.random.randint(0, 27); f0 = np.random.randint(0, 80 - f)
+    assert (rects[0] == (0, 300, f0, f0 + f)) if f else True
+    assert sa.draw_masks(0, 80) is None and sa.draw_masks(10, 20) is None
     with pytest.raises(ValueError, match="duplicate transform"):
         ft.register_audio_feature_transform("global_cmvn")(type("X1", (ft.AudioFeatureTransform,), {}))
     with pytest.raises(ValueError, match="must extend"):

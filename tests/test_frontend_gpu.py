@@ -151,3 +151,63 @@ def test_fast_kernels_ragged_chunks_match_oracle_and_generic(pkg, built_lib, mon
         assert o.shape == ref.shape
         assert ogl.rel_l2(o.cpu().numpy(), ref) < 1e-5
         assert ogl.rel_l2(o.cpu().numpy(), g.cpu().numpy()) < 1e-5
+
+
+def test_utterance_cmvn_bit_exact_and_ragged_batch(pkg, built_lib):
+    """utterance_cmvn: drop-in __call__ bit-identical to the reference's golden outputs (all four flag
+    combinations, T = 1 ... 1998), and the ragged device batch equals the per-utterance calls."""
+    ft = pkg.feature_transforms
+    t = load_golden("transforms.npz")
+    xs = [t[f"ucmvn_{n}_x"] for n in "abcd"]
+    for nm in (0, 1):
+        for nv in (0, 1):
+            tr = ft.get_audio_feature_transform("utterance_cmvn").from_config_dict(
+                {"norm_means": bool(nm), "norm_vars": bool(nv)})
+            for n, x in zip("abcd", xs):
+                y = tr(x)
+                assert y.dtype == np.float32 and np.array_equal(y, t[f"ucmvn_{n}_m{nm}v{nv}"]), (n, nm, nv)
+                assert np.array_equal(y, ofe.utterance_cmvn(x, bool(nm), bool(nv)))
+            flat = torch.from_numpy(np.concatenate(xs)).cuda()
+            yb = tr.apply_cuda(flat, [x.shape[0] for x in xs]).cpu().numpy()
+            assert np.array_equal(yb, np.concatenate([t[f"ucmvn_{n}_m{nm}v{nv}"] for n in "abcd"]))
+    empty = ft.get_audio_feature_transform("utterance_cmvn")()(np.zeros((0, 80), np.float32))
+    assert empty.shape == (0, 80)
+
+
+def test_specaugment_matches_reference(pkg, built_lib):
+    """specaugment: masks are drawn on the host with the reference's RNG call sequence, the fill (and the local-mean
+    mask value) run on the GPU.  Explicit mask values are bit-exact; the local mean is a float64-accumulated mean
+    rounded to float32, which can differ from numpy's float32 pairwise mean in the last place (tolerance 1e-6)."""
+    from test_oracle_golden import SPEC_CFGS
+    ft = pkg.feature_transforms
+    t = load_golden("transforms.npz")
+    keys = {"freq_mask_n": "freq_mask_N", "freq_mask_f": "freq_mask_F", "time_mask_n": "time_mask_N",
+            "time_mask_t": "time_mask_T", "time_mask_p": "time_mask_p", "mask_value": "mask_value"}
+    for cname, cfg in SPEC_CFGS.items():
+        tr = ft.get_audio_feature_transform("specaugment").from_config_dict({keys[k]: v for k, v in cfg.items()})
+        xs, ys = [], []
+        for name, T in (("s", 9), ("m", 250), ("l", 1203)):
+            x, ref = t[f"spec_{cname}_{name}_x"], t[f"spec_{cname}_{name}_y"]
+            np.random.seed(1000 + T)
+            y = tr(x)
+            assert y.shape == ref.shape and y.dtype == np.float32
+            masked = ref != x
+            assert np.array_equal(y[~masked], x[~masked])           # untouched cells are copied bit for bit
+            if cfg["mask_value"] is None:
+                assert np.allclose(y[masked], ref[masked], rtol=1e-6, atol=0)
+            else:
+                assert np.array_equal(y, ref)
+            xs.append(x)
+            ys.append(y)
+        # ragged device batch: utterances draw their masks in order, one fill launch
+        np.random.seed(77)
+        singles = [tr(x) for x in xs]
+        np.random.seed(77)
+        yb = tr.apply_cuda(torch.from_numpy(np.concatenate(xs)).cuda(), [x.shape[0] for x in xs]).cpu().numpy()
+        assert np.array_equal(yb, np.concatenate(singles))
+    # fewer feature columns than freq_mask_F: the reference returns its input untouched
+    tr = ft.get_audio_feature_transform("specaugment").from_config_dict({"freq_mask_N": 1, "freq_mask_F": 100})
+    x = np.ones((5, 80), np.float32)
+    assert tr(x) is x
+    with pytest.raises(NotImplementedError):
+        ft.get_audio_feature_transform("specaugment").from_config_dict({"time_warp_W": 5})(np.ones((50, 80), np.float32))

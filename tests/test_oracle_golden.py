@@ -116,3 +116,29 @@ def test_cmvn_stats_roundtrip():
     allf = np.concatenate(feats)
     assert np.allclose(st["mean"], allf.mean(0), atol=1e-4)
     assert np.allclose(st["std"], allf.std(0), atol=1e-3)
+
+
+def test_utterance_cmvn_matches_reference_bit_exact():
+    t = load_golden("transforms.npz")
+    for name in "abcd":
+        x = t[f"ucmvn_{name}_x"]
+        for nm in (0, 1):
+            for nv in (0, 1):
+                y = fe.utterance_cmvn(x, bool(nm), bool(nv))
+                assert y.dtype == np.float32 and np.array_equal(y, t[f"ucmvn_{name}_m{nm}v{nv}"])
+
+
+SPEC_CFGS = {"ld": dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=100, time_mask_p=1.0, mask_value=None),
+             "zero": dict(freq_mask_n=1, freq_mask_f=10, time_mask_n=3, time_mask_t=40, time_mask_p=0.2, mask_value=0.0),
+             "fonly": dict(freq_mask_n=3, freq_mask_f=15, mask_value=None)}
+
+
+def test_specaugment_matches_reference_bit_exact():
+    t = load_golden("transforms.npz")
+    for cname, cfg in SPEC_CFGS.items():
+        for name, T in (("s", 9), ("m", 250), ("l", 1203)):
+            x = t[f"spec_{cname}_{name}_x"]
+            np.random.seed(1000 + T)
+            y = fe.specaugment(x, **cfg)
+            assert np.array_equal(y, t[f"spec_{cname}_{name}_y"])
+            assert (y != x).any() or cname == "zero" or T < 20
