@@ -142,3 +142,20 @@ def test_specaugment_matches_reference_bit_exact():
             y = fe.specaugment(x, **cfg)
             assert np.array_equal(y, t[f"spec_{cname}_{name}_y"])
             assert (y != x).any() or cname == "zero" or T < 20
+
+
+def test_conv_formulation_reproduces_reference_bit_for_bit(golden_basis):
+    """oracle/conv_formulation.py is the reference's own dense-convolution formulation: same torch ops in the same
+    order, so the golden waveforms come back exactly; and it pins the FFT oracle from a second, independent side."""
+    from oracle import conv_formulation as cf
+    _, pinv = golden_basis
+    g = load_golden("gl_small.npz")
+    eng = cf.ConvGriffinLim()
+    for case in ("c1", "c2"):
+        x, n_iter, seed = g[case + "_logmel"], int(g[case + "_n_iter"]), int(g[case + "_seed"])
+        y = cf.vocoder_forward(x, seeded_phase(seed, x.shape[0]), n_iter, pinv, gl=eng)
+        assert np.array_equal(y, g[case + "_wave"])
+        assert gl.rel_l2(gl.vocoder_forward(x, seeded_phase(seed, x.shape[0]), n_iter, basis=pinv), y) < 1e-4
+    w = load_golden("wss.npz")
+    for k in w.files:
+        assert np.array_equal(eng.window_sum_square(int(k[1:])).numpy(), w[k])
