@@ -191,6 +191,16 @@ int s2st_utterance_sum(int n_utts, const int32_t* frame_offsets_dev, int n_cols,
 int s2st_fill_rects(int n_rects, const int32_t* rects_dev, const float* values_dev, int n_cols, float* x_dev,
                     void* stream);
 
+/* batch_dynamic_time_warping (examples/s2s_trans/tasks/s2s_translation.py:414-464, the MCD validation metric):
+ * distance_dev [bsz, m, n] float32 (zero padded), shapes_dev int64 [bsz, 2] = (M_b, N_b) or NULL (= full size)
+ * -> cumdist_dev float32, backptr_dev int32 (0 = left, 1 = up-left, 2 = up), pathmap_dev int32 (1 on the optimal
+ * path from (M_b-1, N_b-1) back to (0, 0)), all [bsz, m, n].  Bit-identical to the reference run on the CPU. */
+int s2st_dtw(int bsz, int m, int n, const float* distance_dev, const int64_t* shapes_dev, float* cumdist_dev,
+             int32_t* backptr_dev, int32_t* pathmap_dev, void* stream);
+/* compute_rms_dist (s2s_translation.py:467-475): out_dev [m, n] = sqrt(|x1[i] - x2[j]|^2 / d), x1_dev [m, d],
+ * x2_dev [n, d]. */
+int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

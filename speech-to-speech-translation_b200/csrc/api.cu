@@ -769,4 +769,22 @@ int s2st_fill_rects(int n_rects, const int32_t* rects_dev, const float* values_d
     return launch_fill_rects(n_rects, rects_dev, values_dev, n_cols, x_dev, static_cast<cudaStream_t>(stream));
 }
 
+int s2st_dtw(int bsz, int m, int n, const float* distance_dev, const int64_t* shapes_dev, float* cumdist_dev,
+             int32_t* backptr_dev, int32_t* pathmap_dev, void* stream) {
+    if (bsz < 0 || m < 0 || n < 0 || (bsz > 0 && m > 0 && n > 0 && (!distance_dev || !cumdist_dev || !backptr_dev || !pathmap_dev))) {
+        set_error("bad argument to s2st_dtw");
+        return S2ST_EINVAL;
+    }
+    return launch_dtw(bsz, m, n, distance_dev, reinterpret_cast<const long long*>(shapes_dev), cumdist_dev, backptr_dev,
+                      pathmap_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev, float* out_dev, void* stream) {
+    if (m < 0 || n < 0 || d < 1 || (m > 0 && n > 0 && (!x1_dev || !x2_dev || !out_dev))) {
+        set_error("bad argument to s2st_rms_dist");
+        return S2ST_EINVAL;
+    }
+    return launch_rms_dist(m, n, d, x1_dev, x2_dev, out_dev, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

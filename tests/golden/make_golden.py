@@ -230,6 +230,42 @@ def main():
     np.savez_compressed(os.path.join(HERE, "transforms.npz"), **tr)
     print("transforms ok", len(tr))
 
+    # ---- MCD metric: DTW + distance, the reference's own functions ----------------------------------
+    # examples/s2s_trans/tasks/s2s_translation.py cannot be imported (fairseq task machinery), but the metric is a set
+    # of pure functions: their unmodified source is compiled from the file.
+    import ast
+    import torch.nn.functional as F
+    src = open(os.path.join(REF, "examples/s2s_trans/tasks/s2s_translation.py")).read()
+    want = {"antidiag_indices", "batch_dynamic_time_warping", "compute_l2_dist", "compute_rms_dist", "get_divisor",
+            "batch_compute_distortion", "batch_mel_cepstral_distortion"}
+    mod = ast.Module([n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want], [])
+    ns = {"torch": torch, "np": np, "F": F}
+    exec(compile(mod, "s2s_translation.py", "exec"), ns)
+    rng = np.random.RandomState(3)
+    dt = {}
+    shapes = [(5, 7), (12, 9), (1, 6), (30, 31)]
+    dm = np.zeros((len(shapes), 30, 31), np.float32)
+    for b, (m, n) in enumerate(shapes):
+        dm[b, :m, :n] = rng.rand(m, n).astype(np.float32) * 3
+    dm[1, :12, :9] = rng.randint(0, 3, (12, 9))          # many exact ties
+    c, bp, pm = ns["batch_dynamic_time_warping"](torch.from_numpy(dm), torch.LongTensor(shapes))
+    dt.update(ragged_dist=dm, ragged_shapes=np.asarray(shapes, np.int64), ragged_cum=c.numpy(), ragged_bp=bp.numpy(),
+              ragged_path=pm.numpy())
+    dfull = (rng.rand(2, 40, 23).astype(np.float32) ** 2)
+    c, bp, pm = ns["batch_dynamic_time_warping"](torch.from_numpy(dfull))
+    dt.update(full_dist=dfull, full_cum=c.numpy(), full_bp=bp.numpy(), full_path=pm.numpy())
+    x1, x2 = rng.randn(37, 13).astype(np.float32) * 4, rng.randn(29, 13).astype(np.float32) * 4
+    dt.update(x1=x1, x2=x2, rms=ns["compute_rms_dist"](torch.from_numpy(x1), torch.from_numpy(x2)).numpy())
+    # end to end: MCD of two waveform pairs at 24 kHz (torchaudio MFCC, CPU)
+    ya = [torch.from_numpy(synth_audio(9000, 24000, 31)), torch.from_numpy(synth_audio(14000, 24000, 32))]
+    yb = [torch.from_numpy(synth_audio(11000, 24000, 33)), torch.from_numpy(synth_audio(12500, 24000, 34))]
+    for nt in ("path", "len1", None):
+        rets = ns["batch_mel_cepstral_distortion"](ya, yb, 24000, normalize_type=nt)
+        dt["mcd_" + str(nt)] = np.asarray([float(r[0]) for r in rets], np.float64)
+    dt.update(mcd_ya0=ya[0].numpy(), mcd_ya1=ya[1].numpy(), mcd_yb0=yb[0].numpy(), mcd_yb1=yb[1].numpy())
+    np.savez_compressed(os.path.join(HERE, "dtw.npz"), **dt)
+    print("dtw ok", {k: v.shape for k, v in dt.items() if k.startswith("mcd_") and v.ndim == 1 and v.size == 2})
+
 
 if __name__ == "__main__":
     main()

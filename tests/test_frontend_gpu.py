@@ -211,3 +211,43 @@ def test_specaugment_matches_reference(pkg, built_lib):
     assert tr(x) is x
     with pytest.raises(NotImplementedError):
         ft.get_audio_feature_transform("specaugment").from_config_dict({"time_warp_W": 5})(np.ones((50, 80), np.float32))
+
+
+def test_dtw_bit_exact_and_mcd_metric(pkg, built_lib):
+    """The MCD validation metric (examples/s2s_trans/tasks/s2s_translation.py:414-552): DTW recurrence, back pointers
+    and path bit-identical to the reference's functions (ragged shapes, exact ties, full-size default), distance matrix
+    within 1e-5, and the end-to-end distortion of two waveform pairs (torchaudio MFCC, as in the reference)."""
+    import importlib
+    mcd = importlib.import_module(pkg.__name__ + ".mcd")
+    from oracle import dtw as odtw
+    d = load_golden("dtw.npz")
+    dist = torch.from_numpy(d["ragged_dist"]).cuda()
+    cum, bp, path = mcd.batch_dynamic_time_warping(dist, torch.from_numpy(d["ragged_shapes"]))
+    assert cum.is_cuda and bp.dtype == torch.int32 and path.dtype == torch.int32
+    assert torch.equal(cum.cpu(), torch.from_numpy(d["ragged_cum"]))
+    assert torch.equal(bp.cpu(), torch.from_numpy(d["ragged_bp"]))
+    assert torch.equal(path.cpu(), torch.from_numpy(d["ragged_path"]))
+    cum, bp, path = mcd.batch_dynamic_time_warping(torch.from_numpy(d["full_dist"]))   # CPU tensor in -> CPU out
+    assert not cum.is_cuda
+    assert np.array_equal(cum.numpy(), d["full_cum"]) and np.array_equal(bp.numpy(), d["full_bp"])
+    assert np.array_equal(path.numpy(), d["full_path"])
+    # a larger case against the oracle (one CTA walks > 1 block-width of cells per diagonal)
+    rng = np.random.RandomState(0)
+    big = rng.rand(3, 300, 280).astype(np.float32)
+    oc, ob, op = odtw.batch_dynamic_time_warping(big[:1, :120, :100].copy())
+    c, b, p = mcd.batch_dynamic_time_warping(torch.from_numpy(big[:1, :120, :100].copy()).cuda())
+    assert np.array_equal(c.cpu().numpy(), oc) and np.array_equal(b.cpu().numpy(), ob) and np.array_equal(p.cpu().numpy(), op)
+    c, b, p = mcd.batch_dynamic_time_warping(torch.from_numpy(big).cuda())
+    assert torch.isfinite(c).all() and int(p[0].sum()) >= 300 and (p.sum(dim=(1, 2)) <= 579).all()
+    # distance
+    r = mcd.compute_rms_dist(torch.from_numpy(d["x1"]).cuda(), torch.from_numpy(d["x2"]).cuda()).cpu().numpy()
+    assert ogl.rel_l2(r, d["rms"]) < 1e-5 and ogl.rel_l2(r, odtw.compute_rms_dist(d["x1"], d["x2"])) < 1e-6
+    # end to end
+    ya = [torch.from_numpy(d["mcd_ya0"]).cuda(), torch.from_numpy(d["mcd_ya1"]).cuda()]
+    yb = [torch.from_numpy(d["mcd_yb0"]).cuda(), torch.from_numpy(d["mcd_yb1"]).cuda()]
+    for nt in ("path", "len1", None):
+        rets = mcd.batch_mel_cepstral_distortion(ya, yb, 24000, normalize_type=nt)
+        got = np.asarray([float(r[0]) for r in rets])
+        assert np.allclose(got, d["mcd_" + str(nt)], rtol=2e-3), (nt, got, d["mcd_" + str(nt)])
+    with pytest.raises(ValueError, match="not supported"):
+        mcd.batch_mel_cepstral_distortion(ya, yb, 24000, normalize_type="bogus")

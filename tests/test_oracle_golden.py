@@ -159,3 +159,18 @@ def test_conv_formulation_reproduces_reference_bit_for_bit(golden_basis):
     w = load_golden("wss.npz")
     for k in w.files:
         assert np.array_equal(eng.window_sum_square(int(k[1:])).numpy(), w[k])
+
+
+def test_dtw_and_rms_dist_match_reference():
+    """oracle/dtw.py against the reference's own batch_dynamic_time_warping / compute_rms_dist (golden from the
+    unmodified functions, incl. a case full of exact ties and ragged shapes)."""
+    from oracle import dtw as odtw
+    d = load_golden("dtw.npz")
+    cum, bp, path = odtw.batch_dynamic_time_warping(d["ragged_dist"], d["ragged_shapes"])
+    for b, (m, n) in enumerate(d["ragged_shapes"]):
+        assert np.array_equal(cum[b, :m, :n], d["ragged_cum"][b, :m, :n])
+        assert np.array_equal(bp[b, :m, :n], d["ragged_bp"][b, :m, :n])
+    assert np.array_equal(path, d["ragged_path"])
+    cum, bp, path = odtw.batch_dynamic_time_warping(d["full_dist"])
+    assert np.array_equal(cum, d["full_cum"]) and np.array_equal(bp, d["full_bp"]) and np.array_equal(path, d["full_path"])
+    assert gl.rel_l2(odtw.compute_rms_dist(d["x1"], d["x2"]), d["rms"]) < 1e-6
