@@ -45,3 +45,37 @@ def compute_rms_dist(x1, x2):
     x1, x2 = np.asarray(x1, np.float64), np.asarray(x2, np.float64)
     d2 = ((x1[:, None, :] - x2[None, :, :]) ** 2).sum(-1)
     return np.sqrt(d2 / x1.shape[1]).astype(np.float32)
+
+
+def batch_dynamic_time_warping_torch(distance, shapes=None):
+    """The reference's FORMULATION of the same recurrence (s2s_translation.py:414-464) in torch: one round of gathers /
+    min / scatter per anti-diagonal and a host back trace with one .item() per step -- kept for timing the reference's
+    approach on the GPU next to the fused kernel (tools/bench_adjacent.py); results equal the loops above."""
+    import torch
+    bsz, m, n = distance.shape
+    cum = torch.zeros_like(distance)
+    bp = torch.full(distance.shape, -1, dtype=torch.int32, device=distance.device)
+    cum[:, 0, :] = distance[:, 0, :].cumsum(-1)
+    cum[:, :, 0] = distance[:, :, 0].cumsum(-1)
+    bp[:, 0, :] = 0
+    bp[:, :, 0] = 2
+    for off in range(2, m + n - 1):
+        j = torch.arange(max(1, off - m + 1), min(n, off), device=distance.device)
+        i = off - j
+        cand = torch.stack([cum[:, i, j - 1], cum[:, i - 1, j - 1], cum[:, i - 1, j]], dim=2)
+        v, b = cand.min(dim=-1)
+        bp[:, i, j] = b.int()
+        cum[:, i, j] = v + distance[:, i, j]
+    path = torch.zeros_like(bp)
+    step = {0: (0, -1), 1: (-1, -1), 2: (-1, 0)}
+    for b in range(bsz):
+        i = m - 1 if shapes is None else int(shapes[b][0]) - 1
+        j = n - 1 if shapes is None else int(shapes[b][1]) - 1
+        cells = [(i, j)]
+        while (i != 0 or j != 0) and len(cells) < 10000:
+            di, dj = step[bp[b, i, j].item()]
+            i, j = i + di, j + dj
+            cells.append((i, j))
+        idx = torch.tensor(cells, device=distance.device)
+        path[b, idx[:, 0], idx[:, 1]] = 1
+    return cum, bp, path

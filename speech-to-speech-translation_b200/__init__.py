@@ -1,7 +1,8 @@
 """B200-native (sm_100a) waveform-synthesis and speech-feature front-end.
 
 Drop-in for the Griffin-Lim vocoder and the fbank80 / logmelspec80 / global-CMVN front-end of
-fengpeng-yue/speech-to-speech-translation (a fairseq fork).  Host code is Python / PyTorch (device
+fengpeng-yue/speech-to-speech-translation (a fairseq fork), plus the rows next to that path: the other registry
+transforms (utterance CMVN, SpecAugment masking) and the DTW of the MCD validation metric (``mcd``).  Host code is Python / PyTorch (device
 memory, streams, torch.distributed); the arithmetic is a hand-written CUDA library behind a C ABI
 (``include/s2st_b200.h``, loaded with ctypes from ``libs2st_b200.so`` in this directory).  There is
 no CPU fallback: without the built library every entry point raises.
@@ -10,6 +11,7 @@ The directory name is not a Python identifier; import it as ``import s2st_b200``
 the repository root) or with ``importlib.import_module("speech-to-speech-translation_b200")``.
 """
 from . import _lib  # noqa: F401
+from . import mcd  # noqa: F401
 from .audio_utils import (TTSMelScale, TTSSpectrogram, fbank_batch, get_fbank, get_fourier_basis,  # noqa: F401
                           get_mel_filters, get_window)
 from .feature_transforms import (AudioFeatureTransform, CompositeAudioFeatureTransform,  # noqa: F401
