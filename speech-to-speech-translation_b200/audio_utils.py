@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .plans import get_fbank_plan, get_stft_plan, require_cuda
+from .plans import get_fbank_plan, get_stft_plan, require_cuda, upload_small
 
 SF_AUDIO_FILE_EXTENSIONS = {".wav", ".flac", ".ogg"}
 
@@ -80,7 +80,7 @@ def _ragged_offsets(lengths, hop, device):
     fo[1:] = np.cumsum(frames)
     wo = np.zeros(len(lengths) + 1, np.int64)
     wo[1:] = np.cumsum(lengths)
-    return torch.from_numpy(fo).to(device), torch.from_numpy(wo).to(device), frames
+    return upload_small(fo, device), upload_small(wo, device), frames
 
 
 class TTSSpectrogram(torch.nn.Module):
@@ -188,7 +188,7 @@ def fbank_batch(waveforms, sample_rate: int, n_bins: int = 80, cmvn_mean=None, c
     out = torch.empty(total, n_bins, dtype=torch.float32, device=dev)
     if total > 0:
         flat = torch.cat([w.to(dev, torch.float32) for w in waves]).contiguous()
-        fo_d, wo_d = torch.from_numpy(fo).to(dev), torch.from_numpy(wo).to(dev)
+        fo_d, wo_d = upload_small(fo, dev), upload_small(wo, dev)
         mean_d = None if cmvn_mean is None else torch.as_tensor(cmvn_mean).to(dev, torch.float32).contiguous()
         std_d = None if cmvn_std is None else torch.as_tensor(cmvn_std).to(dev, torch.float32).contiguous()
         with torch.cuda.device(dev):

@@ -813,9 +813,21 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
     return best;
 }
 
+// cudaFuncSetAttribute is a driver call per launch otherwise (65 per synthesis step): do it once per kernel, device
+// and size.  Not thread-safe by design (the worst case is a redundant call).
+template <auto Kernel>
+int allow_dynamic_smem(size_t smem, int device) {
+    static size_t granted[64] = {};  // one table per kernel (the kernel is a template argument)
+    if (device < 0 || device >= 64 || granted[device] < smem) {
+        S2ST_CUDA_CHECK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (device >= 0 && device < 64) granted[device] = smem;
+    }
+    return S2ST_OK;
+}
+
 template <int NZ, bool FIRST, bool PRUNED, bool STD = false>
 int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream) {
-    S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_gl_pass<NZ, FIRST, PRUNED, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = allow_dynamic_smem<k_gl_pass<NZ, FIRST, PRUNED, STD>>(smem, p.device)) return rc;
     k_gl_pass<NZ, FIRST, PRUNED, STD><<<grid, kGlThreads, smem, stream>>>(p);
     S2ST_CUDA_CHECK(cudaGetLastError());
     return S2ST_OK;
@@ -899,6 +911,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     S2ST_CUDA_CHECK(cudaGetLastError());
 
     GlParams p;
+    p.device = plan->device;
     p.hop = plan->hop;
     p.half = plan->n_fft / 2;
     p.rot = plan->rot;
@@ -963,7 +976,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
         int rc;
         if (it > 0 && r64) {
             const size_t smem64 = gl_pass_r64_smem();
-            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_gl_pass_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+            if (int rc2 = allow_dynamic_smem<k_gl_pass_r64>(smem64, p.device)) return rc2;
             k_gl_pass_r64<<<grid, kGlThreads, smem64, stream>>>(p);
             S2ST_CUDA_CHECK(cudaGetLastError());
             rc = S2ST_OK;

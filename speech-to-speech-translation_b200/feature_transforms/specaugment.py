@@ -15,13 +15,13 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..plans import require_cuda
+from ..plans import require_cuda, upload_small
 from . import AudioFeatureTransform, register_audio_feature_transform
 
 
 def utterance_mean_cuda(x: torch.Tensor, frames: Sequence[int]) -> np.ndarray:
     """Mean of all elements of each utterance of a ragged batch x [sum T_i, n_feat] (float64 accumulation)."""
-    fo = torch.tensor(np.concatenate([[0], np.cumsum(frames)]), dtype=torch.int32).to(x.device)
+    fo = upload_small(np.concatenate([[0], np.cumsum(frames)]).astype(np.int32), x.device)
     sums = torch.zeros(len(frames), dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
         rc = _lib.load().s2st_utterance_sum(len(frames), _lib.ptr(fo), x.shape[1], _lib.ptr(x), _lib.ptr(sums),
@@ -111,8 +111,8 @@ class SpecAugmentTransform(AudioFeatureTransform):
                 values.append(v)
             row += T
         if rects:
-            rd = torch.tensor(rects, dtype=torch.int32).to(x.device)
-            vd = torch.tensor(values, dtype=torch.float32).to(x.device)
+            rd = upload_small(np.asarray(rects, np.int32), x.device)
+            vd = upload_small(np.asarray(values, np.float32), x.device)
             with torch.cuda.device(x.device):
                 rc = _lib.load().s2st_fill_rects(len(rects), _lib.ptr(rd), _lib.ptr(vd), x.shape[1], _lib.ptr(out),
                                                  _lib.stream_ptr(x.device))

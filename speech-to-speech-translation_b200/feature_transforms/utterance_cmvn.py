@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..plans import require_cuda
+from ..plans import require_cuda, upload_small
 from . import AudioFeatureTransform, register_audio_feature_transform
 
 
@@ -22,7 +22,7 @@ def utterance_cmvn_cuda(x: torch.Tensor, frames: Sequence[int], norm_means: bool
     x = x.contiguous()
     assert sum(frames) == x.shape[0], "frames must add up to the number of rows"
     out = torch.empty_like(x) if out is None else out
-    fo = torch.tensor(np.concatenate([[0], np.cumsum(frames)]), dtype=torch.int32).to(x.device, non_blocking=True)
+    fo = upload_small(np.concatenate([[0], np.cumsum(frames)]).astype(np.int32), x.device)
     with torch.cuda.device(x.device):
         rc = _lib.load().s2st_utterance_cmvn(len(frames), _lib.ptr(fo), x.shape[1], _lib.ptr(x), int(bool(norm_means)),
                                              int(bool(norm_vars)), _lib.ptr(out), _lib.stream_ptr(x.device))

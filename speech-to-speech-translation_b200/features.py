@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .audio_utils import _ragged_offsets, fbank_batch, get_mel_filters  # noqa: F401  (fbank_batch re-exported)
 from .feature_transforms.global_cmvn import cmvn_denormalize_cuda
-from .plans import get_stft_plan, require_cuda
+from .plans import get_stft_plan, require_cuda, upload_small
 
 
 def logmel_batch(waveforms: List, sample_rate: int = 24000, win_length: int = 1200, hop_length: int = 300,

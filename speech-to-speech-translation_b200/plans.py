@@ -6,6 +6,7 @@ audio_utils.py:246-257,275-282): window, transform tables, mel / pseudo-inverse 
 """
 import ctypes
 import hashlib
+import weakref
 
 import numpy as np
 import torch
@@ -32,6 +33,17 @@ def require_cuda(device=None):
         return torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
     return torch.device("cuda", torch.cuda.current_device() if device.index is None else device.index)
+
+
+def upload_small(a: np.ndarray, device) -> torch.Tensor:
+    """Host array -> device tensor without stalling the host: the array is staged in pinned memory (torch's caching
+    host allocator recycles the block once the copy has run) and copied with a truly asynchronous H2D.
+    ``torch.from_numpy(a).to(device)`` from pageable memory makes the driver synchronise the stream before the copy, i.e.
+    every call would wait for all GPU work enqueued before it -- which serialises back-to-back synthesis calls."""
+    a = np.ascontiguousarray(a)
+    staged = torch.empty(a.shape, dtype=torch.from_numpy(a.reshape(-1)[:0]).dtype, pin_memory=True)
+    staged.numpy()[...] = a
+    return staged.to(device, non_blocking=True)
 
 
 class StftPlan:
@@ -128,8 +140,28 @@ class FbankPlan:
 _cache = {}
 
 
+_digest_memo = {}
+
+
 def _digest(a):
-    return None if a is None else hashlib.sha1(_as_f32(a).tobytes()).hexdigest()
+    """Content digest of a constant (window, mel basis, ...).  For tensors the result is memoised on the tensor OBJECT
+    (weak reference + version counter): hashing needs the data on the host, and for a CUDA-resident module buffer
+    that is a device-to-host copy -- a full stream synchronisation -- which must not happen on every call."""
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        hit = _digest_memo.get(id(a))
+        if hit is not None and hit[0]() is a and hit[1] == a._version:
+            return hit[2]
+        d = hashlib.sha1(_as_f32(a).tobytes()).hexdigest()
+        if len(_digest_memo) > 256:
+            _digest_memo.clear()
+        try:
+            _digest_memo[id(a)] = (weakref.ref(a), a._version, d)
+        except TypeError:
+            pass
+        return d
+    return hashlib.sha1(_as_f32(a).tobytes()).hexdigest()
 
 
 def get_stft_plan(device, n_fft, win_length, hop_length, n_mels, window, inv_mel=None, mel=None):

@@ -16,7 +16,7 @@ from torch import nn
 
 from . import _lib
 from .audio_utils import TTSSpectrogram, get_mel_filters
-from .plans import get_stft_plan, require_cuda
+from .plans import get_stft_plan, require_cuda, upload_small
 
 logger = logging.getLogger(__name__)
 
@@ -82,7 +82,7 @@ class GriffinLim(torch.nn.Module):
         plan = self._plan(dev)
         total = n_utts * frames_per_utt
         fo_h = np.arange(0, total + 1, frames_per_utt, dtype=np.int32)
-        fo = torch.from_numpy(fo_h).to(dev)
+        fo = upload_small(fo_h, dev)
         L = (frames_per_utt - 1) * self.hop_length
         wave = torch.empty(n_utts, L, dtype=torch.float32, device=dev)
         if L == 0:
@@ -144,9 +144,20 @@ class GriffinLimVocoder(nn.Module):
 
     # -- plans ----------------------------------------------------------------------------------
     def _plan(self, device):
+        # The plan registry keys on a digest of the constants, which needs them on the host: for CUDA-resident buffers
+        # that is a device-to-host copy, i.e. a full stream synchronisation.  Doing it per call serialised back-to-back
+        # synthesis calls (the host could not enqueue step i+1 before step i had finished), so the lookup is memoised
+        # on the identity / version of the buffers and only repeated after .cuda() / .half() / in-place edits.
         g = self.gl_transform
-        return get_stft_plan(device, g.n_fft, g.win_length, g.hop_length, self.n_mels, g.window.float(),
-                             inv_mel=self.inv_mel_transform.basis.float())
+        w, b = g.window, self.inv_mel_transform.basis
+        key = (device.index, g.n_fft, g.win_length, g.hop_length, self.n_mels, w.data_ptr(), w._version, w.dtype,
+               b.data_ptr(), b._version, b.dtype)
+        memo = self.__dict__.setdefault("_plan_memo", {})
+        if memo.get("key") != key:
+            memo["key"] = key
+            memo["plan"] = get_stft_plan(device, g.n_fft, g.win_length, g.hop_length, self.n_mels, w.float(),
+                                         inv_mel=b.float())
+        return memo["plan"]
 
     def _device(self, x):
         if x.device.type == "cuda":
@@ -193,7 +204,7 @@ class GriffinLimVocoder(nn.Module):
         n_utts, total = len(frames), int(sum(frames))
         fo = np.zeros(n_utts + 1, np.int32)
         fo[1:] = np.cumsum(frames)
-        fo_d = torch.from_numpy(fo).to(dev, non_blocking=True)
+        fo_d = upload_small(fo, dev)
         n_samples = (total - n_utts) * self.gl_transform.hop_length
         wave = torch.empty(max(n_samples, 0), dtype=torch.float32, device=dev)
         if n_samples <= 0:
