@@ -653,6 +653,61 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
             std::memcpy(&bf, &bi, sizeof(float));
             col[(k % kpl) * 16 + k / kpl] = make_float4(w0, w1, bf, 0.0f);
         }
+        if (ok && p->fast_mode == 0) {
+            // atomic-free accumulation (same scheme as the log-mel kernel, s2st_plan::mel_col): a sub-lane keeps one pair
+            // of running sums per run of its bins that feed the same mel bin b and stores them to the run's slot of a
+            // per-half-warp slab after every step; entry = (w into b, w into b + 1, 1 if the run continues else 0, slot).
+            // mel_gather[m * 8 + q] lists the slab floats that add up to mel bin m.
+            // Slots are numbered across the whole half-warp (a sub-lane at low frequencies changes mel bin at almost
+            // every step, one at high frequencies once or twice: ~100 runs in total), so the slab is tiny.
+            constexpr int max_runs = 160, max_terms = 8;  // 2 * max_runs + 1 floats fit behind the power spectrum
+            std::vector<std::vector<int>> terms(n_bins);
+            int slot = -1;
+            for (int sl = 0; sl < 16 && ok; ++sl) {
+                int cur = -1;
+                for (int j = 0; j < kpl && ok; ++j) {
+                    float4& e = col[j * 16 + sl];
+                    const bool empty = e.x == 0.0f && e.y == 0.0f;
+                    int b;
+                    std::memcpy(&b, &e.z, sizeof(int));
+                    if (empty) b = cur < 0 ? 0 : cur;  // an empty column continues the current run
+                    float w0 = e.x, w1 = e.y;
+                    if (!empty && e.y == 0.0f && cur >= 0 && b == cur + 1) {  // only the upper bin of the run: stay in it
+                        b = cur;
+                        w1 = w0;
+                        w0 = 0.0f;
+                    }
+                    const bool keep = b == cur;
+                    if (!keep) {
+                        ++slot;
+                        cur = b;
+                        if (slot >= max_runs) {
+                            ok = false;
+                            break;
+                        }
+                        terms[b].push_back(slot * 2);
+                        if (b + 1 < n_bins) terms[b + 1].push_back(slot * 2 + 1);
+                    }
+                    float sf;
+                    std::memcpy(&sf, &slot, sizeof(float));
+                    e = make_float4(w0, w1, keep ? 1.0f : 0.0f, sf);
+                }
+            }
+            const int zero_float = 2 * (slot + 1);
+            int n_terms = 1;
+            for (int m = 0; m < n_bins && ok; ++m) {
+                if ((int)terms[m].size() > max_terms) ok = false;
+                n_terms = std::max(n_terms, (int)terms[m].size());
+            }
+            if (ok) {
+                std::vector<int> gather((size_t)n_bins * max_terms, zero_float);  // unused entries -> a float kept at zero
+                for (int m = 0; m < n_bins; ++m)
+                    for (size_t q = 0; q < terms[m].size(); ++q) gather[(size_t)m * max_terms + q] = terms[m][q];
+                p->mel_terms = n_terms;
+                p->mel_zero = zero_float;
+                if (rc == S2ST_OK) rc = upload(&p->mel_gather, gather);
+            }
+        }
         if (!ok) p->fast_mode = -1;
         if (rc == S2ST_OK) rc = upload(&p->tw16, tw16);
         if (rc == S2ST_OK) rc = upload(&p->vsplit, vsplit);
@@ -681,6 +736,7 @@ int s2st_fbank_plan_destroy(s2st_fbank_plan* plan) {
     cudaFree(plan->vsplit);
     cudaFree(plan->winp);
     cudaFree(plan->mel_col);
+    cudaFree(plan->mel_gather);
     cudaFree(plan->mel_ptr);
     cudaFree(plan->mel_idx);
     cudaFree(plan->mel_val);

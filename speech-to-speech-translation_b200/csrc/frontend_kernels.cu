@@ -22,27 +22,6 @@ namespace s2st {
 
 namespace {
 
-// One step of the column-wise mel accumulation (see k_fbank_fast): FFT bin with table entry c = (weight into mel
-// bin b, weight into b + 1, b) and value v.  While b stays the same the two partial sums stay in registers; when it
-// changes they are added to the shared accumulator.  Branch-free (predicated red.shared), because the lanes of a
-// warp change bins at different steps and a divergent flush block would run at almost every step.
-__device__ __forceinline__ void mel_col_step(float& lo, float& hi, int& cur, const float4 c, const float v, float* macc) {
-    const int b = __float_as_int(c.z);
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(macc + cur);
-    asm volatile(
-        "{ .reg .pred q; setp.ne.s32 q, %0, %1; @q red.shared.add.f32 [%2], %3; @q red.shared.add.f32 [%2+4], %4; }" ::"r"(b),
-        "r"(cur), "r"(addr), "f"(lo), "f"(hi)
-        : "memory");
-    const bool changed = b != cur;
-    lo = fmaf(c.x, v, changed ? 0.0f : lo);
-    hi = fmaf(c.y, v, changed ? 0.0f : hi);
-    cur = b;
-}
-__device__ __forceinline__ void mel_col_flush(const float lo, const float hi, const int cur, float* macc) {
-    atomicAdd(macc + cur, lo);
-    atomicAdd(macc + cur + 1, hi);
-}
-
 __device__ __forceinline__ int find_utt(const int32_t* __restrict__ fo, int n_utts, long long f) {
     int lo = 0, hi = n_utts - 1;  // last u with fo[u] <= f (utterances with zero frames are skipped)
     while (lo < hi) {
@@ -399,10 +378,15 @@ __global__ void __launch_bounds__(32 * kFbankWarps) k_fbank(const __grid_constan
 // (weight into bin b, weight into bin b + 1, b), accumulates in registers while b stays the same and adds
 // the partial sums to a small shared-memory accumulator when it changes: balanced across lanes (the row-wise
 // gather is not: high mel bins are ten times wider than low ones) and free of dependent index loads.
+#ifndef S2ST_FB_BLOCKS
+#define S2ST_FB_BLOCKS 3
+#endif
+constexpr int kFbBlocks0 = S2ST_FB_BLOCKS;  // resident blocks per SM of the 16 kHz kernel: 3 (80 registers, no spills) measured 2 % faster than 4 (64 registers, 44 B spilled)
 constexpr int kFbWarps = 8;
 constexpr int kFbChunk = 16;
 constexpr int kFbRows = 13;                 // rows of 16 elements that can hold window samples (13 * 16 >= 200)
 constexpr int kFbScratchBytes = 2048;       // per half-warp: 16 x 16 complex
+constexpr int kFbPwrFloats = 16 * 17;          // MODE 0: power spectrum staging; the mel slab (<= 2 * 160 + 1 floats) follows it
 
 struct FbankFastParams {
     int win, shift, n_bins, n_utts, mel_nnz;
@@ -415,7 +399,9 @@ struct FbankFastParams {
     const float* wave;
     const float* cmvn_mean;
     const float* cmvn_std;
-    const float4* mel_col;  // MODE 0: [256] (w into bin b, w into bin b + 1, b, 0) in the order the sub-lanes read it
+    const float4* mel_col;  // MODE 0: [256] (w into bin b, w into bin b + 1, run continues, slot) in the order the sub-lanes read it
+    const int* mel_gather;  // MODE 0: [n_bins * 8] slab floats that add up to each mel bin (s2st_fbank_plan::mel_gather)
+    int mel_terms, mel_zero;
     const int* mel_ptr;     // MODE 1: CSR rows of the mel bank (its 128-bin rows are short: the row gather wins)
     const int* mel_idx;
     const float* mel_val;
@@ -441,7 +427,7 @@ __device__ __forceinline__ void group_transpose16(float2 (&a)[16], char* scratch
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast(const __grid_constant__ FbankFastParams p) {
+__global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_fbank_fast(const __grid_constant__ FbankFastParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);                 // 256
     float2* s_vs = s_tw + 256;                                          // 256
@@ -449,7 +435,8 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast
     float4* s_col = reinterpret_cast<float4*>(s_win + kFbRows * 32);    // MODE 0: 256 column entries
     int2* s_mel = reinterpret_cast<int2*>(s_col);                       // MODE 1: mel_nnz CSR entries (idx, val bits)
     int* s_ptr = reinterpret_cast<int*>(s_mel + ((p.mel_nnz + 1) & ~1));  //         n_bins + 1 row pointers
-    char* s_scr = MODE == 0 ? reinterpret_cast<char*>(s_col + 256)
+    int* s_gather = reinterpret_cast<int*>(s_col + 256);                // MODE 0: [n_bins][8]
+    char* s_scr = MODE == 0 ? reinterpret_cast<char*>(s_gather + ((8 * p.n_bins + 3) & ~3))
                             : reinterpret_cast<char*>(s_ptr + ((p.n_bins + 1 + 3) & ~3));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & 15, grp = lane >> 4;
     for (int i = tid; i < 256; i += blockDim.x) {
@@ -459,6 +446,7 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast
     for (int i = tid; i < kFbRows * 16 * (MODE == 0 ? 2 : 1); i += blockDim.x) s_win[i] = p.winp[i];
     if constexpr (MODE == 0) {
         for (int i = tid; i < 256; i += blockDim.x) s_col[i] = p.mel_col[i];
+        for (int i = tid; i < 8 * p.n_bins; i += blockDim.x) s_gather[i] = p.mel_gather[i];
     } else {
         for (int i = tid; i < p.mel_nnz; i += blockDim.x) s_mel[i] = make_int2(p.mel_idx[i], __float_as_int(p.mel_val[i]));
         for (int i = tid; i <= p.n_bins; i += blockDim.x) s_ptr[i] = p.mel_ptr[i];
@@ -495,17 +483,26 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast
             float2 a[16];
             if constexpr (MODE == 0) {
                 const bool al = (reinterpret_cast<uintptr_t>(src[0]) & 7) == 0;
+                if (valid[0] && al && (p.win & 1) == 0) {
+                    // the common case (8-byte aligned frame start, even window length): one predicated 8-byte load
+                    // per row, no nested branches
+                    const float2* s2 = reinterpret_cast<const float2*>(src[0]) + sub;
+                    const int n2 = (p.win >> 1) - sub;  // element 16 r + sub exists iff 16 r < n2
 #pragma unroll
-                for (int r = 0; r < kFbRows; ++r) {
-                    const int j = 32 * r + 2 * sub;
-                    float2 v = make_float2(0.0f, 0.0f);
-                    if (valid[0] && j + 1 < p.win) {
-                        if (al) v = __ldg(reinterpret_cast<const float2*>(src[0] + j));
-                        else v = make_float2(__ldg(src[0] + j), __ldg(src[0] + j + 1));
-                    } else if (valid[0] && j < p.win) {
-                        v.x = __ldg(src[0] + j);
+                    for (int r = 0; r < kFbRows; ++r) a[r] = 16 * r < n2 ? __ldg(s2 + 16 * r) : make_float2(0.0f, 0.0f);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kFbRows; ++r) {
+                        const int j = 32 * r + 2 * sub;
+                        float2 v = make_float2(0.0f, 0.0f);
+                        if (valid[0] && j + 1 < p.win) {
+                            if (al) v = __ldg(reinterpret_cast<const float2*>(src[0] + j));
+                            else v = make_float2(__ldg(src[0] + j), __ldg(src[0] + j + 1));
+                        } else if (valid[0] && j < p.win) {
+                            v.x = __ldg(src[0] + j);
+                        }
+                        a[r] = v;
                     }
-                    a[r] = v;
                 }
                 float sum = 0.0f;
 #pragma unroll
@@ -597,14 +594,22 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast
                 // and for the run-per-lane read below)
 #pragma unroll
                 for (int k2 = 0; k2 < 16; ++k2) pwr[sub * 17 + k2] = pw[k2];
-                for (int i = sub; i < acc_floats; i += 16) macc[i] = 0.0f;
                 __syncwarp();
-                // mel: sub-lane s owns FFT bins [16 s, 16 s + 16)
+                // mel: sub-lane s owns FFT bins [16 s, 16 s + 16).  Running (lo, hi) partial sums per run of bins that
+                // feed the same mel bin, stored to the run's slot after every step (the last store of a run is its
+                // total): no branches, no atomics.  The slab (one (lo, hi) pair per run, ~100 runs per frame) sits
+                // behind the power spectrum.
                 float lo = 0.0f, hi = 0.0f;
-                int cur = __float_as_int(s_col[sub].z);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) mel_col_step(lo, hi, cur, s_col[j * 16 + sub], pwr[j * 17 + sub], macc);  // bin 16 sub + j
-                mel_col_flush(lo, hi, cur, macc);
+                float2* slab2 = reinterpret_cast<float2*>(pwr + kFbPwrFloats);
+#pragma unroll 4
+                for (int j = 0; j < 16; ++j) {
+                    const float4 c = s_col[j * 16 + sub];
+                    const float v = pwr[j * 17 + sub];  // bin 16 sub + j
+                    lo = fmaf(c.x, v, lo * c.z);
+                    hi = fmaf(c.y, v, hi * c.z);
+                    slab2[__float_as_int(c.w)] = make_float2(lo, hi);
+                }
+                if (sub == 0) pwr[kFbPwrFloats + p.mel_zero] = 0.0f;  // the float unused gather entries point at
             } else {
                 // frame A at [0, 128), frame B at [128, 256); row gather: sub-lane s owns mel bins s, s + 16, ...
 #pragma unroll
@@ -631,7 +636,14 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? 4 : 3) k_fbank_fast
             for (int i = 0; i < n_mel_iter; ++i) {
                 const int m = sub + 16 * i;
                 if (m < p.n_bins) {
-                    float v0 = logf(fmaxf(macc[m], 1.1920928955078125e-07f));
+                    float e0;
+                    if constexpr (MODE == 0) {
+                        e0 = 0.0f;
+                        for (int q = 0; q < p.mel_terms; ++q) e0 += pwr[kFbPwrFloats + s_gather[8 * m + q]];
+                    } else {
+                        e0 = macc[m];
+                    }
+                    float v0 = logf(fmaxf(e0, 1.1920928955078125e-07f));
                     float v1 = MODE == 1 ? logf(fmaxf(macc[p.n_bins + 1 + m], 1.1920928955078125e-07f)) : 0.0f;
                     if (p.cmvn_mean) {
                         const float mu = __ldg(p.cmvn_mean + m), sd = __ldg(p.cmvn_std + m);
@@ -818,18 +830,21 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
         q.cmvn_mean = cmvn_mean;
         q.cmvn_std = cmvn_std;
         q.mel_col = plan->mel_col;
+        q.mel_gather = plan->mel_gather;
+        q.mel_terms = plan->mel_terms;
+        q.mel_zero = plan->mel_zero;
         q.mel_ptr = plan->mel_ptr;
         q.mel_idx = plan->mel_idx;
         q.mel_val = plan->mel_val;
         q.mel_nnz = plan->mel_nnz;
         q.out = out;
         const size_t acc_floats = (size_t)(((plan->fast_mode + 1) * (plan->n_bins + 1) + 3) & ~3);
-        const size_t tab = plan->fast_mode == 0 ? sizeof(float4) * 256
+        const size_t tab = plan->fast_mode == 0 ? sizeof(float4) * 256 + sizeof(int) * (size_t)((8 * plan->n_bins + 3) & ~3)
                                                 : sizeof(int2) * ((plan->mel_nnz + 1) & ~1) + sizeof(int) * ((plan->n_bins + 1 + 3) & ~3);
         const size_t fsmem = sizeof(float2) * 512 + sizeof(float) * kFbRows * 32 + tab +
                              (size_t)kFbWarps * 2 * (kFbScratchBytes + 4 * acc_floats);
         const long long pair_chunks = ((total_frames + kFbChunk - 1) / kFbChunk + 1) / 2;
-        const int fgrid = (int)min((long long)plan->num_sms * (plan->fast_mode == 0 ? 4 : 3), (pair_chunks + kFbWarps - 1) / kFbWarps);
+        const int fgrid = (int)min((long long)plan->num_sms * (plan->fast_mode == 0 ? kFbBlocks0 : 3), (pair_chunks + kFbWarps - 1) / kFbWarps);
         if (plan->fast_mode == 0) {
             S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
             k_fbank_fast<0><<<fgrid, 32 * kFbWarps, fsmem, stream>>>(q);

@@ -63,7 +63,10 @@ struct s2st_fbank_plan {
     float2* tw16;       // [256] exp(-2 pi i k1 n2 / 256) at [k1 * 16 + n2]
     float2* vsplit;     // [256] -i exp(-2 pi i k / 512)
     float* winp;        // window in the kernel's register layout, zero padded (see FbankFastParams)
-    float4* mel_col;    // [256] per FFT bin: (weight into mel bin b, weight into b + 1, b as int bits, 0)
+    float4* mel_col;    // [256] per FFT bin; fast_mode 0: (w into mel bin b, w into b + 1, run continues ? 1 : 0, slot), see api.cu
+    int* mel_gather;    // fast_mode 0: [n_bins * 8] slab floats that add up to each mel bin
+    int mel_terms;      //              longest gather list
+    int mel_zero;       //              index of the slab float that is kept at zero
 };
 
 namespace s2st {
