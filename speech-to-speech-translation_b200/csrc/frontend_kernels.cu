@@ -167,28 +167,42 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
     for (long long chunk = (long long)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (long long)gridDim.x * 8) {
         long long f = chunk * kLmChunk;
         int u = find_utt(p.frame_offsets, p.n_utts, f);
+        // the utterance's table entries stay in registers while the chunk stays inside it (no dependent loads per frame)
+        long long fo_u = __ldg(p.frame_offsets + u), fo_next = __ldg(p.frame_offsets + u + 1);
+        long long woff = __ldg(p.wave_offsets + u);
+        int n = (int)(__ldg(p.wave_offsets + u + 1) - woff);
         {
             // the chunk's frames are (mostly) consecutive hops of one utterance: ask L2 for their samples now
-            const long long woff = __ldg(p.wave_offsets + u);
-            const long long n = __ldg(p.wave_offsets + u + 1) - woff;
-            const long long b0 = (f - __ldg(p.frame_offsets + u)) * p.hop + p.rot - p.half;
+            const long long b0 = (f - fo_u) * p.hop + p.rot - p.half;
             const long long span = (long long)(kLmChunk - 1) * p.hop + 64 * NZ;
             for (long long j = b0 + 32 * lane; j < b0 + span; j += 32 * 32)
                 if (j >= 0 && j < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wave + woff + j));
         }
 #pragma unroll 1
         for (int it = 0; it < kLmChunk && f < p.total_frames; ++it, ++f) {
-            while (u + 1 < p.n_utts && f >= __ldg(p.frame_offsets + u + 1)) ++u;
-            const int t = (int)(f - __ldg(p.frame_offsets + u));
-            const long long woff = __ldg(p.wave_offsets + u);
-            const int n = (int)(__ldg(p.wave_offsets + u + 1) - woff);
+            while (u + 1 < p.n_utts && f >= fo_next) {
+                ++u;
+                fo_u = fo_next;
+                fo_next = __ldg(p.frame_offsets + u + 1);
+                woff = __ldg(p.wave_offsets + u);
+                n = (int)(__ldg(p.wave_offsets + u + 1) - woff);
+            }
+            const int t = (int)(f - fo_u);
             const float* src = p.wave + woff;
             const int base0 = t * p.hop + p.rot - p.half;
             float2 a[32];
-            if (base0 >= 0 && base0 + 64 * NZ <= n && (((woff + base0) & 1) == 0)) {
-                const float2* s2 = reinterpret_cast<const float2*>(src + base0) + lane;
+            if (base0 >= 0 && base0 + 64 * NZ <= n) {
+                // interior frame: no reflection.  An utterance that starts at an odd sample of the concatenated
+                // buffer cannot use 8-byte loads; it still skips the index arithmetic of the edge path
+                if (((woff + base0) & 1) == 0) {
+                    const float2* s2 = reinterpret_cast<const float2*>(src + base0) + lane;
 #pragma unroll
-                for (int r = 0; r < NZ; ++r) a[brev5(r)] = __ldg(s2 + 32 * r);
+                    for (int r = 0; r < NZ; ++r) a[brev5(r)] = __ldg(s2 + 32 * r);
+                } else {
+                    const float* s1 = src + base0 + 2 * lane;
+#pragma unroll
+                    for (int r = 0; r < NZ; ++r) a[brev5(r)] = make_float2(__ldg(s1 + 64 * r), __ldg(s1 + 64 * r + 1));
+                }
             } else {
                 const int base = base0 + 2 * lane;
 #pragma unroll
@@ -463,6 +477,9 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
     for (long long cp = (long long)blockIdx.x * kFbWarps + warp; 2 * cp < n_chunks; cp += (long long)gridDim.x * kFbWarps) {
         long long f = (2 * cp + grp) * kFbChunk;
         int u = find_utt(p.frame_offsets, p.n_utts, f < p.total_frames ? f : p.total_frames - 1);
+        // the utterance's table entries stay in registers while the chunk stays inside it (no dependent loads per frame)
+        long long fo_u = __ldg(p.frame_offsets + u), fo_next = __ldg(p.frame_offsets + u + 1);
+        const float* wave_u = p.wave + __ldg(p.wave_offsets + u);
 #pragma unroll 1
         for (int it = 0; it < kFbChunk / (MODE + 1); ++it) {
             // ---- resolve the frame(s) of this step
@@ -472,8 +489,13 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
             for (int q = 0; q <= MODE; ++q) {
                 valid[q] = f < p.total_frames;
                 if (valid[q]) {
-                    while (u + 1 < p.n_utts && f >= __ldg(p.frame_offsets + u + 1)) ++u;
-                    src[q] = p.wave + __ldg(p.wave_offsets + u) + (f - __ldg(p.frame_offsets + u)) * p.shift;
+                    while (u + 1 < p.n_utts && f >= fo_next) {
+                        ++u;
+                        fo_u = fo_next;
+                        fo_next = __ldg(p.frame_offsets + u + 1);
+                        wave_u = p.wave + __ldg(p.wave_offsets + u);
+                    }
+                    src[q] = wave_u + (f - fo_u) * p.shift;
                 } else {
                     src[q] = p.wave;  // a readable address; nothing is stored for this frame
                 }
@@ -483,13 +505,21 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
             float2 a[16];
             if constexpr (MODE == 0) {
                 const bool al = (reinterpret_cast<uintptr_t>(src[0]) & 7) == 0;
-                if (valid[0] && al && (p.win & 1) == 0) {
-                    // the common case (8-byte aligned frame start, even window length): one predicated 8-byte load
-                    // per row, no nested branches
-                    const float2* s2 = reinterpret_cast<const float2*>(src[0]) + sub;
+                if (valid[0] && (p.win & 1) == 0) {
+                    // the common case (even window length): predicated loads, no nested branches -- one 8-byte load
+                    // per row when the frame starts 8-byte aligned, two 4-byte loads otherwise (an utterance that
+                    // begins at an odd sample of the concatenated buffer)
                     const int n2 = (p.win >> 1) - sub;  // element 16 r + sub exists iff 16 r < n2
+                    if (al) {
+                        const float2* s2 = reinterpret_cast<const float2*>(src[0]) + sub;
 #pragma unroll
-                    for (int r = 0; r < kFbRows; ++r) a[r] = 16 * r < n2 ? __ldg(s2 + 16 * r) : make_float2(0.0f, 0.0f);
+                        for (int r = 0; r < kFbRows; ++r) a[r] = 16 * r < n2 ? __ldg(s2 + 16 * r) : make_float2(0.0f, 0.0f);
+                    } else {
+                        const float* s1 = src[0] + 2 * sub;
+#pragma unroll
+                        for (int r = 0; r < kFbRows; ++r)
+                            a[r] = 16 * r < n2 ? make_float2(__ldg(s1 + 32 * r), __ldg(s1 + 32 * r + 1)) : make_float2(0.0f, 0.0f);
+                    }
                 } else {
 #pragma unroll
                     for (int r = 0; r < kFbRows; ++r) {

@@ -23,16 +23,24 @@ AUDIO_FEATURE_TRANSFORM_REGISTRY = {}
 AUDIO_FEATURE_TRANSFORM_CLASS_NAMES = set()
 
 
+def _registration_error(name, cls):
+    """The three ways a registration can be refused (feature_transforms/__init__.py:20-31), same messages."""
+    if name in AUDIO_FEATURE_TRANSFORM_REGISTRY:
+        return f"Cannot register duplicate transform ({name})"
+    if not (isinstance(cls, type) and issubclass(cls, AudioFeatureTransform)):
+        return f"Transform ({name}: {cls.__name__}) must extend AudioFeatureTransform"
+    if cls.__name__ in AUDIO_FEATURE_TRANSFORM_CLASS_NAMES:
+        return f"Cannot register audio feature transform with duplicate class name ({cls.__name__})"
+    return None
+
+
 def register_audio_feature_transform(name):
     def decorator(cls):
-        if name in AUDIO_FEATURE_TRANSFORM_REGISTRY:
-            raise ValueError(f"Cannot register duplicate transform ({name})")
-        if not (isinstance(cls, type) and issubclass(cls, AudioFeatureTransform)):
-            raise ValueError(f"Transform ({name}: {cls.__name__}) must extend AudioFeatureTransform")
-        if cls.__name__ in AUDIO_FEATURE_TRANSFORM_CLASS_NAMES:
-            raise ValueError(f"Cannot register audio feature transform with duplicate class name ({cls.__name__})")
-        AUDIO_FEATURE_TRANSFORM_REGISTRY[name] = cls
+        problem = _registration_error(name, cls)
+        if problem is not None:
+            raise ValueError(problem)
         AUDIO_FEATURE_TRANSFORM_CLASS_NAMES.add(cls.__name__)
+        AUDIO_FEATURE_TRANSFORM_REGISTRY[name] = cls
         return cls
 
     return decorator
@@ -69,6 +77,14 @@ class CompositeAudioFeatureTransform(AudioFeatureTransform):
     def __call__(self, x):
         for t in self.transforms:
             x = t(x)
+        return x
+
+    def apply_cuda(self, x, frames):
+        """The chain on a ragged, device-resident batch (x [sum T_i, n_feat] float32 CUDA, utterance i owning the next
+        frames[i] rows): one or two launches per transform for the whole batch instead of a numpy round trip per
+        utterance.  Every registered transform of this package implements ``apply_cuda(x, frames)``."""
+        for t in self.transforms:
+            x = t.apply_cuda(x, frames)
         return x
 
     def __repr__(self):

@@ -65,7 +65,8 @@ class _GlobalCMVNBase(AudioFeatureTransform):
                               torch.from_numpy(np.ascontiguousarray(self.std, np.float32)).to(device))
         return self._dev[key]
 
-    def apply_cuda(self, x: torch.Tensor) -> torch.Tensor:
+    def apply_cuda(self, x: torch.Tensor, frames=None) -> torch.Tensor:
+        """x [..., n_feat] float32 on CUDA; ``frames`` (the ragged layout) is irrelevant to a global transform."""
         mean, std = self._stats(x.device)
         return cmvn_apply_cuda(x, mean, std)
 

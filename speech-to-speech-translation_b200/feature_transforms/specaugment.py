@@ -31,46 +31,36 @@ def utterance_mean_cuda(x: torch.Tensor, frames: Sequence[int]) -> np.ndarray:
     return sums.cpu().numpy() / counts
 
 
+# config key -> constructor argument, in the reference's order (specaugment.py:16-27)
+_CONFIG_KEYS = (("time_warp_W", "time_warp_w", 0), ("freq_mask_N", "freq_mask_n", 0), ("freq_mask_F", "freq_mask_f", 0),
+                ("time_mask_N", "time_mask_n", 0), ("time_mask_T", "time_mask_t", 0), ("time_mask_p", "time_mask_p", 0.0),
+                ("mask_value", "mask_value", None))
+
+
 @register_audio_feature_transform("specaugment")
 class SpecAugmentTransform(AudioFeatureTransform):
-    """SpecAugment (https://arxiv.org/abs/1904.08779)"""
+    """SpecAugment (https://arxiv.org/abs/1904.08779): frequency and time masking."""
 
     @classmethod
     def from_config_dict(cls, config=None):
-        _config = {} if config is None else config
-        return SpecAugmentTransform(
-            _config.get("time_warp_W", 0),
-            _config.get("freq_mask_N", 0),
-            _config.get("freq_mask_F", 0),
-            _config.get("time_mask_N", 0),
-            _config.get("time_mask_T", 0),
-            _config.get("time_mask_p", 0.0),
-            _config.get("mask_value", None),
-        )
+        cfg = config or {}
+        return cls(**{arg: cfg.get(key, default) for key, arg, default in _CONFIG_KEYS})
 
     def __init__(self, time_warp_w: int = 0, freq_mask_n: int = 0, freq_mask_f: int = 0, time_mask_n: int = 0,
                  time_mask_t: int = 0, time_mask_p: float = 0.0, mask_value: Optional[float] = 0.0):
-        # Sanity checks
-        assert mask_value is None or isinstance(
-            mask_value, numbers.Number
-        ), f"mask_value (type: {type(mask_value)}) must be None or a number"
-        if freq_mask_n > 0:
-            assert freq_mask_f > 0, f"freq_mask_F ({freq_mask_f}) must be larger than 0 when doing freq masking."
-        if time_mask_n > 0:
-            assert time_mask_t > 0, f"time_mask_T ({time_mask_t}) must be larger than 0 when doing time masking."
-        self.time_warp_w = time_warp_w
-        self.freq_mask_n = freq_mask_n
-        self.freq_mask_f = freq_mask_f
-        self.time_mask_n = time_mask_n
-        self.time_mask_t = time_mask_t
-        self.time_mask_p = time_mask_p
-        self.mask_value = mask_value
+        # the reference's sanity checks (specaugment.py:40-53), same messages
+        if not (mask_value is None or isinstance(mask_value, numbers.Number)):
+            raise AssertionError(f"mask_value (type: {type(mask_value)}) must be None or a number")
+        if freq_mask_n > 0 and not freq_mask_f > 0:
+            raise AssertionError(f"freq_mask_F ({freq_mask_f}) must be larger than 0 when doing freq masking.")
+        if time_mask_n > 0 and not time_mask_t > 0:
+            raise AssertionError(f"time_mask_T ({time_mask_t}) must be larger than 0 when doing time masking.")
+        for _key, arg, _default in _CONFIG_KEYS:
+            setattr(self, arg, locals()[arg])
 
     def __repr__(self):
-        return (self.__class__.__name__ + "(" + ", ".join([
-            f"time_warp_w={self.time_warp_w}", f"freq_mask_n={self.freq_mask_n}", f"freq_mask_f={self.freq_mask_f}",
-            f"time_mask_n={self.time_mask_n}", f"time_mask_t={self.time_mask_t}", f"time_mask_p={self.time_mask_p}",
-        ]) + ")")
+        shown = ", ".join(f"{arg}={getattr(self, arg)}" for _key, arg, _default in _CONFIG_KEYS[:-1])
+        return f"{type(self).__name__}({shown})"
 
     def draw_masks(self, num_frames: int, num_freqs: int):
         """Rectangles (row0, row1, col0, col1) for one [num_frames, num_freqs] spectrogram, consuming numpy's global

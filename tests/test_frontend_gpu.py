@@ -251,3 +251,21 @@ def test_dtw_bit_exact_and_mcd_metric(pkg, built_lib):
         assert np.allclose(got, d["mcd_" + str(nt)], rtol=2e-3), (nt, got, d["mcd_" + str(nt)])
     with pytest.raises(ValueError, match="not supported"):
         mcd.batch_mel_cepstral_distortion(ya, yb, 24000, normalize_type="bogus")
+
+
+def test_composite_chain_on_a_ragged_device_batch(pkg, built_lib, tmp_path):
+    """CompositeAudioFeatureTransform.apply_cuda == the numpy chain applied utterance by utterance."""
+    ft = pkg.feature_transforms
+    rng = np.random.RandomState(5)
+    np.savez(tmp_path / "stats.npz", mean=rng.randn(80).astype(np.float32), std=rng.uniform(0.5, 2, 80).astype(np.float32))
+    cfg = {"transforms": ["utterance_cmvn", "global_cmvn", "specaugment"],
+           "global_cmvn": {"stats_npz_path": str(tmp_path / "stats.npz")},
+           "specaugment": {"freq_mask_N": 2, "freq_mask_F": 20, "time_mask_N": 1, "time_mask_T": 30, "time_mask_p": 0.5,
+                           "mask_value": 0.0}}
+    chain = ft.CompositeAudioFeatureTransform.from_config_dict(cfg)
+    xs = [(rng.randn(T, 80) * 2 - 3).astype(np.float32) for T in (40, 7, 513)]
+    np.random.seed(9)
+    singles = [chain(x) for x in xs]
+    np.random.seed(9)
+    yb = chain.apply_cuda(torch.from_numpy(np.concatenate(xs)).cuda(), [x.shape[0] for x in xs]).cpu().numpy()
+    assert np.array_equal(yb, np.concatenate(singles))
