@@ -22,6 +22,18 @@ namespace s2st {
 
 namespace {
 
+// Sum of the slab floats a mel bin's gather list names (8 ints per bin, unused entries point at a float kept at
+// zero).  Fixed trip count (4 or 8, warp-uniform), indices fetched with 16-byte loads: no loop-carried index loads.
+__device__ __forceinline__ float gather_sum(const float* __restrict__ slab, const int* __restrict__ list, int terms) {
+    const int4 g = *reinterpret_cast<const int4*>(list);
+    float acc = ((slab[g.x] + slab[g.y]) + slab[g.z]) + slab[g.w];
+    if (terms > 4) {
+        const int4 h = *reinterpret_cast<const int4*>(list + 4);
+        acc = (((acc + slab[h.x]) + slab[h.y]) + slab[h.z]) + slab[h.w];
+    }
+    return acc;
+}
+
 __device__ __forceinline__ int find_utt(const int32_t* __restrict__ fo, int n_utts, long long f) {
     int lo = 0, hi = n_utts - 1;  // last u with fo[u] <= f (utterances with zero frames are skipped)
     while (lo < hi) {
@@ -234,23 +246,20 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
             {
                 // column-wise mel: running (lo, hi) partial sums per run of bins that feed the same mel bin, written
                 // to the run's slot after every step (the last write of a run is its total): no branches, no atomics
-                float lo = 0.0f, hi = 0.0f;
+                float2 lh = make_float2(0.0f, 0.0f);  // (lo, hi) as one packed pair: 2 instructions per step
                 const float* sp = scratch + kPrunedRows * lane;
                 float2* my = reinterpret_cast<float2*>(slab) + kLmSlots * lane;
 #pragma unroll
                 for (int j = 0; j < kPrunedRows; ++j) {
                     const float4 c = s_col[j * 32 + lane];
-                    const float v = sp[j];
-                    lo = fmaf(c.x, v, lo * c.z);
-                    hi = fmaf(c.y, v, hi * c.z);
-                    my[__float_as_int(c.w)] = make_float2(lo, hi);
+                    lh = fma2(make_float2(c.x, c.y), bcast2(sp[j]), mul2(lh, bcast2(c.z)));
+                    my[__float_as_int(c.w)] = lh;
                 }
                 if (lane == 0) slab[2 * 32 * kLmSlots] = 0.0f;  // (the transposes use the whole scratch)
             }
             __syncwarp();
             for (int m = lane; m < p.n_mels; m += 32) {
-                float acc = 0.0f;
-                for (int q = 0; q < p.mel_terms; ++q) acc += slab[s_gather[8 * m + q]];
+                const float acc = gather_sum(slab, s_gather + 8 * m, p.mel_terms);
                 float v = logf(fmaxf(acc, p.eps));
                 if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
                 p.logmel_out[f * p.n_mels + m] = v;
@@ -629,15 +638,13 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
                 // feed the same mel bin, stored to the run's slot after every step (the last store of a run is its
                 // total): no branches, no atomics.  The slab (one (lo, hi) pair per run, ~100 runs per frame) sits
                 // behind the power spectrum.
-                float lo = 0.0f, hi = 0.0f;
+                float2 lh = make_float2(0.0f, 0.0f);  // (lo, hi) as one packed pair: 2 instructions per step
                 float2* slab2 = reinterpret_cast<float2*>(pwr + kFbPwrFloats);
 #pragma unroll 4
                 for (int j = 0; j < 16; ++j) {
                     const float4 c = s_col[j * 16 + sub];
-                    const float v = pwr[j * 17 + sub];  // bin 16 sub + j
-                    lo = fmaf(c.x, v, lo * c.z);
-                    hi = fmaf(c.y, v, hi * c.z);
-                    slab2[__float_as_int(c.w)] = make_float2(lo, hi);
+                    lh = fma2(make_float2(c.x, c.y), bcast2(pwr[j * 17 + sub]), mul2(lh, bcast2(c.z)));  // bin 16 sub + j
+                    slab2[__float_as_int(c.w)] = lh;
                 }
                 if (sub == 0) pwr[kFbPwrFloats + p.mel_zero] = 0.0f;  // the float unused gather entries point at
             } else {
@@ -668,8 +675,7 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
                 if (m < p.n_bins) {
                     float e0;
                     if constexpr (MODE == 0) {
-                        e0 = 0.0f;
-                        for (int q = 0; q < p.mel_terms; ++q) e0 += pwr[kFbPwrFloats + s_gather[8 * m + q]];
+                        e0 = gather_sum(pwr + kFbPwrFloats, s_gather + 8 * m, p.mel_terms);
                     } else {
                         e0 = macc[m];
                     }
