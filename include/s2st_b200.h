@@ -175,12 +175,14 @@ int s2st_cmvn_denormalize(int64_t n_rows, int n_cols, const float* x_dev, const 
 int s2st_cmvn_accumulate(int64_t n_rows, int n_cols, const float* x_dev, double* sums_dev, void* stream);
 
 /* UtteranceCMVN.__call__ (feature_transforms/utterance_cmvn.py:29-40) for a ragged batch: utterance u owns rows
- * frame_offsets_dev[u] .. frame_offsets_dev[u+1] of x_dev [total_rows, n_cols].  Per utterance and column:
- *   mean = sum_t x / T, var = sum_t x^2 / T - mean^2 (float32, accumulated in row order like numpy's axis-0
- *   reduction), out = x - mean if norm_means, then / sqrt(max(var, 1e-10)) if norm_vars.  Bit-identical to the
- * reference.  In place allowed. */
-int s2st_utterance_cmvn(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev,
-                        int norm_means, int norm_vars, float* out_dev, void* stream);
+ * frame_offsets_dev[u] .. frame_offsets_dev[u+1] of x_dev [total_rows, n_cols] (total_rows = frame_offsets[n_utts]).
+ * Per utterance and column: mean = sum_t x / T, var = sum_t x^2 / T - mean^2 (float32, accumulated in row order like
+ * numpy's axis-0 reduction), out = x - mean if norm_means, then / sqrt(max(var, 1e-10)) if norm_vars.  Bit-identical
+ * to the reference.  stats_dev: caller-owned workspace of n_utts * 2 * n_cols floats; it returns (mean, std) per
+ * utterance.  In place allowed. */
+int s2st_utterance_cmvn(int n_utts, int64_t total_rows, const int32_t* frame_offsets_dev, int n_cols,
+                        const float* x_dev, int norm_means, int norm_vars, float* out_dev, float* stats_dev,
+                        void* stream);
 /* Per-utterance sum of all elements (double): the "local mean" mask value of SpecAugmentTransform
  * (feature_transforms/specaugment.py:88-89) is sums_dev[u] / (T_u * n_cols). */
 int s2st_utterance_sum(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev,

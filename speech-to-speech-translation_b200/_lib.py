@@ -71,8 +71,8 @@ SIGNATURES = {
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "s2st_cmvn_accumulate": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p]),
-    "s2st_utterance_cmvn": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
-                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "s2st_utterance_cmvn": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "s2st_utterance_sum": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p]),
     "s2st_fill_rects": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,

@@ -793,14 +793,15 @@ int s2st_cmvn_accumulate(int64_t n_rows, int n_cols, const float* x_dev, double*
     return launch_cmvn_accumulate(n_rows, n_cols, x_dev, sums_dev, static_cast<cudaStream_t>(stream));
 }
 
-int s2st_utterance_cmvn(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev, int norm_means,
-                        int norm_vars, float* out_dev, void* stream) {
-    if (n_utts < 0 || n_cols < 1 || (n_utts > 0 && (!frame_offsets_dev || !x_dev || !out_dev))) {
+int s2st_utterance_cmvn(int n_utts, int64_t total_rows, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev,
+                        int norm_means, int norm_vars, float* out_dev, float* stats_dev, void* stream) {
+    if (n_utts < 0 || total_rows < 0 || n_cols < 1 ||
+        (n_utts > 0 && total_rows > 0 && (!frame_offsets_dev || !x_dev || !out_dev || !stats_dev))) {
         set_error("bad argument to s2st_utterance_cmvn");
         return S2ST_EINVAL;
     }
-    return launch_utterance_cmvn(n_utts, frame_offsets_dev, n_cols, x_dev, out_dev, norm_means != 0, norm_vars != 0,
-                                 static_cast<cudaStream_t>(stream));
+    return launch_utterance_cmvn(n_utts, total_rows, frame_offsets_dev, n_cols, x_dev, out_dev, norm_means != 0,
+                                 norm_vars != 0, stats_dev, static_cast<cudaStream_t>(stream));
 }
 
 int s2st_utterance_sum(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev, double* sums_dev,

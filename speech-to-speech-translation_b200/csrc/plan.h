@@ -105,8 +105,8 @@ int launch_cmvn_accumulate(long long n_rows, int n_cols, const float* x, double*
 
 
 // transform_kernels.cu
-int launch_utterance_cmvn(int n_utts, const int32_t* fo, int n_cols, const float* x, float* out, bool norm_means,
-                          bool norm_vars, cudaStream_t stream);
+int launch_utterance_cmvn(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const float* x, float* out,
+                          bool norm_means, bool norm_vars, float* stats, cudaStream_t stream);
 int launch_utterance_sum(int n_utts, const int32_t* fo, int n_cols, const float* x, double* sums, cudaStream_t stream);
 int launch_fill_rects(int n_rects, const int32_t* rects, const float* values, int n_cols, float* x, cudaStream_t stream);
 

@@ -10,36 +10,95 @@
 namespace s2st {
 namespace {
 
-// One thread per (utterance, column).  numpy reduces a C-contiguous [T, n] float32 array over axis 0 row by row, in
-// float32 (x.mean(axis=0), (x ** 2).sum(axis=0)), so the reference's statistics are a plain sequential float32
+// Statistics: one thread per (utterance, column).  numpy reduces a C-contiguous [T, n] float32 array over axis 0 row by
+// row, in float32 (x.mean(axis=0), (x ** 2).sum(axis=0)), so the reference's statistics are a plain sequential float32
 // accumulation per column: the same order and roundings are used here (no FMA contraction), which makes the result
-// bit-identical.  Lanes are consecutive columns: every row access of a warp is one coalesced segment.
-__global__ void __launch_bounds__(128) k_utterance_cmvn(const int32_t* __restrict__ fo, int n_cols,
-                                                         const float* __restrict__ x, float* __restrict__ out,
-                                                         int norm_means, int norm_vars) {
+// bit-identical.  Lanes are consecutive columns: every row access of a warp is one coalesced segment; eight rows are
+// in flight per thread.  stats[u] = (mean[n_cols], std[n_cols]).
+__global__ void __launch_bounds__(128) k_utterance_stats(const int32_t* __restrict__ fo, int n_cols,
+                                                          const float* __restrict__ x, float* __restrict__ stats) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= n_cols) return;
     const int r0 = fo[blockIdx.x], T = fo[blockIdx.x + 1] - r0;
     if (T <= 0) return;
     const float* px = x + (size_t)r0 * n_cols + c;
-    float* po = out + (size_t)r0 * n_cols + c;
     float s = 0.0f, s2 = 0.0f;
-#pragma unroll 8
-    for (int r = 0; r < T; ++r) {
-        const float v = px[(size_t)r * n_cols];
+    int r = 0;
+    for (; r + 8 <= T; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(px + (size_t)(r + k) * n_cols);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s = __fadd_rn(s, v[k]);
+            s2 = __fadd_rn(s2, __fmul_rn(v[k], v[k]));
+        }
+    }
+    for (; r < T; ++r) {
+        const float v = __ldg(px + (size_t)r * n_cols);
         s = __fadd_rn(s, v);
         s2 = __fadd_rn(s2, __fmul_rn(v, v));
     }
     const float n = (float)T;
     const float mean = __fdiv_rn(s, n);
     const float var = __fsub_rn(__fdiv_rn(s2, n), __fmul_rn(mean, mean));
-    const float sd = sqrtf(fmaxf(var, 1e-10f));
-#pragma unroll 8
-    for (int r = 0; r < T; ++r) {
-        float v = px[(size_t)r * n_cols];
-        if (norm_means) v = __fsub_rn(v, mean);
-        if (norm_vars) v = __fdiv_rn(v, sd);
-        po[(size_t)r * n_cols] = v;
+    stats[(size_t)blockIdx.x * 2 * n_cols + c] = mean;
+    stats[(size_t)blockIdx.x * 2 * n_cols + n_cols + c] = sqrtf(fmaxf(var, 1e-10f));
+}
+
+// Normalisation: a streaming pass over the concatenated rows (16-byte accesses when n_cols is a multiple of 4, which
+// the 80-bin features are).  A block owns kApplyRows consecutive rows; a thread walks down its column group and
+// follows the utterance boundaries with a running index (one binary search per thread).
+constexpr int kApplyRows = 64;
+template <int VEC>
+__global__ void __launch_bounds__(256) k_utterance_apply(const int32_t* __restrict__ fo, int n_utts, long long n_rows,
+                                                          int n_cols, const float* __restrict__ x,
+                                                          const float* __restrict__ stats, float* __restrict__ out,
+                                                          int norm_means, int norm_vars) {
+    const int groups = n_cols / VEC;              // column groups per row
+    const int rows_per_pass = blockDim.x / groups;  // rows the block touches at once
+    const int rl = threadIdx.x / groups, g = threadIdx.x - rl * groups;
+    if (rl >= rows_per_pass) return;
+    const long long row0 = (long long)blockIdx.x * kApplyRows;
+    long long row = row0 + rl;
+    if (row >= n_rows) return;
+    int lo = 0, hi = n_utts - 1;  // last u with fo[u] <= row
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (fo[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    int u = lo;
+    long long next = fo[u + 1];
+    float mean[VEC], sd[VEC];
+    auto load_stats = [&]() {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            mean[k] = stats[(size_t)u * 2 * n_cols + g * VEC + k];
+            sd[k] = stats[(size_t)u * 2 * n_cols + n_cols + g * VEC + k];
+        }
+    };
+    load_stats();
+    const long long row_end = min(row0 + kApplyRows, n_rows);
+    for (; row < row_end; row += rows_per_pass) {
+        if (row >= next) {
+            while (u + 1 < n_utts && row >= next) next = fo[++u + 1];
+            load_stats();
+        }
+        const size_t off = (size_t)row * n_cols + g * VEC;
+        float v[VEC];
+        if constexpr (VEC == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(x + off));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+            v[0] = __ldcs(x + off);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            if (norm_means) v[k] = __fsub_rn(v[k], mean[k]);
+            if (norm_vars) v[k] = __fdiv_rn(v[k], sd[k]);
+        }
+        if constexpr (VEC == 4) __stcs(reinterpret_cast<float4*>(out + off), make_float4(v[0], v[1], v[2], v[3]));
+        else __stcs(out + off, v[0]);
     }
 }
 
@@ -79,11 +138,22 @@ __global__ void __launch_bounds__(256) k_fill_rects(const int4* __restrict__ rec
 
 }  // namespace
 
-int launch_utterance_cmvn(int n_utts, const int32_t* fo, int n_cols, const float* x, float* out, bool norm_means,
-                          bool norm_vars, cudaStream_t stream) {
-    if (n_utts <= 0) return S2ST_OK;
+int launch_utterance_cmvn(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const float* x, float* out,
+                          bool norm_means, bool norm_vars, float* stats, cudaStream_t stream) {
+    if (n_utts <= 0 || n_rows <= 0) return S2ST_OK;
     dim3 grid((unsigned)n_utts, (unsigned)((n_cols + 127) / 128));
-    k_utterance_cmvn<<<grid, 128, 0, stream>>>(fo, n_cols, x, out, norm_means ? 1 : 0, norm_vars ? 1 : 0);
+    k_utterance_stats<<<grid, 128, 0, stream>>>(fo, n_cols, x, stats);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    const unsigned blocks = (unsigned)((n_rows + kApplyRows - 1) / kApplyRows);
+    const bool vec = n_cols % 4 == 0 && n_cols / 4 <= 256 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
+    if (vec) {
+        k_utterance_apply<4><<<blocks, 256, 0, stream>>>(fo, n_utts, n_rows, n_cols, x, stats, out, norm_means ? 1 : 0, norm_vars ? 1 : 0);
+    } else if (n_cols <= 256) {
+        k_utterance_apply<1><<<blocks, 256, 0, stream>>>(fo, n_utts, n_rows, n_cols, x, stats, out, norm_means ? 1 : 0, norm_vars ? 1 : 0);
+    } else {
+        set_error("s2st_utterance_cmvn supports at most 256 feature columns (got %d)", n_cols);
+        return S2ST_EINVAL;
+    }
     S2ST_CUDA_CHECK(cudaGetLastError());
     return S2ST_OK;
 }

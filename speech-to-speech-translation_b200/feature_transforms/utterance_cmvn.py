@@ -23,9 +23,11 @@ def utterance_cmvn_cuda(x: torch.Tensor, frames: Sequence[int], norm_means: bool
     assert sum(frames) == x.shape[0], "frames must add up to the number of rows"
     out = torch.empty_like(x) if out is None else out
     fo = upload_small(np.concatenate([[0], np.cumsum(frames)]).astype(np.int32), x.device)
+    stats = torch.empty(len(frames), 2, x.shape[1], dtype=torch.float32, device=x.device)  # (mean, std) per utterance
     with torch.cuda.device(x.device):
-        rc = _lib.load().s2st_utterance_cmvn(len(frames), _lib.ptr(fo), x.shape[1], _lib.ptr(x), int(bool(norm_means)),
-                                             int(bool(norm_vars)), _lib.ptr(out), _lib.stream_ptr(x.device))
+        rc = _lib.load().s2st_utterance_cmvn(len(frames), x.shape[0], _lib.ptr(fo), x.shape[1], _lib.ptr(x),
+                                             int(bool(norm_means)), int(bool(norm_vars)), _lib.ptr(out), _lib.ptr(stats),
+                                             _lib.stream_ptr(x.device))
     _lib.check(rc, "s2st_utterance_cmvn")
     return out
 
