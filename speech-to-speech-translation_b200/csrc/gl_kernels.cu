@@ -199,17 +199,20 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                                 const int k = 32 * r + lane;
                                 if (k < kb) {
                                     const float m = __ldg(magrow + (p.mag_perm ? __ldg(p.mag_perm + k) : k));
-                                    float sn, cs, rs, rc;
+                                    // the caller's phase refers to the un-rotated frame; frames are processed
+                                    // rotated by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048).  The
+                                    // rotation angle (an exact multiple of pi / 1024, reduced to [-pi, pi)) is added
+                                    // to the phase before the one sincos -- half the transcendental work of
+                                    // rotating the phasor afterwards; the sum rounds to within 2.4e-7 rad
+                                    const float rot_pi = (float)(((k * p.rot + 1024) & 2047) - 1024) * (1.0f / 1024.0f);
+                                    float sn, cs;
                                     if (p.phase) {
-                                        sincosf(__ldg(phrow + k), &sn, &cs);
+                                        sincosf(fmaf(rot_pi, CUDART_PI_F, __ldg(phrow + k)), &sn, &cs);
                                     } else {  // phi = 2 pi u - pi, u ~ U[0, 1): same law as vocoder.py:103
                                         const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + k;
-                                        sincospif(2.0f * uniform01(p.phase_seed, e) - 1.0f, &sn, &cs);
+                                        sincospif(2.0f * uniform01(p.phase_seed, e) - 1.0f + rot_pi, &sn, &cs);
                                     }
-                                    // the caller's phase refers to the un-rotated frame; frames are processed
-                                    // rotated by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048)
-                                    sincospif((float)((k * p.rot) & 2047) * (1.0f / 1024.0f), &rs, &rc);
-                                    a[r] = make_float2(m * fmaf(cs, rc, -sn * rs), m * fmaf(cs, rs, sn * rc));
+                                    a[r] = make_float2(m * cs, m * sn);
                                 } else {
                                     a[r] = make_float2(0.0f, 0.0f);
                                 }

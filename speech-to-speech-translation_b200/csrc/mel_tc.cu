@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNChunk >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
     const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (kTcNChunk / 8) * 128, sbo = 128;
     uint32_t phase = 0;
+    const bool vec_store = (p.out_stride & 3) == 0 && p.n_out >= kTcChunks * kTcNChunk && (reinterpret_cast<uintptr_t>(p.mag) & 15) == 0;
 
     for (int chunk = 0; chunk < kTcChunks; ++chunk) {
         // B chunk (head and tail are adjacent in global): straight 16-byte copies
@@ -164,10 +165,21 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
                 : "r"(lane_addr + c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (tid < rows) {
+                if (vec_store) {
+                    // the thread's 16 consecutive bins as four 16-byte stores (rows are 16-byte aligned and at least
+                    // 704 wide): scalar stores from 32 different rows per instruction made this epilogue the
+                    // kernel's bottleneck
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = chunk * kTcNChunk + c0 + j;
-                    if (col < p.n_out) orow[c0 + j] = fmaxf(__uint_as_float(r[j]), 0.0f);
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
+                            make_float4(fmaxf(__uint_as_float(r[4 * q]), 0.0f), fmaxf(__uint_as_float(r[4 * q + 1]), 0.0f),
+                                        fmaxf(__uint_as_float(r[4 * q + 2]), 0.0f), fmaxf(__uint_as_float(r[4 * q + 3]), 0.0f));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = chunk * kTcNChunk + c0 + j;
+                        if (col < p.n_out) orow[c0 + j] = fmaxf(__uint_as_float(r[j]), 0.0f);
+                    }
                 }
             }
         }
