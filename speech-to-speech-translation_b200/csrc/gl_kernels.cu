@@ -810,7 +810,7 @@ size_t gl_pass_r64_smem() {
 // S2ST_GL_KERNEL=r64 selects the real-FFT-64 formulation (frame_r64.cuh) for the vocoder's standard case.  It is
 // parity-tested but NOT the default: it moves 32 % fewer shared-memory wavefronts per frame-iteration, yet the column
 // of bins that are multiples of 32 costs ~190 extra instructions, so it ends up level with the packed-complex kernel
-// (0.237 vs 0.240 ms per pass on the config-2 batch) and its first pass is slower.
+// (0.238 vs 0.236 ms per pass on the config-2 batch) and its first pass is slower.
 bool use_r64_kernel() {
     const char* e = getenv("S2ST_GL_KERNEL");
     return e && e[0] == 'r';
