@@ -138,6 +138,10 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
     for (int i = tid; i < hop; i += kGlThreads) s_inv_wss[i] = p.inv_wss[i];
     for (int i = lane; i < ring_floats; i += 32) ring[i] = 0.0f;
     __syncthreads();  // the only block-wide barrier: constant tables are in place
+    // Programmatic dependent launch: the pass is launched while the previous pass is still draining, so everything
+    // above (CTA start-up, 21 KB of constant tables, ring clearing) overlaps its tail; from here on the previous
+    // kernel's output is read.  (A no-op when the kernel is launched the ordinary way.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int n_strips = *p.n_tiles;
     const int kb = PRUNED ? min(p.kb, 32 * kPrunedRows) : p.kb;
@@ -848,6 +852,12 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
 
 // cudaFuncSetAttribute is a driver call per launch otherwise (65 per synthesis step): do it once per kernel, device
 // and size.  Not thread-safe by design (the worst case is a redundant call).
+// S2ST_GL_PDL=0 launches the passes without programmatic dependent launch (A/B runs).
+bool use_pdl() {
+    const char* e = getenv("S2ST_GL_PDL");
+    return !(e && e[0] == '0');
+}
+
 template <auto Kernel>
 int allow_dynamic_smem(size_t smem, int device) {
     static size_t granted[64] = {};  // one table per kernel (the kernel is a template argument)
@@ -861,8 +871,17 @@ int allow_dynamic_smem(size_t smem, int device) {
 template <int NZ, bool FIRST, bool PRUNED, bool STD = false>
 int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream) {
     if (int rc = allow_dynamic_smem<k_gl_pass<NZ, FIRST, PRUNED, STD>>(smem, p.device)) return rc;
-    k_gl_pass<NZ, FIRST, PRUNED, STD><<<grid, kGlThreads, smem, stream>>>(p);
-    S2ST_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGlThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    S2ST_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gl_pass<NZ, FIRST, PRUNED, STD>, p));
     return S2ST_OK;
 }
 
