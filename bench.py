@@ -299,7 +299,11 @@ def run_ours(args):
         per_step.append(plan.pass_times_ms())
     plan.set_pass_timing(False)
     last_pass_ms = np.mean(np.stack(per_step), axis=0)
-    iter_ms = float(np.mean(last_pass_ms[1:])) if len(last_pass_ms) > 1 else float("nan")
+    # one launch per iteration: [initial inverse, iteration 1, ..., iteration n]; persistent mode (all iterations in one
+    # launch, the default when every strip gets a resident warp): [initial inverse, the persistent launch]
+    persistent = len(last_pass_ms) == 2 and N_ITER > 1
+    iters_per_launch = N_ITER if persistent else 1
+    iter_ms = float(np.mean(last_pass_ms[1:])) if len(last_pass_ms) > 1 else float("nan")  # per LAUNCH
 
     # ---- end to end through the public API, host buffers in and out (e2e) -------------------------
     # Every step: H2D of that step's log-mel from pinned memory, synthesis, D2H of the waveforms.  The
@@ -348,7 +352,7 @@ def run_ours(args):
         return
 
     hbm_peak, peak_src = peaks()
-    algo_bytes_iter = ALGO_BYTES_PER_FRAME_ITER * total
+    algo_bytes_iter = ALGO_BYTES_PER_FRAME_ITER * total * iters_per_launch  # per launch
     achieved = algo_bytes_iter / (iter_ms * 1e-3) / 1e9
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------------
     from oracle import griffin_lim as ogl
@@ -377,10 +381,14 @@ def run_ours(args):
                 "with_host_drawn_phase": {"value": world * audio_s / (e2e_host_ms * 1e-3), "ms_per_step": e2e_host_ms,
                                           "h2d_bytes_per_step": int(logmel_h.numel() * 4 + phase_h.numel() * 4)}},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_gl_pass<19,false,true,true> (fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
+        "roofline": {"bound": "hbm", "kernel": ("k_gl_pass<19,false,true,true,PERSIST> (all %d iterations in one cooperative launch: " % N_ITER
+                                                 if persistent else "k_gl_pass<19,false,true,true> (") +
+                                                "fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": measured_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
-                     "launch_ms": iter_ms, "launches_per_step": N_ITER,
+                     # ncu capture of ONE iteration (profiles/r01_glpass_current_ncu_summary.txt) x iterations per launch
+                     "traffic": (measured_traffic_bytes() or 0) * iters_per_launch or None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
+                     "launch_ms": iter_ms, "launches_per_step": N_ITER // iters_per_launch,
+                     "iterations_per_launch": iters_per_launch, "ms_per_iteration": iter_ms / iters_per_launch,
                      "share_of_step": float(np.sum(last_pass_ms[1:]) / ms_step) if len(last_pass_ms) > 1 else None,
                      "first_pass_ms": float(last_pass_ms[0])},
         "cpu_baseline": None if world > 1 else {

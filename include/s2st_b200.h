@@ -92,10 +92,13 @@ int s2st_plan_set_strip_frames(s2st_plan* plan, int frames);
 /* Profiling aid (not part of the reference's interface): when enabled, s2st_gl_synthesize / s2st_istft
  * record a CUDA event on the caller's stream before every Griffin-Lim pass and after the last one;
  * s2st_plan_get_pass_times waits for the last event and returns the device time of each pass of the
- * most recent call in milliseconds (pass 0 = initial inverse, passes 1..n_iter = fused iterations). */
+ * most recent call in milliseconds (pass 0 = initial inverse, passes 1..n_iter = fused iterations).  When the call ran
+ * its iterations as ONE persistent launch (standard geometry, host frame offsets given, every strip resident) two
+ * values come back: the initial inverse and the whole persistent launch. */
 int s2st_plan_set_pass_timing(s2st_plan* plan, int enabled);
 int s2st_plan_get_pass_times(s2st_plan* plan, float* ms_out_host, int capacity, int* n_passes_out);
-/* number of kernel launches one s2st_gl_synthesize call enqueues (for bench.py's gpu_launches) */
+/* number of kernel launches of the plan's most recent s2st_gl_synthesize call (for bench.py's gpu_launches); before
+ * the first call: what a call with one launch per iteration would enqueue */
 int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int* launches_out);
 
 /* ------------------------------------------------------------------------------------------ */

@@ -438,8 +438,10 @@ int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int
         set_error("bad argument");
         return S2ST_EINVAL;
     }
-    // build_tiles + [inverse_mel] + (n_iter + 1) passes (plus one cudaMemsetAsync, not a kernel of ours)
-    *launches_out = 1 + (from_logmel ? 1 : 0) + (n_iter + 1);
+    // What the last synthesis call of this plan launched, if there was one; else the per-pass count: build_tiles +
+    // [inverse_mel] + (n_iter + 1) passes (plus cudaMemsetAsync calls, not kernels of ours).  In persistent mode all
+    // iterations are one launch.
+    *launches_out = plan->last_launches > 0 ? plan->last_launches : 1 + (from_logmel ? 1 : 0) + (n_iter + 1);
     return S2ST_OK;
 }
 

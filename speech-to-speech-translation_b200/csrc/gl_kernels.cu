@@ -45,7 +45,7 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned lon
 }
 
 // Frame load, cold path: reflect padding (audio_utils.py:262-263) at utterance edges / unaligned data.
-template <int NZ>
+template <int NZ, bool L2ONLY = false>
 __device__ __forceinline__ void load_frame_edge(float2 (&a)[32], const float* __restrict__ y, int j, int L) {
 #pragma unroll 1
     for (int r = 0; r < NZ; ++r, j += 64) {
@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_frame_edge(float2 (&a)[32], const float* __
         j1 = j1 >= L ? 2 * (L - 1) - j1 : j1;
         j0 = min(max(j0, 0), L - 1);  // only reachable where the window is zero
         j1 = min(max(j1, 0), L - 1);
-        const float2 v = make_float2(y[j0], y[j1]);
+        const float2 v = L2ONLY ? make_float2(__ldcg(y + j0), __ldcg(y + j1)) : make_float2(y[j0], y[j1]);
         // registers cannot be indexed dynamically: scatter through a switch-free unrolled select
 #pragma unroll
         for (int q = 0; q < NZ; ++q)
@@ -115,8 +115,28 @@ constexpr int kStdHop = 300, kStdWs = 1200, kStdRot = 424;
 #endif
 constexpr bool kGlSharedFft = S2ST_GL_SHARED_FFT != 0;
 constexpr int kGlUnrollPass = kGlSharedFft ? 1 : 2;
-template <int NZ, bool FIRST, bool PRUNED, bool STD>
+// PERSIST: all iterations p.it_first..p.it_last in ONE launch, without a grid-wide barrier between them.  Every warp
+// owns one strip for the whole launch (the host guarantees n_strips <= resident warps and launches cooperatively).  A
+// strip may start iteration `it` as soon as it and its two neighbours in the utterance have finished iteration it - 1:
+// those are the only strips whose output (their hops and the shared seams) its frames read, and the only ones that add
+// into or clear the seams it touches.  Completion is published per strip (release store after a fence), waited for by
+// lane 0 (acquire load); waveform loads bypass L1 (ld.global.cg), because an address is rewritten every third iteration.
+// This removes the tail of every pass (strips shorter than S, warps finishing apart, launch ramp): while a short strip
+// waits for its neighbour, the other warps of its SM run faster.  Measured: not a win (see use_persistent()).
+__device__ __forceinline__ int ld_acquire(const int* ptr) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* ptr, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+
+constexpr unsigned kPersistSleepNs = 100;  // back-off of the neighbour wait (20 ns measured the same)
+
+template <int NZ, bool FIRST, bool PRUNED, bool STD, bool PERSIST = false>
 __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant__ GlParams p) {
+    static_assert(!PERSIST || (!FIRST && STD), "persistent mode is the standard-geometry iteration only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);            // 1024
     float2* s_vtab = s_tw + 1024;                                  // 1024
@@ -158,10 +178,21 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
         ud.n_frames = td.n_frames;
         const int T = ud.n_frames, L = (T - 1) * hop;
         const int j_base = td.f0 * hop + rot_half;  // output sample index of strip-relative sample 0
-        float* out = p.out + ud.wave_off;
-        float* znext = p.zero_next + ud.wave_off;
-        const float* y = p.in + ud.wave_off;
         const bool aligned = STD || (geom4 && ((ud.wave_off & 3) == 0));  // STD: wave_off is a multiple of hop
+#pragma unroll 1
+      for (int it = PERSIST ? p.it_first : 0; it <= (PERSIST ? p.it_last : 0); ++it) {
+        if constexpr (PERSIST) {
+            if (lane == 0) {
+                if (td.prev >= 0)
+                    while (ld_acquire(p.done + td.prev) < it - 1) __nanosleep(kPersistSleepNs);
+                if (td.next >= 0)
+                    while (ld_acquire(p.done + td.next) < it - 1) __nanosleep(kPersistSleepNs);
+            }
+            __syncwarp();
+        }
+        float* out = (PERSIST ? p.bufs[it % 3] : p.out) + ud.wave_off;
+        float* znext = (PERSIST ? p.bufs[(it + 1) % 3] : p.zero_next) + ud.wave_off;
+        const float* y = (PERSIST ? p.bufs[(it + 2) % 3] : p.in) + ud.wave_off;
         const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0) * p.mag_stride;
         const float* phrow = (FIRST && p.phase) ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
 
@@ -337,12 +368,12 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                     if (aligned && jf >= 0 && jf + 64 * NZ <= L) {
                         const float2* src = reinterpret_cast<const float2*>(y + jf) + lane;
 #pragma unroll
-                        for (int r = 0; r < NZ; ++r) a[brev5(r)] = src[32 * r];
+                        for (int r = 0; r < NZ; ++r) a[brev5(r)] = PERSIST ? __ldcg(src + 32 * r) : src[32 * r];
                         // the hop the frame after that adds is not in cache yet: ask L2 for it now (11 lines)
                         const int jp = jf + 64 * NZ - 16 + 32 * lane;
                         if (lane < 11 && jp < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + jp));
                     } else {
-                        load_frame_edge<NZ>(a, y, jf + 2 * lane, L);
+                        load_frame_edge<NZ, PERSIST>(a, y, jf + 2 * lane, L);
                     }
                 }
             }
@@ -406,6 +437,12 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
             emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
         }
         __syncwarp();
+        if constexpr (PERSIST) {
+            __threadfence();  // every lane's stores / reductions of this iteration, before the strip is published
+            __syncwarp();
+            if (lane == 0) st_release(p.done + strip, it);
+        }
+      }
     }
 }
 
@@ -620,7 +657,8 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass_r64(const __grid_cons
 constexpr int kMaxStrip = 64;
 __global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict__ fo, int n_utts, int hop, int S,
                                                        UttDesc* __restrict__ utts, TileDesc* __restrict__ tiles_tmp,
-                                                       TileDesc* __restrict__ tiles, int* __restrict__ n_tiles) {
+                                                       TileDesc* __restrict__ tiles, int* __restrict__ tile_pos,
+                                                       int* __restrict__ n_tiles) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     __shared__ int s_hist[kMaxStrip + 1], s_start[kMaxStrip + 1];
@@ -664,10 +702,10 @@ __global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict_
                 t.wave_off = d.wave_off;
                 t.frame_off = d.frame_off;
                 t.n_frames = T;
-                t.utt = u;
                 t.f0 = k * S;
                 t.nf = min(S, T - k * S);
-                t.pad = 0;
+                t.prev = k > 0 ? first + k - 1 : -1;   // listing indices; remapped below when the table is sorted
+                t.next = k + 1 < nt ? first + k + 1 : -1;
                 listing[first + k] = t;
             }
             if (sorted && nt > 0) {
@@ -692,7 +730,15 @@ __global__ void __launch_bounds__(1024) k_build_tiles(const int32_t* __restrict_
     __syncthreads();
     for (int i = tid; i < total; i += 1024) {
         const TileDesc t = tiles_tmp[i];
-        tiles[atomicAdd(&s_start[t.nf], 1)] = t;
+        const int np = atomicAdd(&s_start[t.nf], 1);
+        tile_pos[i] = np;
+        tiles[np] = t;
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += 1024) {
+        TileDesc* t = tiles + tile_pos[i];
+        if (t->prev >= 0) t->prev = tile_pos[t->prev];
+        if (t->next >= 0) t->next = tile_pos[t->next];
     }
 }
 
@@ -775,6 +821,8 @@ struct GlWorkspace {
     UttDesc* utts;
     TileDesc* tiles;
     TileDesc* tiles_tmp;
+    int* tile_pos;   // listing index -> position in the sorted table
+    int* done;       // persistent mode: last finished iteration per strip
     int* n_tiles;
     float* mag;
     float* buf[2];
@@ -799,6 +847,8 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
     w.utts = reinterpret_cast<UttDesc*>(take(sizeof(UttDesc) * (size_t)n_utts));
     w.tiles = reinterpret_cast<TileDesc*>(take(sizeof(TileDesc) * (size_t)w.max_tiles));
     w.tiles_tmp = reinterpret_cast<TileDesc*>(take(sizeof(TileDesc) * (size_t)w.max_tiles));
+    w.tile_pos = reinterpret_cast<int*>(take(sizeof(int) * (size_t)w.max_tiles));
+    w.done = reinterpret_cast<int*>(take(sizeof(int) * (size_t)w.max_tiles));
     w.n_tiles = reinterpret_cast<int*>(take(sizeof(int)));
     w.mag = reinterpret_cast<float*>(take(sizeof(float) * (size_t)total_frames * w.mag_stride));
     for (int i = 0; i < 2; ++i)
@@ -852,6 +902,15 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
 
 // cudaFuncSetAttribute is a driver call per launch otherwise (65 per synthesis step): do it once per kernel, device
 // and size.  Not thread-safe by design (the worst case is a redundant call).
+// S2ST_GL_PERSISTENT=1 runs all iterations in one cooperative launch (k_gl_pass PERSIST).  Bitwise identical results,
+// parity-tested, but measured 1.6 % SLOWER than one launch per iteration with programmatic dependent launch on the
+// config-2 batch (15.82 vs 15.57 ms per step): what the missing grid barrier saves (pass tails, launch ramp) is less
+// than what the per-strip waits, fences and L2-only waveform loads cost.  Hence opt-in.
+bool use_persistent() {
+    const char* e = getenv("S2ST_GL_PERSISTENT");
+    return e && e[0] == '1';
+}
+
 // S2ST_GL_PDL=0 launches the passes without programmatic dependent launch (A/B runs).
 bool use_pdl() {
     const char* e = getenv("S2ST_GL_PDL");
@@ -959,7 +1018,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     const int s_floor = plan->nphase > kMinStrip ? plan->nphase : kMinStrip;
     const int S = plan->strip_frames > 0 ? (plan->strip_frames < s_floor ? s_floor : plan->strip_frames)
                                          : choose_strip(plan, n_utts, total_frames, frame_offsets_host);
-    k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, S, w.utts, w.tiles_tmp, w.tiles, w.n_tiles);
+    k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, S, w.utts, w.tiles_tmp, w.tiles, w.tile_pos, w.n_tiles);
     S2ST_CUDA_CHECK(cudaGetLastError());
 
     GlParams p;
@@ -1014,10 +1073,54 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     ring[(n_iter + 2) % 3] = w.buf[1];
     // pass 0 accumulates its seams into ring[0]: clear it (later passes get theirs cleared by the pass before)
     S2ST_CUDA_CHECK(cudaMemsetAsync(ring[0], 0, sizeof(float) * (size_t)w.wave_samples, stream));
+    // Persistent mode (see k_gl_pass PERSIST): all iterations in one cooperative launch when every strip gets a
+    // resident warp of its own.  Needs the exact strip count, i.e. the host copy of the frame offsets.
+    const bool std_geom0 = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
+                           plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
+    bool persist = std_geom0 && !r64 && n_iter >= 1 && frame_offsets_host && use_persistent();
+    plan->last_launches = 1 + (logmel ? 1 : 0) + (n_iter + 1);  // build_tiles, [inverse_mel], the passes
+    if (persist) {
+        long long strips = 0;
+        for (int u = 0; u < n_utts; ++u) strips += (frame_offsets_host[u + 1] - frame_offsets_host[u] + S - 1) / S;
+        persist = strips <= (long long)grid * kGlWarps;
+    }
     for (int it = 0; it <= n_iter; ++it) {
         p.in = ring[(it + 2) % 3];
         p.out = ring[it % 3];
         p.zero_next = ring[(it + 1) % 3];
+        if (persist && it == 1) {
+            if (timed) {  // events: [0] before the initial inverse, [1] before / [2] after the persistent launch
+                if (!plan->timing_events[1]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[1]));
+                S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[1], stream));
+            }
+            for (int k = 0; k < 3; ++k) p.bufs[k] = ring[k];
+            p.done = w.done;
+            p.it_first = 1;
+            p.it_last = n_iter;
+            S2ST_CUDA_CHECK(cudaMemsetAsync(w.done, 0, sizeof(int) * (size_t)w.max_tiles, stream));
+            if (int rc2 = allow_dynamic_smem<k_gl_pass<19, false, true, true, true>>(smem, p.device)) return rc2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(kGlThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, k_gl_pass<19, false, true, true, true>, p) == cudaSuccess) {
+                plan->last_launches = 1 + (logmel ? 1 : 0) + 2;
+                if (timed) {
+                    if (!plan->timing_events[2]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[2]));
+                    S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[2], stream));
+                    plan->timing_recorded = 3;
+                }
+                return S2ST_OK;
+            }
+            (void)cudaGetLastError();  // not co-resident (another kernel holds SMs): run the passes one by one
+            persist = false;
+        }
         if (timed) {
             if (!plan->timing_events[it]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[it]));
             S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[it], stream));

@@ -41,6 +41,7 @@ struct s2st_plan {
     int mel_terms;
     // profiling aid (s2st_plan_set_pass_timing): CUDA events around every Griffin-Lim pass of the LAST call
     int strip_frames;             // 0 = choose per call (s2st_plan_set_strip_frames)
+    int last_launches;            // kernel launches of the last gl_run (0 before the first call)
     int timing_enabled;
     int timing_recorded;          // events recorded by the last gl_run (passes + 1), 0 if none
     cudaEvent_t timing_events[kMaxTimedPasses + 1];

@@ -228,6 +228,28 @@ def test_real_fft64_formulation_matches_golden_oracle_and_default_kernel(pkg, vo
     assert torch.isfinite(z).all()
 
 
+def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
+    """S2ST_GL_PERSISTENT=1: all iterations in one cooperative launch, strips synchronising with their neighbours only
+    (no grid-wide barrier).  Same arithmetic, commuting seam reductions -> the waveforms must be bitwise equal to the
+    default one-launch-per-iteration path, for ragged batches with single-strip, multi-strip and tail-strip utterances."""
+    plan = voc._plan(torch.device("cuda", 0))
+    frames = [5, 9, 31, 64, 65, 100, 257, 400] + [120] * 40
+    feats = [synth_logmel(T, 300 + i, "smooth" if i % 2 else "iid").cuda() for i, T in enumerate(frames)]
+    phases = [seeded_phase(400 + i, T) for i, T in enumerate(frames)]
+    for strip in (0, 7):
+        plan.set_strip_frames(strip)
+        try:
+            base = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
+            monkeypatch.setenv("S2ST_GL_PERSISTENT", "1")
+            pers = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
+            monkeypatch.delenv("S2ST_GL_PERSISTENT")
+            assert plan.gl_launch_count(12) == 4  # build_tiles, inverse_mel, initial inverse, the persistent launch
+        finally:
+            plan.set_strip_frames(0)
+        for a, b in zip(base, pers):
+            assert torch.equal(a, b)
+
+
 def test_config1_500_frames_64_iters(pkg, voc, basis):
     """BASELINE config 1: one 500-frame utterance, 64 iterations, seeded phase."""
     x = synth_logmel(500, 1234)
