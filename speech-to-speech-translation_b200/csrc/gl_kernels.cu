@@ -238,11 +238,13 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                                     // rotated by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048).  The
                                     // rotation angle (an exact multiple of pi / 1024, reduced to [-pi, pi)) is added
                                     // to the phase before the one sincos -- half the transcendental work of
-                                    // rotating the phasor afterwards; the sum rounds to within 2.4e-7 rad
+                                    // rotating the phasor afterwards
                                     const float rot_pi = (float)(((k * p.rot + 1024) & 2047) - 1024) * (1.0f / 1024.0f);
                                     float sn, cs;
                                     if (p.phase) {
-                                        sincosf(fmaf(rot_pi, CUDART_PI_F, __ldg(phrow + k)), &sn, &cs);
+                                        // in units of pi: sincospi reduces its argument exactly (no slow path), the
+                                        // product phase / pi rounds to within 1e-7 rad
+                                        sincospif(fmaf(__ldg(phrow + k), 0.31830988618379067154f, rot_pi), &sn, &cs);
                                     } else {  // phi = 2 pi u - pi, u ~ U[0, 1): same law as vocoder.py:103
                                         const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + k;
                                         sincospif(2.0f * uniform01(p.phase_seed, e) - 1.0f + rot_pi, &sn, &cs);
