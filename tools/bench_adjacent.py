@@ -34,8 +34,9 @@ out["utterance_cmvn"] = {"utterances": len(frames), "rows": sum(frames), "ms": m
 sa = pkg.feature_transforms.get_audio_feature_transform("specaugment").from_config_dict(
     {"freq_mask_N": 2, "freq_mask_F": 27, "time_mask_N": 2, "time_mask_T": 100, "time_mask_p": 1.0})
 np.random.seed(0)
+sa.apply_cuda(x, frames); torch.cuda.synchronize()  # first call: allocations, pinned staging
 t0 = time.perf_counter(); y = sa.apply_cuda(x, frames); torch.cuda.synchronize()
-out["specaugment_batch_2000_utts_ms_wall"] = 1e3 * (time.perf_counter() - t0)
+out["specaugment_batch_2000_utts_ms_wall"] = 1e3 * (time.perf_counter() - t0)  # host mask drawing + clone + mean + fill
 B, M, N = 64, 480, 470
 d = torch.rand(B, M, N, device=dev)
 ms = timeit(lambda: mcd.batch_dynamic_time_warping(d), n=5)
