@@ -1,9 +1,10 @@
 """CPU oracle for the waveform-synthesis / feature front-end hot path.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
-only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
-``--impl reference`` legs may import it, and only as the checker (or as the
-timed CPU baseline), never as a fallback for the CUDA path.
+only ``tests/`` (including the measurement scripts under ``tests/measure/`` that
+time the reference's formulations), ``__graft_entry__.smoke()`` and ``bench.py``'s
+CPU-baseline / ``--impl reference`` legs may import it, and only as the checker (or
+as the timed baseline), never as a fallback for the CUDA path.
 
 It is a numpy restatement (FFT based, float64 inside a transform, float32 at
 every point where the reference stores a float32 tensor) of the reference's
@@ -15,8 +16,11 @@ algorithms:
 * ``oracle.griffin_lim``  -- vocoder.py:24-144 + audio_utils.py:218-271.
 * ``oracle.frontend``     -- audio_utils.py:136-149,274-285,
                              examples/speech_synthesis/data_utils.py:46-76,190-220,
-                             feature_transforms/global_cmvn.py:26-29,
-                             speech_generator_for_s2st.py:21-29.
+                             feature_transforms/global_cmvn.py:26-29, utterance_cmvn.py:29-40,
+                             specaugment.py:79-131, speech_generator_for_s2st.py:21-29.
+* ``oracle.conv_formulation`` -- the Griffin-Lim path once more, in the reference's own
+                             dense-convolution formulation (torch; bit-identical to it).
+* ``oracle.dtw``          -- examples/s2s_trans/tasks/s2s_translation.py:414-475 (MCD metric).
 
 Parity pinning: the reference holds no golden vectors or tests for this path
 (SURVEY.md section 4), so the oracle is pinned against outputs of the reference

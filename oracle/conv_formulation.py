@@ -10,7 +10,7 @@ Why it exists next to the numpy FFT oracle (griffin_lim.py):
   runs (8.4 MFLOP per frame and transform as a dense convolution, plus a per-call Python loop for the
   window-sum-square, vocoder.py:71-82, kept here on purpose because it is ~20 % of the reference's time), so timing
   the FFT oracle would understate the reference arm's cost;
-* ``tools/bench_conv_gpu.py`` runs the same code on the GPU (cuDNN convolutions): the "existing kernels" bar of
+* ``tests/measure/conv_formulation_on_gpu.py`` runs the same code on the GPU (cuDNN convolutions): the "existing kernels" bar of
   SURVEY section 8d.
 """
 import numpy as np

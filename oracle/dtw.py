@@ -50,7 +50,7 @@ def compute_rms_dist(x1, x2):
 def batch_dynamic_time_warping_torch(distance, shapes=None):
     """The reference's FORMULATION of the same recurrence (s2s_translation.py:414-464) in torch: one round of gathers /
     min / scatter per anti-diagonal and a host back trace with one .item() per step -- kept for timing the reference's
-    approach on the GPU next to the fused kernel (tools/bench_adjacent.py); results equal the loops above."""
+    approach on the GPU next to the fused kernel (tests/measure/adjacent_rows.py); results equal the loops above."""
     import torch
     bsz, m, n = distance.shape
     cum = torch.zeros_like(distance)

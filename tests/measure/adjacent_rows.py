@@ -1,9 +1,9 @@
 """Measurements for the rows next to the hot path: utterance CMVN, SpecAugment fill, batched DTW.
 Algorithmic bytes: utterance CMVN 8 B per element (read + write; the kernel reads twice, the second time from L2),
-DTW 16 B per cell (distance in; cumulative distance, back pointer, path out).   python tools/bench_adjacent.py"""
+DTW 16 B per cell (distance in; cumulative distance, back pointer, path out).   python tests/measure/adjacent_rows.py"""
 import importlib, json, os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from oracle import dtw as odtw

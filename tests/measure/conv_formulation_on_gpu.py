@@ -1,10 +1,10 @@
 """The "existing kernels" bar of SURVEY section 8d: the reference's dense-convolution Griffin-Lim (oracle/conv_formulation.py,
 bit-identical to the reference on CPU) run on the GPU through cuDNN, one utterance per call like the reference's
 generator loop, with TF32 off (parity grade) and on (what a user gets by default), next to this library on the same
-inputs.   python tools/bench_conv_gpu.py"""
+inputs.   python tests/measure/conv_formulation_on_gpu.py"""
 import importlib, json, os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from oracle import conv_formulation as ocf

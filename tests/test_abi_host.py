@@ -149,6 +149,16 @@ def test_short_utterance_raises_like_reference(pkg):
     voc_mod._check_length(1, 300, 2048, 0)  # inverse only: any T
 
 
+def test_only_tests_smoke_and_bench_import_the_oracle():
+    """oracle/ is test infrastructure: besides tests/ only bench.py (CPU baseline legs) and __graft_entry__.smoke()
+    may import it -- not the package (next test) and not the measurement tools under tools/."""
+    import re
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
 def test_product_never_imports_oracle():
     pkg_dir = os.path.join(ROOT, "speech-to-speech-translation_b200")
     for dirpath, _, files in os.walk(pkg_dir):
