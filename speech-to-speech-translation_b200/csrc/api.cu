@@ -328,9 +328,10 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         }
         if (ok && rc == S2ST_OK) {
             // unused gather entries point at a float the kernel keeps at zero (index 2 * 32 * 17)
+            // two planes of int4 per mel bin: entry q of bin m at ((q / 4) * n_mels + m) * 4 + q % 4
             std::vector<int> gather((size_t)n_mels * max_terms, 2 * lanes * max_slots);
             for (int m = 0; m < n_mels; ++m)
-                for (size_t q = 0; q < terms[m].size(); ++q) gather[(size_t)m * max_terms + q] = terms[m][q];
+                for (size_t q = 0; q < terms[m].size(); ++q) gather[((q / 4) * n_mels + m) * 4 + q % 4] = terms[m][q];
             p->mel_terms = n_terms;
             rc = upload(&p->mel_col, col);
             if (rc == S2ST_OK) rc = upload(&p->mel_gather, gather);
@@ -660,13 +661,10 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
             // of running sums per run of its bins that feed the same mel bin b and stores them to the run's slot of a
             // per-half-warp slab after every step; entry = (w into b, w into b + 1, 1 if the run continues else 0, slot).
             // mel_gather[m * 8 + q] lists the slab floats that add up to mel bin m.
-            // Slots are numbered across the whole half-warp (a sub-lane at low frequencies changes mel bin at almost
-            // every step, one at high frequencies once or twice: ~100 runs in total), so the slab is tiny.
-            constexpr int max_runs = 160, max_terms = 8;  // 2 * max_runs + 1 floats fit behind the power spectrum
+            constexpr int max_rows = 13, max_terms = 8;  // kFbSlabRows in frontend_kernels.cu
             std::vector<std::vector<int>> terms(n_bins);
-            int slot = -1;
             for (int sl = 0; sl < 16 && ok; ++sl) {
-                int cur = -1;
+                int cur = -1, run = -1, slot = 0;
                 for (int j = 0; j < kpl && ok; ++j) {
                     float4& e = col[j * 16 + sl];
                     const bool empty = e.x == 0.0f && e.y == 0.0f;
@@ -681,12 +679,14 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
                     }
                     const bool keep = b == cur;
                     if (!keep) {
-                        ++slot;
+                        ++run;
                         cur = b;
-                        if (slot >= max_runs) {
+                        if (run >= max_rows) {
                             ok = false;
                             break;
                         }
+                        // slab[run][sub-lane]: at every step the 16 sub-lanes store to 16 different bank pairs
+                        slot = run * 16 + sl;
                         terms[b].push_back(slot * 2);
                         if (b + 1 < n_bins) terms[b + 1].push_back(slot * 2 + 1);
                     }
@@ -695,7 +695,7 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
                     e = make_float4(w0, w1, keep ? 1.0f : 0.0f, sf);
                 }
             }
-            const int zero_float = 2 * (slot + 1);
+            const int zero_float = 2 * 16 * max_rows;
             int n_terms = 1;
             for (int m = 0; m < n_bins && ok; ++m) {
                 if ((int)terms[m].size() > max_terms) ok = false;
@@ -703,8 +703,8 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
             }
             if (ok) {
                 std::vector<int> gather((size_t)n_bins * max_terms, zero_float);  // unused entries -> a float kept at zero
-                for (int m = 0; m < n_bins; ++m)
-                    for (size_t q = 0; q < terms[m].size(); ++q) gather[(size_t)m * max_terms + q] = terms[m][q];
+                for (int m = 0; m < n_bins; ++m)  // two planes of int4 per mel bin, as in the log-mel plan
+                    for (size_t q = 0; q < terms[m].size(); ++q) gather[((q / 4) * n_bins + m) * 4 + q % 4] = terms[m][q];
                 p->mel_terms = n_terms;
                 p->mel_zero = zero_float;
                 if (rc == S2ST_OK) rc = upload(&p->mel_gather, gather);

@@ -23,12 +23,14 @@ namespace s2st {
 namespace {
 
 // Sum of the slab floats a mel bin's gather list names (8 ints per bin, unused entries point at a float kept at
-// zero).  Fixed trip count (4 or 8, warp-uniform), indices fetched with 16-byte loads: no loop-carried index loads.
-__device__ __forceinline__ float gather_sum(const float* __restrict__ slab, const int* __restrict__ list, int terms) {
-    const int4 g = *reinterpret_cast<const int4*>(list);
+// zero).  Fixed trip count (4 or 8, warp-uniform).  The table is stored as two planes of int4 ([2][n_bins]): lanes
+// with consecutive bins fetch consecutive 16-byte entries (the [n_bins][8] layout cost 4 extra wavefronts per load).
+__device__ __forceinline__ float gather_sum(const float* __restrict__ slab, const int4* __restrict__ list4, int m,
+                                            int n_bins, int terms) {
+    const int4 g = list4[m];
     float acc = ((slab[g.x] + slab[g.y]) + slab[g.z]) + slab[g.w];
     if (terms > 4) {
-        const int4 h = *reinterpret_cast<const int4*>(list + 4);
+        const int4 h = list4[n_bins + m];
         acc = (((acc + slab[h.x]) + slab[h.y]) + slab[h.z]) + slab[h.w];
     }
     return acc;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
             }
             __syncwarp();
             for (int m = lane; m < p.n_mels; m += 32) {
-                const float acc = gather_sum(slab, s_gather + 8 * m, p.mel_terms);
+                const float acc = gather_sum(slab, reinterpret_cast<const int4*>(s_gather), m, p.n_mels, p.mel_terms);
                 float v = logf(fmaxf(acc, p.eps));
                 if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
                 p.logmel_out[f * p.n_mels + m] = v;
@@ -409,7 +411,12 @@ constexpr int kFbWarps = 8;
 constexpr int kFbChunk = 16;
 constexpr int kFbRows = 13;                 // rows of 16 elements that can hold window samples (13 * 16 >= 200)
 constexpr int kFbScratchBytes = 2048;       // per half-warp: 16 x 16 complex
-constexpr int kFbPwrFloats = 16 * 17;          // MODE 0: power spectrum staging; the mel slab (<= 2 * 160 + 1 floats) follows it
+constexpr int kFbPwrFloats = 16 * 17;          // MODE 0: power spectrum staging; the mel slab follows it
+constexpr int kFbSlabRows = 13;                // MODE 0: most runs (mel bin changes) one sub-lane goes through; slab = [rows][16] (lo, hi)
+// MODE 0 bytes per half-warp: FFT scratch (2048) overlaid by power spectrum + slab (+ the always-zero float), rounded so
+// that the regions of a warp's two half-warps start 16 banks apart (their 16-lane accesses then never share a bank)
+constexpr int kFbRegion0Floats = 720;
+static_assert(kFbRegion0Floats >= kFbPwrFloats + 2 * 16 * kFbSlabRows + 1 && kFbRegion0Floats * 4 >= 2048 && kFbRegion0Floats % 32 == 16, "region layout");
 
 struct FbankFastParams {
     int win, shift, n_bins, n_utts, mel_nnz;
@@ -476,7 +483,8 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
     }
     __syncthreads();
     const int acc_floats = ((MODE + 1) * (p.n_bins + 1) + 3) & ~3;
-    char* scratch = s_scr + (size_t)(warp * 2 + grp) * (kFbScratchBytes + 4 * acc_floats);
+    const size_t region = MODE == 0 ? (size_t)4 * kFbRegion0Floats : (size_t)(kFbScratchBytes + 4 * acc_floats);
+    char* scratch = s_scr + (size_t)(warp * 2 + grp) * region;
     float* pwr = reinterpret_cast<float*>(scratch);
     float* macc = reinterpret_cast<float*>(scratch + kFbScratchBytes);
     const int prev_lane = (lane & 16) | ((sub + 15) & 15);
@@ -675,7 +683,7 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
                 if (m < p.n_bins) {
                     float e0;
                     if constexpr (MODE == 0) {
-                        e0 = gather_sum(pwr + kFbPwrFloats, s_gather + 8 * m, p.mel_terms);
+                        e0 = gather_sum(pwr + kFbPwrFloats, reinterpret_cast<const int4*>(s_gather), m, p.n_bins, p.mel_terms);
                     } else {
                         e0 = macc[m];
                     }
@@ -877,8 +885,8 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
         const size_t acc_floats = (size_t)(((plan->fast_mode + 1) * (plan->n_bins + 1) + 3) & ~3);
         const size_t tab = plan->fast_mode == 0 ? sizeof(float4) * 256 + sizeof(int) * (size_t)((8 * plan->n_bins + 3) & ~3)
                                                 : sizeof(int2) * ((plan->mel_nnz + 1) & ~1) + sizeof(int) * ((plan->n_bins + 1 + 3) & ~3);
-        const size_t fsmem = sizeof(float2) * 512 + sizeof(float) * kFbRows * 32 + tab +
-                             (size_t)kFbWarps * 2 * (kFbScratchBytes + 4 * acc_floats);
+        const size_t region = plan->fast_mode == 0 ? (size_t)4 * kFbRegion0Floats : (size_t)(kFbScratchBytes + 4 * acc_floats);
+        const size_t fsmem = sizeof(float2) * 512 + sizeof(float) * kFbRows * 32 + tab + (size_t)kFbWarps * 2 * region;
         const long long pair_chunks = ((total_frames + kFbChunk - 1) / kFbChunk + 1) / 2;
         const int fgrid = (int)min((long long)plan->num_sms * (plan->fast_mode == 0 ? kFbBlocks0 : 3), (pair_chunks + kFbWarps - 1) / kFbWarps);
         if (plan->fast_mode == 0) {
