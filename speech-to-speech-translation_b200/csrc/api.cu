@@ -307,8 +307,8 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
                         ok = false;
                         break;
                     }
-                    terms[b].push_back((l * max_slots + slot) * 2);
-                    if (b + 1 < n_mels) terms[b + 1].push_back((l * max_slots + slot) * 2 + 1);
+                    terms[b].push_back((slot * lanes + l) * 2);  // slab[slot][lane]
+                    if (b + 1 < n_mels) terms[b + 1].push_back((slot * lanes + l) * 2 + 1);
                 }
                 float w0 = 0.0f, w1 = 0.0f;
                 if (count) {
@@ -317,7 +317,8 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
                     if (count == 2) w1 = mel_host[(size_t)last * kBins + k];
                 }
                 float sf;
-                std::memcpy(&sf, &slot, sizeof(float));
+                const int slot_index = slot * lanes;  // float2 index of slab[slot][0]; the kernel adds the lane
+                std::memcpy(&sf, &slot_index, sizeof(float));
                 col[j * lanes + l] = make_float4(w0, w1, keep ? 1.0f : 0.0f, sf);
             }
         }

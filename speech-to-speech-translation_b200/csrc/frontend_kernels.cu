@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
 // log(max(., eps)) -> optional CMVN -> one 320-byte row.
 constexpr int kLmChunk = 8;
 constexpr int kLmCols = 32 * kPrunedRows;      // 704 spectrum bins
-constexpr int kLmSlots = 17;                   // partial-sum slots per lane (pitch of the slab: conflict-free 8-byte stores)
+constexpr int kLmSlots = 17;                   // partial-sum slots per lane; slab[slot][lane] (lo, hi): a step's 32 stores hit 32 different bank pairs whatever the slots
 constexpr int kLmSlabFloats = 2 * 32 * kLmSlots + 4;  // + the always-zero float unused gather entries point at
 static_assert(kLmCols + kLmSlabFloats <= kScratchFloats, "spectrum + slab live in the warp scratch");
 template <int NZ>
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
                 // to the run's slot after every step (the last write of a run is its total): no branches, no atomics
                 float2 lh = make_float2(0.0f, 0.0f);  // (lo, hi) as one packed pair: 2 instructions per step
                 const float* sp = scratch + kPrunedRows * lane;
-                float2* my = reinterpret_cast<float2*>(slab) + kLmSlots * lane;
+                float2* my = reinterpret_cast<float2*>(slab) + lane;  // slab[slot][lane]: the table holds slot * 32
 #pragma unroll
                 for (int j = 0; j < kPrunedRows; ++j) {
                     const float4 c = s_col[j * 32 + lane];
