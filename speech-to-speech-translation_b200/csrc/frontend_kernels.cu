@@ -156,7 +156,7 @@ constexpr int kLmChunk = 8;
 constexpr int kLmCols = 32 * kPrunedRows;      // 704 spectrum bins
 constexpr int kLmSlots = 17;                   // partial-sum slots per lane; slab[slot][lane] (lo, hi): a step's 32 stores hit 32 different bank pairs whatever the slots
 constexpr int kLmSlabFloats = 2 * 32 * kLmSlots + 4;  // + the always-zero float unused gather entries point at
-static_assert(kLmCols + kLmSlabFloats <= kScratchFloats, "spectrum + slab live in the warp scratch");
+static_assert(kLmCols + 4 + kLmSlabFloats <= kScratchFloats, "spectrum + slab live in the warp scratch");
 template <int NZ>
 __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ StftParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
     for (int i = tid; i < 8 * p.n_mels; i += blockDim.x) s_gather[i] = p.mel_gather[i];
     for (int i = tid; i < 64 * NZ; i += blockDim.x) s_win[i] = p.win_a[i];
     float* scratch = s_warp + warp * kScratchFloats;
-    float* slab = scratch + kLmCols;  // [32][17] (lo, hi) pairs, then the zero float unused gather entries read
+    float* slab = scratch + kLmCols + 4;  // [17][32] (lo, hi) pairs, then the zero float unused gather entries read
     __syncthreads();
     const long long n_chunks = (p.total_frames + kLmChunk - 1) / kLmChunk;
     for (long long chunk = (long long)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (long long)gridDim.x * 8) {
@@ -242,14 +242,16 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
             for (int r = 0; r < kPrunedRows; ++r) {
                 float mag;  // |2 X|: MUFU.SQRT (2 ulp) instead of the IEEE sequence; the features are compared at 1e-5
                 asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(a[r].x, a[r].x, a[r].y * a[r].y)));
-                scratch[32 * r + lane] = 0.5f * mag;
+                scratch[32 * r + lane + (r >= 11 ? 1 : 0)] = 0.5f * mag;  // one float of padding after bin 351: see sp below
             }
             __syncwarp();
             {
                 // column-wise mel: running (lo, hi) partial sums per run of bins that feed the same mel bin, written
                 // to the run's slot after every step (the last write of a run is its total): no branches, no atomics
                 float2 lh = make_float2(0.0f, 0.0f);  // (lo, hi) as one packed pair: 2 instructions per step
-                const float* sp = scratch + kPrunedRows * lane;
+                // lane l owns bins 22 l .. 22 l + 21; lanes l and l + 16 would start 352 floats = 0 banks apart, the
+                // padding float after bin 351 moves the upper half-warp by one bank: conflict-free reads
+                const float* sp = scratch + kPrunedRows * lane + (lane >> 4);
                 float2* my = reinterpret_cast<float2*>(slab) + lane;  // slab[slot][lane]: the table holds slot * 32
 #pragma unroll
                 for (int j = 0; j < kPrunedRows; ++j) {
