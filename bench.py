@@ -1,28 +1,33 @@
 #!/usr/bin/env python
 """Headline benchmark: Griffin-Lim audio-seconds per second (64 iterations, 24 kHz) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|gl|gl_sharded|frontend]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch: BASELINE.json config 2, a Fisher-test-shaped
-ragged batch of 256 synthetic log-mel utterances (T ~ U{56..400}, seed 0, length-sorted) taken
-through inverse-mel, the initial inverse and 64 fused STFT/iSTFT Griffin-Lim iterations.  With N > 1
-every rank runs its own batch of that shape (weak scaling, no collective on the data path).
+Workloads (BASELINE.json `configs`):
 
-Prints ONE JSON line (rank 0).  ``value`` is device-timed with inputs resident in HBM; ``e2e`` goes
-through the public API from pinned host buffers (H2D of log-mel + initial phase, D2H of waveforms
-inside the timed region); ``roofline`` is the fused iteration kernel against the measured HBM peak;
-``cpu_baseline`` is the numpy oracle timed on this box's host cores on a bounded sample.
-``--impl reference`` times that CPU port with all host cores instead (the reference is Python/PyTorch
-CPU code that cannot travel to the GPU box).
+* ``gl`` (default at N = 1) -- config 2: a Fisher-test-shaped ragged batch of 256 synthetic log-mel utterances
+  (T ~ U{56..400}, seed 0, length-sorted) through inverse-mel, the initial inverse and 64 fused STFT/iSTFT
+  Griffin-Lim iterations.  One step = one pass over that batch.  Extra keys time config 1 (one 500-frame utterance
+  through ``GriffinLimVocoder.forward``) and config 5 (a 60 s utterance, 64 / 256 iterations).
+* ``gl_sharded`` (default at N > 1) -- config 4: ONE global list of 10 000 utterances (same length law, seed 0)
+  sharded by utterance over the ranks (longest-processing-time-first on frames x iterations), cut into length
+  buckets per rank, synthesised bucket by bucket, and gathered to rank 0 over NCCL at the end (strong scaling; the
+  gather is the only collective).  One step = the whole list once.
+* ``frontend`` -- config 3: fbank80 + fused global CMVN over 10 000 synthetic utterances of 8-20 s at 16 kHz
+  (logmelspec80 at 24 kHz and fbank80 at 8 kHz on a share of it beside it).
+
+Prints ONE JSON line (rank 0).  ``value`` is device-timed with inputs resident in HBM; ``e2e`` goes through the
+public API from pinned host buffers (H2D of the inputs incl. the seeded initial phase, D2H of the results inside the
+timed region); ``roofline`` is the dominant kernel against the measured HBM peak; ``cpu_baseline`` is the CPU port
+timed on this box's host cores on a bounded sample.  ``--impl reference`` times the reference's own CPU formulation
+with all host cores instead (the reference is Python/PyTorch CPU code that cannot travel to the GPU box).
 """
 import argparse
 import importlib
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -32,16 +37,34 @@ sys.path.insert(0, ROOT)
 PKG = "speech-to-speech-translation_b200"
 
 SR, N_FFT, WIN, HOP, N_MELS, F_MIN, F_MAX, N_ITER = 24000, 2048, 1200, 300, 80, 20.0, 8000.0, 64
+N_BINS = N_FFT // 2 + 1
 N_UTTS = 256
+N_UTTS_SHARDED = 10000
+BUCKET_FRAMES = 300000                  # frames per synthesis call of the sharded workload
 ALGO_BYTES_PER_FRAME_ITER = 6500        # 1200 B wave in + 4100 B magnitude + 1200 B wave out
 ALGO_BYTES_PER_FRAME_ONCE = 13820       # inverse-mel + initial inverse
+FBANK_BYTES_PER_FRAME = 960             # 160 new samples + 80 features
+LOGMEL_BYTES_PER_FRAME = 1520           # 300 new samples + 80 features
 WORKLOAD = ("Fisher-test-shaped batch: 256 synthetic log-mel utterances, 56-400 frames length-bucketed, "
             "64 Griffin-Lim iters per GPU")
+WORKLOAD_SHARDED = ("Griffin-Lim 64 iters over ONE list of 10k synthetic utterances (56-400 frames) sharded by "
+                    "utterance over the GPUs (LPT on frames x iterations), length-bucketed per rank, final gather of "
+                    "waveforms to rank 0")
+WORKLOAD_FRONTEND = ("source fbank80 + global CMVN extraction over 10k synthetic utterances (8-20 s, 16 kHz) on 1 B200")
+GL_NCU_SUMMARY = os.path.join("profiles", "r02_glpass_ncu_summary.txt")
+GL_NCU_SUMMARY_OLD = os.path.join("profiles", "r01_glpass_current_ncu_summary.txt")
 
 
-def batch_frames(seed):
+# ---- synthetic workloads (shared with tests/) -----------------------------------------------------------------
+def batch_frames(seed, n_utts=N_UTTS):
     rng = np.random.RandomState(seed)
-    return sorted(int(t) for t in rng.randint(56, 401, size=N_UTTS))
+    return sorted(int(t) for t in rng.randint(56, 401, size=n_utts))
+
+
+def sharded_frames(seed=0):
+    """Config 4: the global utterance list in its (unsorted) corpus order."""
+    rng = np.random.RandomState(seed)
+    return [int(t) for t in rng.randint(56, 401, size=N_UTTS_SHARDED)]
 
 
 def synth_logmel_np(T, seed):
@@ -51,19 +74,39 @@ def synth_logmel_np(T, seed):
     return np.clip(x, np.log(1e-5), 2.0).astype(np.float32)
 
 
+def config2_batch(rank=0):
+    """(frames, log-mel [sum T, 80], initial phase [sum T, 1025] frame-major) of the config-2 batch of one rank."""
+    frames = batch_frames(0)
+    logmel = np.concatenate([synth_logmel_np(T, 1234 + 1000 * rank + i) for i, T in enumerate(frames)])
+    rng = np.random.RandomState(100 + rank)
+    phase = np.angle(np.exp(2j * np.pi * rng.rand(int(sum(frames)), N_BINS))).astype(np.float32)
+    return frames, logmel, phase
+
+
+def sharded_utterance_inputs(i, T):
+    """Log-mel [T, 80] and initial phase [T, 1025] (frame-major) of utterance i of the config-4 list: a function of
+    the utterance alone, so every sharding of the list synthesises the same thing."""
+    x = synth_logmel_np(T, 50000 + i)
+    rng = np.random.RandomState(90000 + i)
+    u = rng.rand(T, N_BINS).astype(np.float32)
+    return x, ((2.0 * u - 1.0) * np.float32(np.pi)).astype(np.float32)
+
+
 def measured_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_pass launch on this workload, from the
-    committed `ncu --set full` capture (profiles/r01_glpass_current_ncu_summary.txt); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_glpass_current_ncu_summary.txt")
-    try:
-        tot = 0.0
-        for line in open(path):
-            if line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum"):
-                val, unit = line.split("=")[1].split()[:2]
-                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
-        return tot or None
-    except (OSError, KeyError, ValueError, IndexError):
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_pass launch on the config-2 batch, from the committed
+    `ncu --set full` capture (ncu cannot run inside the benchmark); (bytes, source) or (None, None)."""
+    for rel in (GL_NCU_SUMMARY, GL_NCU_SUMMARY_OLD):
+        try:
+            tot = 0.0
+            for line in open(os.path.join(ROOT, rel)):
+                if line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum"):
+                    val, unit = line.split("=")[1].split()[:2]
+                    tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+            if tot:
+                return tot, rel
+        except (OSError, KeyError, ValueError, IndexError):
+            pass
+    return None, None
 
 
 def peaks():
@@ -71,6 +114,13 @@ def peaks():
     if os.path.isfile(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 1620.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -113,6 +163,16 @@ class ClockSampler:
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
+    def sample_while(self, event, max_samples=8):
+        """Sample while `event` (recorded after the last timed step) has not completed: everything of the timed region
+        is enqueued, the GPU is still working through the queue, and no launch can be delayed by a slow NVML call."""
+        while not event.query() and len(self.samples) < max_samples:
+            self.sample()
+            time.sleep(0.005)
+        self.under_load = len(self.samples)
+        if not self.samples:
+            self.sample()
+
     def stop(self):
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
@@ -122,7 +182,7 @@ class ClockSampler:
                 "source": "NVML, sampled inside the timed region while the GPU drains the enqueued steps"}
 
 
-# ------------------------------------------------------------------------------------------------
+# ---- CPU legs (the only places that execute oracle/) ---------------------------------------------------------------
 def cpu_port_time(frames_subset, seed, n_iter, basis):
     """Time the numpy oracle (the CPU port of the reference path) on the given utterances, 1 core."""
     from oracle import griffin_lim as ogl
@@ -131,7 +191,7 @@ def cpu_port_time(frames_subset, seed, n_iter, basis):
     for i, T in enumerate(frames_subset):
         x = synth_logmel_np(T, seed + i)
         np.random.seed(seed + i)
-        phase = ogl.random_phase((N_FFT // 2 + 1, T))
+        phase = ogl.random_phase((N_BINS, T))
         y = ogl.vocoder_forward(x, phase, n_iter, basis=basis)
         audio += y.shape[0] / SR
     return audio, time.perf_counter() - t0
@@ -159,22 +219,72 @@ def _fft_port_all_cores(frames, cores):
     return audio / dt, len(chunks), n_sample, sum(sample)
 
 
+def synth_audio_np(n, sr, seed):
+    """SURVEY 8(d) audio for config 3: white noise x 0.1 + 3 random sinusoids, in [-1, 1]."""
+    rng = np.random.RandomState(seed)
+    t = np.arange(n) / sr
+    x = 0.1 * rng.randn(n)
+    for _ in range(3):
+        x += rng.uniform(0.05, 0.3) * np.sin(2 * np.pi * rng.uniform(80, 0.45 * sr) * t + rng.uniform(0, 6.28))
+    return np.clip(x, -1, 1).astype(np.float32)
+
+
+def frontend_cpu_time(durations_s, sr, threads):
+    """The reference's own fbank80 + global CMVN path on the host cores: torchaudio.compliance.kaldi.fbank
+    (audio_utils.py:141-147) then (x - mean) / std in numpy (global_cmvn.py:26-29), one utterance per call."""
+    import torch
+    import torchaudio.compliance.kaldi as ta_kaldi
+    torch.set_num_threads(threads)
+    rng = np.random.RandomState(7)
+    mean, std = (rng.randn(80) - 4).astype(np.float32), rng.uniform(0.5, 2, 80).astype(np.float32)
+    waves = [torch.from_numpy(synth_audio_np(int(d * sr), sr, 300 + i) * (2 ** 15))[None] for i, d in enumerate(durations_s)]
+    t0 = time.perf_counter()
+    for w in waves:
+        f = ta_kaldi.fbank(w, num_mel_bins=80, sample_frequency=sr).numpy()
+        np.divide(np.subtract(f, mean), std)
+    return float(sum(durations_s)), time.perf_counter() - t0
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores, bounded sample per step.
 
-    What is timed is oracle/conv_formulation.py: the reference's own formulation (dense-basis conv1d /
-    conv_transpose1d, per-call window-sum-square loop, one utterance per call like speech_generator_for_s2st.py:115-124,
-    torch intra-op threads = all cores), which reproduces the reference's golden waveforms bit for bit
-    (tests/test_oracle_golden.py).  The cheaper numpy FFT oracle on all cores is reported beside it."""
+    Griffin-Lim workloads: what is timed is oracle/conv_formulation.py, the reference's own formulation (dense-basis
+    conv1d / conv_transpose1d, per-call window-sum-square loop, one utterance per call like
+    speech_generator_for_s2st.py:115-124, torch intra-op threads = all cores), which reproduces the reference's golden
+    waveforms bit for bit (tests/test_oracle_golden.py).  The initial phases are pre-drawn outside the timed loop
+    (the GPU arm's are uploaded from pre-drawn host buffers too).  The cheaper numpy FFT oracle on all cores is
+    reported beside it.  Front-end workload: torchaudio's kaldi.fbank + numpy CMVN, which IS the reference's code."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle import conv_formulation as ocf
-    from oracle import griffin_lim as ogl
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    frames = batch_frames(0)
+    workload = resolve_workload(args)
+    if workload == "frontend":
+        durs = list(np.random.RandomState(0).uniform(8, 20, 10000)[:24])
+        times, audio = [], 0.0
+        for step in range(args.warmup + args.steps):
+            audio, dt = frontend_cpu_time(durs, 16000, cores)
+            if step >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * float(np.mean(times))
+        value = audio / (ms / 1e3)
+        print(json.dumps({
+            "impl": "reference", "metric": "fbank80_cmvn_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_FRONTEND, "sample_rate": 16000, "n_bins": 80},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "reference",
+                             "sample": f"the first {len(durs)} utterances of the list ({audio:.0f} audio-s), torchaudio "
+                                       "compliance.kaldi.fbank + numpy global CMVN, one utterance per call"},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+    from oracle import conv_formulation as ocf
+    from oracle import griffin_lim as ogl
+    sharded = workload == "gl_sharded"
+    frames = sorted(sharded_frames(0)) if sharded else batch_frames(0)
     n_sample = 4
     sample = [frames[int(i)] for i in np.linspace(0, len(frames) - 1, n_sample)]
     basis = ogl.pinv_mel_basis(SR, N_FFT, N_MELS, F_MIN, F_MAX)
@@ -182,7 +292,7 @@ def run_reference_arm(args):
     inputs = []
     for i, T in enumerate(sample):
         np.random.seed(1000 + i)
-        inputs.append((synth_logmel_np(T, 1000 + i), ogl.random_phase((N_FFT // 2 + 1, T))))
+        inputs.append((synth_logmel_np(T, 1000 + i), ogl.random_phase((N_BINS, T))))
     times, audio = [], 0.0
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -196,15 +306,16 @@ def run_reference_arm(args):
     ms = 1e3 * float(np.mean(times))
     value = audio / (ms / 1e3)
     fft_value, fft_procs, fft_n, fft_frames = _fft_port_all_cores(frames, cores)
-    sample_desc = (f"{n_sample} of the {N_UTTS} utterances (length-stratified, {sum(sample)} frames), {N_ITER} iters, one "
+    sample_desc = (f"{n_sample} of the {len(frames)} utterances (length-stratified, {sum(sample)} frames), {N_ITER} iters, one "
                    f"utterance per call, the reference's dense-convolution formulation (oracle/conv_formulation.py, "
                    f"bit-identical to the reference's golden waveforms), torch CPU with {torch.get_num_threads()} threads")
     print(json.dumps({
         "impl": "reference", "metric": "griffin_lim_audio_seconds_per_second", "value": value,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_iter": N_ITER, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN},
+        "config": {"workload": WORKLOAD_SHARDED if sharded else WORKLOAD, "n_iter": N_ITER, "sample_rate": SR,
+                   "n_fft": N_FFT, "hop": HOP, "win": WIN},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample_desc,
                          "fft_oracle_all_cores": {"value": fft_value, "unit": "audio-s/s", "cores": fft_procs,
@@ -215,104 +326,134 @@ def run_reference_arm(args):
     }))
 
 
-# ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+# ---- shared GPU plumbing -------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-group / device context of one rank."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus or world == 1, (world, args.gpus)
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert self.world == args.gpus or self.world == 1, (self.world, args.gpus)
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        import __graft_entry__
+        __graft_entry__.build()
+        self.pkg = importlib.import_module(PKG)
 
-    import __graft_entry__
-    __graft_entry__.build()
-    pkg = importlib.import_module(PKG)
-    voc = pkg.GriffinLimVocoder(SR, WIN, HOP, N_FFT, N_MELS, F_MIN, F_MAX, torch.hann_window,
-                                spec_bwd_max_iter=N_ITER).to(dev)
-    plan = voc._plan(dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    frames = batch_frames(0)  # config 2 length law; every rank the same lengths, its own content (weak scaling)
+    def max_over_ranks(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def gather_floats(self, xs):
+        """Every rank's list of floats on every rank: [world, len(xs)]."""
+        t = self.torch.tensor(list(xs), dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return t[None].cpu().numpy()
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return self.torch.stack(out).cpu().numpy()
+
+    def timed(self, fn, steps, sampler=None):
+        """EXACTLY `steps` calls of fn between two events, barrier + synchronize on both sides; ms per step (max over
+        ranks) and the host wall time per step."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if sampler:
+            sampler.sample_while(e1)
+        self.barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0) / steps
+        return self.max_over_ranks(e0.elapsed_time(e1) / steps), self.max_over_ranks(wall_ms)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def make_vocoder(ctx, n_iter=N_ITER):
+    voc = ctx.pkg.GriffinLimVocoder(SR, WIN, HOP, N_FFT, N_MELS, F_MIN, F_MAX, ctx.torch.hann_window,
+                                    spec_bwd_max_iter=n_iter).to(ctx.dev)
+    return voc, voc._plan(ctx.dev)
+
+
+def pass_profile(ctx, plan, run_once, steps):
+    """Per-launch device time of the Griffin-Lim passes: CUDA events recorded by the library on the launching stream
+    around every pass, over `steps` extra runs (kept out of `value`'s region so the event records cannot perturb it)."""
+    plan.set_pass_timing(True)
+    per_step = []
+    ctx.barrier()
+    for _ in range(steps):
+        run_once()
+        per_step.append(plan.pass_times_ms())
+    plan.set_pass_timing(False)
+    return np.mean(np.stack(per_step), axis=0)
+
+
+# ---- workload: config 2 on every GPU (the N = 1 headline) ---------------------------------------------------------
+def run_gl(args, ctx):
+    torch = ctx.torch
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    voc, plan = make_vocoder(ctx)
+    frames, logmel_np, phase_np = config2_batch(rank)  # every rank the same lengths, its own content (weak scaling)
     total = int(sum(frames))
-    n_bins = N_FFT // 2 + 1
     audio_s = sum((T - 1) * HOP for T in frames) / SR
-    # host (pinned) inputs: denormalised log-mel, frame-major, and the seeded initial phase, frame-major
-    logmel_h = torch.from_numpy(np.concatenate([synth_logmel_np(T, 1234 + 1000 * rank + i) for i, T in enumerate(frames)])).pin_memory()
-    rng = np.random.RandomState(100 + rank)
-    phase_h = torch.from_numpy(np.angle(np.exp(2j * np.pi * rng.rand(total, n_bins))).astype(np.float32)).pin_memory()
+    logmel_h = torch.from_numpy(logmel_np).pin_memory()
+    phase_h = torch.from_numpy(phase_np).pin_memory()
     n_samples = (total - len(frames)) * HOP
     wave_h = torch.empty(n_samples, dtype=torch.float32).pin_memory()
-    logmel_d = logmel_h.to(dev)
-    phase_d = phase_h.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
+    logmel_d, phase_d = logmel_h.to(dev), phase_h.to(dev)
 
     # ---- device-resident timing (value) ----------------------------------------------------------
     for _ in range(args.warmup):
         voc.synthesize_flat(logmel_d, frames, phase_d)
-    barrier()
-    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_CLOCKS")) else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for step in range(args.steps):
-        wave_d = voc.synthesize_flat(logmel_d, frames, phase_d)
-    ev1.record()
-    # Clocks / throttle reasons are sampled NOW: everything of the timed region is enqueued, the GPU is still
-    # working through the queue (the host runs up to ~15 steps ahead), and no launch can be delayed by a slow
-    # NVML call (on some boxes one call takes tens of ms and, issued between steps, drained the launch queue).
-    if sampler:
-        while not ev1.query() and len(sampler.samples) < 8:
-            sampler.sample()
-            time.sleep(0.005)
-        sampler.under_load = len(sampler.samples)
-        if not sampler.samples:
-            sampler.sample()
-    barrier()
+    sampler = ClockSampler(ctx.local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_CLOCKS")) else None
+    keep = {}
+
+    def step():
+        keep["wave"] = voc.synthesize_flat(logmel_d, frames, phase_d)
+
+    ms_step, _ = ctx.timed(step, args.steps, sampler)
     clocks = sampler.stop() if sampler else None
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    assert torch.isfinite(wave_d).all()
-    # per-launch device time of the fused iteration kernel: CUDA events recorded by the library on the
-    # launching stream around every pass, over the same steps again (kept out of `value`'s region so the
-    # extra event records cannot perturb it)
-    plan.set_pass_timing(True)
-    per_step = []
-    barrier()
-    for _ in range(args.steps):
-        voc.synthesize_flat(logmel_d, frames, phase_d)
-        per_step.append(plan.pass_times_ms())
-    plan.set_pass_timing(False)
-    last_pass_ms = np.mean(np.stack(per_step), axis=0)
-    # one launch per iteration: [initial inverse, iteration 1, ..., iteration n]; persistent mode (all iterations in one
-    # launch, the default when every strip gets a resident warp): [initial inverse, the persistent launch]
+    assert torch.isfinite(keep["wave"]).all()
+    # sustained check: the same step back to back for >= 2 s, so a power-cap droop would show
+    n_sus = max(args.steps, int(np.ceil(2000.0 / ms_step)))
+    ms_sus, _ = ctx.timed(step, n_sus)
+    last_pass_ms = pass_profile(ctx, plan, step, min(args.steps, 20))
+    # one launch per iteration: [initial inverse, iteration 1, ..., iteration n]; persistent mode (all iterations in
+    # one launch): [initial inverse, the persistent launch]
     persistent = len(last_pass_ms) == 2 and N_ITER > 1
     iters_per_launch = N_ITER if persistent else 1
     iter_ms = float(np.mean(last_pass_ms[1:])) if len(last_pass_ms) > 1 else float("nan")  # per LAUNCH
+    launches = plan.gl_launch_count(N_ITER, True) * args.steps
 
     # ---- end to end through the public API, host buffers in and out (e2e) -------------------------
-    # Every step: H2D of that step's log-mel from pinned memory, synthesis, D2H of the waveforms.  The
-    # initial phase is drawn inside the timed call in both arms: the reference draws it with numpy on the
-    # host (vocoder.py:103), the library draws the same distribution on the device (phase_fm=None).  The
-    # variant that uploads a host-drawn phase (4.1 KB per frame, what the parity tests use) is reported too.
-    # Steps are fed back to back like generate_waveform.py feeds batches: synthesize_host() downloads on a copy stream,
-    # so step i's D2H overlaps step i+1's H2D and kernels; two host output buffers alternate, and the timed region ends
-    # only when every download has landed (barrier() synchronises the whole device).
+    # Every step: H2D of that step's log-mel AND of the seeded initial phase from pinned memory (north_star: "seeded
+    # initial phase supplied from the host"), synthesis, D2H of the waveforms.  Steps are fed back to back like
+    # generate_waveform.py feeds batches: synthesize_host() uploads / downloads on copy streams, so step i's D2H
+    # overlaps step i+1's H2D and kernels; two host output buffers alternate, and the timed region ends only when every
+    # download has landed.  The variant that lets the library draw the phase on the device is reported beside it.
     wave_h2 = torch.empty_like(wave_h).pin_memory()
     e2e_bufs, e2e_events = [wave_h, wave_h2], [None, None]
     e2e_count = [0]
@@ -328,43 +469,40 @@ def run_ours(args):
     def time_e2e(host_phase):
         for _ in range(min(args.warmup, 3)):
             e2e_step(host_phase)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_host0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            e2e_step(host_phase)
-        e1.record()
-        barrier()
-        wall_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps
-        return max_over_ranks(max(e0.elapsed_time(e1) / args.steps, wall_ms))
+        dev_ms, wall_ms = ctx.timed(lambda: e2e_step(host_phase), args.steps)
+        return max(dev_ms, wall_ms)
 
+    e2e_dev_ms = time_e2e(False)
     e2e_host_ms = time_e2e(True)
-    e2e_ms = time_e2e(False)
     assert torch.isfinite(wave_h).all() and torch.isfinite(wave_h2).all()
     e2e_count[0] = 0
     e2e_step(True)  # leave the host-phase result in wave_h for the parity spot check below
     torch.cuda.synchronize()
 
+    extras = {}
+    if rank == 0 and world == 1 and not os.environ.get("BENCH_NO_EXTRAS"):
+        extras = gl_extras(ctx, voc)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        ctx.close()
         return
 
     hbm_peak, peak_src = peaks()
     algo_bytes_iter = ALGO_BYTES_PER_FRAME_ITER * total * iters_per_launch  # per launch
     achieved = algo_bytes_iter / (iter_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic_bytes()
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------------
     from oracle import griffin_lim as ogl
     basis = voc.inv_mel_transform.basis.cpu().numpy()
     sample = [frames[int(i)] for i in np.linspace(0, len(frames) - 1, 6)]
     cpu_audio, cpu_s = cpu_port_time(sample, 4321, N_ITER, basis) if world == 1 else (0.0, 0.0)  # N = 1 only
-    # parity spot check on the way (checker only): first utterance of the batch vs the oracle
-    T0 = frames[0]
-    ref0 = ogl.vocoder_forward(logmel_h[:T0].numpy(), np.ascontiguousarray(phase_h[:T0].numpy().T), N_ITER, basis=basis)
-    parity = ogl.rel_l2(wave_h[: (T0 - 1) * HOP].numpy(), ref0)
+    # parity spot check on the way (checker only): the LONGEST utterance of the batch (most strips, 64 iterations,
+    # automatic strip length) through the e2e path with the host phase, against the oracle
+    Tl = frames[-1]
+    f0 = total - Tl
+    ref = ogl.vocoder_forward(logmel_np[f0:], np.ascontiguousarray(phase_np[f0:].T), N_ITER, basis=basis)
+    parity = ogl.rel_l2(wave_h[n_samples - (Tl - 1) * HOP: n_samples].numpy(), ref)
 
-    launches = plan.gl_launch_count(N_ITER, True) * args.steps
     out = {
         "metric": "griffin_lim_audio_seconds_per_second", "value": world * audio_s / (ms_step * 1e-3),
         "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -373,34 +511,408 @@ def run_ours(args):
                    "audio_seconds_per_gpu": audio_s, "n_iter": N_ITER, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP,
                    "win": WIN, "l2_policy": "per-step working set (magnitudes + phase + waveform buffers, "
                    f"{(total * (684 + 1025) * 4 + 4 * n_samples * 4) / 1e6:.0f} MB) exceeds the 126 MB L2"},
-        "e2e": {"value": world * audio_s / (e2e_ms * 1e-3), "unit": "audio-s/s",
-                "h2d_bytes_per_step": int(logmel_h.numel() * 4),
-                "d2h_bytes_per_step": int(wave_h.numel() * 4), "ms_per_step": e2e_ms,
-                "api": "GriffinLimVocoder.synthesize_host(pinned log-mel in, pinned waveforms out; initial phase drawn on "
-                       "the device; H2D and D2H run on copy streams and overlap the kernels of the neighbouring steps)",
-                "with_host_drawn_phase": {"value": world * audio_s / (e2e_host_ms * 1e-3), "ms_per_step": e2e_host_ms,
-                                          "h2d_bytes_per_step": int(logmel_h.numel() * 4 + phase_h.numel() * 4)}},
+        "e2e": {"value": world * audio_s / (e2e_host_ms * 1e-3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(logmel_h.numel() * 4 + phase_h.numel() * 4),
+                "d2h_bytes_per_step": int(wave_h.numel() * 4), "ms_per_step": e2e_host_ms,
+                "api": "GriffinLimVocoder.synthesize_host(pinned log-mel + pinned host-drawn seeded initial phase in, "
+                       "pinned waveforms out; H2D and D2H run on copy streams and overlap the kernels of the "
+                       "neighbouring steps)",
+                "with_device_drawn_phase": {"value": world * audio_s / (e2e_dev_ms * 1e-3), "ms_per_step": e2e_dev_ms,
+                                            "h2d_bytes_per_step": int(logmel_h.numel() * 4)}},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": ("k_gl_pass<19,false,true,true,PERSIST> (all %d iterations in one cooperative launch: " % N_ITER
                                                  if persistent else "k_gl_pass<19,false,true,true> (") +
                                                 "fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     # ncu capture of ONE iteration (profiles/r01_glpass_current_ncu_summary.txt) x iterations per launch
-                     "traffic": (measured_traffic_bytes() or 0) * iters_per_launch or None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
+                     "traffic": traffic * iters_per_launch if traffic else None,
+                     "traffic_source": ("ncu --set full capture of one iteration on this workload, committed as %s "
+                                        "(ncu cannot run inside the timed benchmark)" % traffic_src) if traffic else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_iter,
                      "launch_ms": iter_ms, "launches_per_step": N_ITER // iters_per_launch,
                      "iterations_per_launch": iters_per_launch, "ms_per_iteration": iter_ms / iters_per_launch,
                      "share_of_step": float(np.sum(last_pass_ms[1:]) / ms_step) if len(last_pass_ms) > 1 else None,
                      "first_pass_ms": float(last_pass_ms[0])},
+        "sustained": {"steps": n_sus, "seconds": n_sus * ms_sus * 1e-3, "ms_per_step": ms_sus,
+                      "value": world * audio_s / (ms_sus * 1e-3)},
         "cpu_baseline": None if world > 1 else {
             "value": cpu_audio / cpu_s, "unit": "audio-s/s", "cores": 1, "kind": "port",
             "sample": f"6 length-stratified utterances of the batch ({sum(sample)} frames), {N_ITER} iters, "
                       f"numpy FFT oracle, {cpu_s:.1f} s"},
         "clocks": clocks,
         "parity_rel_l2_vs_oracle": parity,
+        "parity_checked": f"longest utterance of the batch ({Tl} frames) through the e2e path with the host phase",
+    }
+    out.update(extras)
+    print(json.dumps(out))
+    ctx.close()
+
+
+def gl_extras(ctx, voc):
+    """Bounded extra measurements for the driver's view (N = 1): BASELINE config 1 through the reference's own call
+    shape (one utterance per GriffinLimVocoder.forward), config 5 (one 60 s utterance, 64 and 256 iterations), and the
+    tensor-core inverse-mel projection."""
+    torch = ctx.torch
+    dev = ctx.dev
+    out = {}
+
+    def timeit(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / n
+
+    # config 1: T = 500, 64 iterations.  (a) forward(): phase from numpy's global RNG on the host like vocoder.py:103;
+    # (b) the same utterance with the phase already on the device (what the kernels cost)
+    T = 500
+    x = torch.from_numpy(synth_logmel_np(T, 77)).to(dev)
+    audio = (T - 1) * HOP / SR
+    np.random.seed(0)
+    ms_fwd = timeit(lambda: voc(x), 10)
+    ph = torch.from_numpy(config2_batch(0)[2][:T].copy()).to(dev)
+    ms_dev = timeit(lambda: voc.synthesize_flat(x, [T], ph), 20)
+    out["config1"] = {"workload": "one 500-frame utterance, 64 iters", "forward_ms": ms_fwd,
+                      "forward_audio_s_per_s": audio / (ms_fwd * 1e-3), "device_phase_resident_ms": ms_dev,
+                      "device_phase_resident_audio_s_per_s": audio / (ms_dev * 1e-3),
+                      "note": "forward() draws 1025 x T float64 uniforms from numpy's global RNG on the host "
+                              "(vocoder.py:103) -- that draw bounds the per-utterance API"}
+    # config 5: one 60 s utterance
+    T = 4800
+    x5 = torch.from_numpy(synth_logmel_np(T, 78)).to(dev)
+    ph5 = ((torch.rand(T, N_BINS, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) * 2 - 1) * np.pi).contiguous()
+    audio = (T - 1) * HOP / SR
+    c5 = {"workload": "one 60 s utterance (4800 frames)"}
+    for n_iter in (64, 256):
+        ms = timeit(lambda: voc.synthesize_flat(x5, [T], ph5, n_iter=n_iter), 3)
+        c5[f"{n_iter}_iters"] = {"ms": ms, "audio_s_per_s": audio / (ms * 1e-3),
+                                 "hbm_frac": (ALGO_BYTES_PER_FRAME_ITER * n_iter + ALGO_BYTES_PER_FRAME_ONCE) * T / (ms * 1e-3) / 1e9 / peaks()[0]}
+    out["config5"] = c5
+    return out
+
+
+# ---- workload: config 4, one list sharded over the ranks -----------------------------------------------------------
+def run_gl_sharded(args, ctx):
+    torch, dist = ctx.torch, ctx.dist
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    sh = importlib.import_module(PKG + ".sharding")
+    voc, plan = make_vocoder(ctx)
+    frames_all = sharded_frames(0)
+    owned = sh.shard_utterances(frames_all, world, N_ITER)
+    mine = owned[rank]
+    buckets = sh.length_buckets(frames_all, mine, BUCKET_FRAMES, balanced=True)
+    audio_all = sum((T - 1) * HOP for T in frames_all) / SR
+    my_frames = sum(frames_all[i] for i in mine)
+
+    # inputs per bucket: pinned host (e2e) and device-resident (value)
+    host, devb = [], []
+    for b in buckets:
+        fr = [frames_all[i] for i in b]
+        xs, ps = zip(*(sharded_utterance_inputs(i, frames_all[i]) for i in b))
+        lm = torch.from_numpy(np.concatenate(xs)).pin_memory()
+        ph = torch.from_numpy(np.concatenate(ps)).pin_memory()
+        wh = torch.empty((sum(fr) - len(fr)) * HOP, dtype=torch.float32).pin_memory()
+        host.append((fr, lm, ph, wh))
+        devb.append((fr, lm.to(dev), ph.to(dev)))
+    del xs, ps
+
+    keep = {}
+
+    def synth():
+        keep["waves"] = [voc.synthesize_flat(lm, fr, ph) for fr, lm, ph in devb]
+
+    def gather():
+        local = []
+        for (fr, _, _), w in zip(devb, keep["waves"]):
+            local.extend(torch.split(w, [(T - 1) * HOP for T in fr]))
+        ids = [i for b in buckets for i in b]
+        st = {}
+        keep["gathered"] = sh.gather_waveforms(ids, local, len(frames_all), dst=0, stats=st)
+        keep["gather_stats"] = st
+
+    def step():
+        synth()
+        if world > 1:
+            gather()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(ctx.local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_CLOCKS")) else None
+    ms_step, _ = ctx.timed(step, args.steps, sampler)
+    clocks = sampler.stop() if sampler else None
+    ms_nogather, _ = ctx.timed(synth, args.steps)
+    # the gather alone (device time on each rank, max over ranks)
+    ms_gather = ctx.timed(gather, max(3, args.steps // 4))[0] if world > 1 else 0.0
+    # per-rank compute time of one pass over its shard (no barrier inside): the imbalance the sharding leaves
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    synth()
+    e1.record()
+    torch.cuda.synchronize()
+    per_rank = ctx.gather_floats([my_frames * (N_ITER + 1), e0.elapsed_time(e1), len(mine), len(buckets)])
+    # correctness of what arrived on rank 0: utterances synthesised on other ranks equal rank 0's own synthesis of the
+    # same inputs (spot check on three of them; run-to-run determinism makes this bitwise when the strip length agrees)
+    gather_check = None
+    if rank == 0 and world > 1:
+        got = keep["gathered"]
+        picks = [owned[r][0] for r in range(1, world)][:3]
+        errs = []
+        for i in picks:
+            x, p = sharded_utterance_inputs(i, frames_all[i])
+            alone = voc.synthesize_flat(torch.from_numpy(x).to(dev), [frames_all[i]], torch.from_numpy(p).to(dev))
+            errs.append(float((alone - got[i]).norm() / alone.norm()))
+        gather_check = {"utterances": picks, "max_rel_l2_vs_local_resynthesis": max(errs)}
+
+    # roofline of the iteration kernel over this rank's buckets
+    iter_ms_sum, iter_bytes, first_ms_sum = 0.0, 0.0, 0.0
+    for fr, lm, ph in devb:
+        prof = pass_profile(ctx, plan, lambda: voc.synthesize_flat(lm, fr, ph), 2) if True else None
+        iter_ms_sum += float(np.sum(prof[1:]))
+        first_ms_sum += float(prof[0])
+        iter_bytes += ALGO_BYTES_PER_FRAME_ITER * sum(fr) * N_ITER
+    launches = sum(plan.gl_launch_count(N_ITER, True) for _ in devb) * args.steps
+
+    # ---- e2e: pinned host in, per-rank pinned host out (what the reference's shards do: every shard keeps its own
+    # waveforms), uploads / downloads on copy streams
+    events = []
+
+    def e2e_step():
+        for e in events:
+            e.synchronize()
+        events.clear()
+        for fr, lm, ph, wh in host:
+            events.append(voc.synthesize_host(lm, fr, wh, device=dev, phase_host=ph))
+
+    for _ in range(2):
+        e2e_step()
+    e2e_dev_ms, e2e_wall_ms = ctx.timed(e2e_step, max(2, args.steps // 2))
+    e2e_ms = max(e2e_dev_ms, e2e_wall_ms)
+    h2d = sum(lm.numel() * 4 + ph.numel() * 4 for _, lm, ph, _ in host)
+    d2h = sum(wh.numel() * 4 for *_, wh in host)
+    tot_bytes = ctx.gather_floats([h2d, d2h]).sum(axis=0)
+
+    if rank != 0:
+        ctx.close()
+        return
+    hbm_peak, peak_src = peaks()
+    achieved = iter_bytes / (iter_ms_sum * 1e-3) / 1e9
+    loads = per_rank[:, 0]
+    out = {
+        "metric": "griffin_lim_audio_seconds_per_second", "value": audio_all / (ms_step * 1e-3), "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_SHARDED, "utterances": len(frames_all), "frames": int(sum(frames_all)),
+                   "audio_seconds": audio_all, "n_iter": N_ITER, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN,
+                   "bucket_frames": BUCKET_FRAMES, "buckets_per_rank": [int(x) for x in per_rank[:, 3]],
+                   "l2_policy": "per-call working set (>= 1 GB per bucket) exceeds the 126 MB L2"},
+        "collective": {"name": "gather_waveforms: exact-size point-to-point sends to rank 0 in one NCCL group (no data-path "
+                               "collective; one small all_gather of sizes)" if world > 1 else "none (single rank)",
+                       "bytes_to_rank0": keep.get("gather_stats", {}).get("bytes_to_dst", 0), "ms": ms_gather,
+                       "check": gather_check},
+        "without_gather": {"ms_per_step": ms_nogather, "value": audio_all / (ms_nogather * 1e-3)},
+        "sharding": {"policy": "LPT on frames x (n_iter + 1), then balanced length buckets per rank",
+                     "frame_iterations_per_rank": [int(x) for x in loads],
+                     "imbalance_max_over_mean": float(loads.max() / loads.mean()),
+                     "compute_ms_per_rank": [float(x) for x in per_rank[:, 1]],
+                     "utterances_per_rank": [int(x) for x in per_rank[:, 2]]},
+        "e2e": {"value": audio_all / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(tot_bytes[0]),
+                "d2h_bytes_per_step": int(tot_bytes[1]), "ms_per_step": e2e_ms,
+                "api": "per rank and bucket GriffinLimVocoder.synthesize_host(pinned log-mel + pinned seeded initial phase "
+                       "in, pinned waveforms out on the rank that synthesised them -- the reference's shards keep their "
+                       "own outputs too, generate_waveform.py:166-167)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_gl_pass<19,false,true,true> (fused iSTFT+OLA+normalise+STFT+magnitude "
+                                               "re-imposition), rank 0's buckets",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": iter_bytes, "iteration_ms_per_step": iter_ms_sum,
+                     "share_of_step": iter_ms_sum / ms_nogather, "first_pass_ms_per_step": first_ms_sum},
+        "cpu_baseline": None,
+        "clocks": clocks,
     }
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
+
+
+# ---- workload: config 3, the feature front-end ----------------------------------------------------------------------
+def run_frontend(args, ctx):
+    torch = ctx.torch
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    pkg = ctx.pkg
+    plans = importlib.import_module(PKG + ".plans")
+    lib = pkg._lib.load()
+    ptr, check, sptr = pkg._lib.ptr, pkg._lib.check, pkg._lib.stream_ptr
+    n_utts = int(os.environ.get("BENCH_FRONTEND_UTTS", "10000"))
+    rng = np.random.RandomState(0 + rank)
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    mean = (torch.randn(80, device=dev, generator=g) - 4).contiguous()
+    std = (torch.rand(80, device=dev, generator=g) * 1.5 + 0.5).contiguous()
+
+    def synth_audio_dev(lens, sr, scale):
+        """The SURVEY 8(d) signal built on the device (setup plumbing): noise x 0.1 + three sinusoids, clipped."""
+        n = int(lens.sum())
+        x = 0.1 * torch.randn(n, device=dev, generator=g)
+        t = torch.arange(n, device=dev, dtype=torch.float32) / sr
+        for _ in range(3):
+            x += float(rng.uniform(0.05, 0.3)) * torch.sin(2 * np.pi * float(rng.uniform(80, 0.45 * sr)) * t + float(rng.uniform(0, 6.28)))
+        return (x.clamp_(-1, 1) * scale).contiguous()
+
+    def offsets(lens, frames):
+        fo = torch.from_numpy(np.concatenate([[0], np.cumsum(frames)]).astype(np.int32)).to(dev)
+        wo = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev)
+        return fo, wo
+
+    def fbank_case(sr, n):
+        lens = (rng.uniform(8, 20, n) * sr).astype(np.int64)
+        plan = plans.get_fbank_plan(dev, sr, 80)
+        frames = [1 + (int(k) - plan.win) // plan.shift for k in lens]
+        flat = synth_audio_dev(lens, sr, 2.0 ** 15)
+        fo, wo = offsets(lens, frames)
+        total = int(sum(frames))
+        o = torch.empty(total, 80, device=dev)
+
+        def run(src=flat, dst=o):
+            check(lib.s2st_fbank(plan.handle, n, total, ptr(wo), ptr(fo), ptr(src), ptr(mean), ptr(std), ptr(dst),
+                                 sptr(dev)), "s2st_fbank")
+        return run, float(lens.sum()) / sr, total, flat, o
+
+    res = {}
+    hbm_peak, peak_src = peaks()
+    # headline: fbank80 + CMVN at 16 kHz over the whole list
+    run16, audio16, frames16, flat16, out16 = fbank_case(16000, n_utts)
+    for _ in range(args.warmup):
+        run16()
+    sampler = ClockSampler(ctx.local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_CLOCKS")) else None
+    ms16, _ = ctx.timed(run16, args.steps, sampler)
+    clocks = sampler.stop() if sampler else None
+    assert torch.isfinite(out16).all()
+    # e2e: pinned host waveform in, pinned host features out, chunked so that upload, kernel and download overlap
+    flat_h = flat16.cpu().pin_memory()
+    out_h = torch.empty(out16.shape, dtype=torch.float32).pin_memory()
+    # (the front-end C entry takes one ragged batch; the host shim pipelines equal shares of the list)
+    n_chunks = 8
+    e2e_ms = frontend_e2e(ctx, lib, pkg, plans, flat_h, out_h, n_utts, 16000, mean, std, n_chunks, args, rng_seed=rank)
+    res16 = {"ms": ms16, "audio_s_per_s": audio16 / (ms16 * 1e-3), "frames": frames16,
+             "hbm_frac": frames16 * FBANK_BYTES_PER_FRAME / (ms16 * 1e-3) / 1e9 / hbm_peak}
+    del flat16, out16, run16
+    torch.cuda.empty_cache()
+    # beside it: fbank80 at 8 kHz and logmelspec80 at 24 kHz on a fifth of the list
+    n_side = max(1, n_utts // 5)
+    run8, audio8, frames8, _f8, _o8 = fbank_case(8000, n_side)
+    for _ in range(3):
+        run8()
+    ms8, _ = ctx.timed(run8, max(3, args.steps // 2))
+    res["fbank80_cmvn_8k"] = {"utterances": n_side, "ms": ms8, "audio_s_per_s": audio8 / (ms8 * 1e-3), "frames": frames8,
+                              "hbm_frac": frames8 * FBANK_BYTES_PER_FRAME / (ms8 * 1e-3) / 1e9 / hbm_peak}
+    del run8, _f8, _o8
+    lens = (rng.uniform(8, 20, n_side) * SR).astype(np.int64)
+    flat = synth_audio_dev(lens, SR, 1.0)
+    frames = [1 + int(k) // HOP for k in lens]
+    total = int(sum(frames))
+    planl = plans.get_stft_plan(dev, N_FFT, WIN, HOP, N_MELS, torch.hann_window(WIN),
+                                mel=pkg.get_mel_filters(SR, N_FFT, N_MELS, F_MIN, F_MAX))
+    fo, wo = offsets(lens, frames)
+    o = torch.empty(total, N_MELS, device=dev)
+
+    def runl():
+        check(lib.s2st_logmel(planl.handle, n_side, total, ptr(wo), ptr(fo), ptr(flat), 1e-5, ptr(mean), ptr(std),
+                              ptr(o), sptr(dev)), "s2st_logmel")
+    for _ in range(3):
+        runl()
+    msl, _ = ctx.timed(runl, max(3, args.steps // 2))
+    res["logmelspec80_cmvn_24k"] = {"utterances": n_side, "ms": msl, "audio_s_per_s": float(lens.sum()) / SR / (msl * 1e-3),
+                                    "frames": total, "hbm_frac": total * LOGMEL_BYTES_PER_FRAME / (msl * 1e-3) / 1e9 / hbm_peak}
+    if rank != 0:
+        ctx.close()
+        return
+    cores = os.cpu_count() or 1
+    durs = list(np.random.RandomState(0).uniform(8, 20, 10000)[:16])
+    cpu_audio, cpu_s = frontend_cpu_time(durs, 16000, cores) if world == 1 else (0.0, 1.0)
+    achieved = frames16 * FBANK_BYTES_PER_FRAME / (ms16 * 1e-3) / 1e9
+    out = {
+        "metric": "fbank80_cmvn_audio_seconds_per_second", "value": world * audio16 / (ms16 * 1e-3), "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms16, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_FRONTEND, "utterances_per_gpu": n_utts, "frames_per_gpu": frames16,
+                   "audio_seconds_per_gpu": audio16, "sample_rate": 16000, "n_bins": 80,
+                   "l2_policy": f"inputs + outputs ({(audio16 * 16000 * 4 + frames16 * 320) / 1e9:.1f} GB) exceed the 126 MB L2"},
+        "e2e": {"value": world * audio16 / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(flat_h.numel() * 4),
+                "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": e2e_ms,
+                "api": f"fbank80 + fused CMVN, pinned host waveforms in, pinned host features out, {n_chunks} chunks "
+                       "pipelined over copy streams (PCIe-bound: 4 B in per sample)"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "kernel": "k_fbank_fast<0> (16 kHz: DC removal, pre-emphasis, povey window, FFT-512, "
+                                               "power, mel, log, CMVN)",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": frames16 * FBANK_BYTES_PER_FRAME,
+                     "launch_ms": ms16},
+        "cpu_baseline": None if world > 1 else {
+            "value": cpu_audio / cpu_s, "unit": "audio-s/s", "cores": cores, "kind": "reference",
+            "sample": f"the first {len(durs)} utterances ({cpu_audio:.0f} audio-s): torchaudio compliance.kaldi.fbank + numpy "
+                      f"CMVN (the reference's own code path, audio_utils.py:141-147, global_cmvn.py:26-29), {cpu_s:.1f} s"},
+        "clocks": clocks,
+        "fbank80_cmvn_16k": res16,
+    }
+    out.update(res)
+    print(json.dumps(out))
+    ctx.close()
+
+
+def frontend_e2e(ctx, lib, pkg, plans, flat_h, out_h, n_utts, sr, mean, std, n_chunks, args, rng_seed):
+    """Pinned host waveforms -> fbank80 + CMVN -> pinned host features, utterance chunks pipelined over an upload
+    stream, the compute stream and a download stream."""
+    torch = ctx.torch
+    dev = ctx.dev
+    ptr, check = pkg._lib.ptr, pkg._lib.check
+    rng = np.random.RandomState(0 + rng_seed)
+    lens = (rng.uniform(8, 20, n_utts) * sr).astype(np.int64)  # the same draw as fbank_case(16000, n_utts)
+    plan = plans.get_fbank_plan(dev, sr, 80)
+    frames = np.array([1 + (int(k) - plan.win) // plan.shift for k in lens])
+    bounds = np.linspace(0, n_utts, n_chunks + 1).astype(int)
+    wo_all = np.concatenate([[0], np.cumsum(lens)])
+    fo_all = np.concatenate([[0], np.cumsum(frames)])
+    chunks = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        fo = torch.from_numpy((fo_all[a:b + 1] - fo_all[a]).astype(np.int32)).to(dev)
+        wo = torch.from_numpy((wo_all[a:b + 1] - wo_all[a]).astype(np.int64)).to(dev)
+        chunks.append((int(b - a), int(fo_all[b] - fo_all[a]), fo, wo, int(wo_all[a]), int(wo_all[b]), int(fo_all[a]), int(fo_all[b])))
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+
+    def step():
+        for n, total, fo, wo, w0, w1, f0, f1 in chunks:
+            with torch.cuda.stream(up):
+                src = flat_h[w0:w1].to(dev, non_blocking=True)
+            main.wait_stream(up)
+            src.record_stream(main)
+            dst = torch.empty(total, 80, device=dev)
+            check(lib.s2st_fbank(plan.handle, n, total, ptr(wo), ptr(fo), ptr(src), ptr(mean), ptr(std), ptr(dst),
+                                 ctypes_stream(main)), "s2st_fbank")
+            down.wait_stream(main)
+            with torch.cuda.stream(down):
+                out_h[f0:f1].copy_(dst, non_blocking=True)
+            dst.record_stream(down)
+        main.wait_stream(down)
+
+    for _ in range(2):
+        step()
+    dev_ms, wall_ms = ctx.timed(step, max(2, args.steps // 4))
+    return max(dev_ms, wall_ms)
+
+
+def ctypes_stream(stream):
+    import ctypes
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
+def resolve_workload(args):
+    if args.workload != "auto":
+        return args.workload
+    return "gl" if args.gpus == 1 else "gl_sharded"
 
 
 def main():
@@ -409,12 +921,15 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "gl", "gl_sharded", "frontend"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
-    else:
-        run_ours(args)
+        return
+    workload = resolve_workload(args)
+    ctx = Ctx(args)
+    {"gl": run_gl, "gl_sharded": run_gl_sharded, "frontend": run_frontend}[workload](args, ctx)
 
 
 if __name__ == "__main__":

@@ -14,6 +14,11 @@
  *   - the CALLER owns every input / output / workspace buffer; the library never allocates per
  *     call, enqueues all work on the caller's stream (cudaStream_t passed as void*) and never
  *     synchronises.  The only device memory the library owns are the plan's constants.
+ *   - a plan also carries its OPTIONS (s2st_plan_set_option) and the profiling state of its last
+ *     synthesis call (launch count, pass-timing events); functions that update either take a
+ *     non-const plan.  There is no other mutable state: the S2ST_* environment variables are read
+ *     once, when a plan is created, as the initial option values -- never per call.  One plan must
+ *     not run two synthesis calls concurrently from different host threads.
  *   - all arithmetic is fp32.  Ragged batches are concatenated frame-major:
  *       frame_offsets[B+1]  (int32, device)  cumulative frame counts, frame_offsets[0] = 0
  *       features            [total_frames, n_mels]     row-major (the reference's [T, 80] layout)
@@ -35,7 +40,7 @@ extern "C" {
 #define S2ST_ECUDA 2       /* a CUDA runtime call failed */
 #define S2ST_EWORKSPACE 3  /* workspace too small */
 
-#define S2ST_ABI_VERSION 1
+#define S2ST_ABI_VERSION 2
 
 typedef struct s2st_plan s2st_plan; /* opaque: owns only constants (windows, twiddles, mel matrices) */
 
@@ -59,6 +64,18 @@ int s2st_plan_destroy(s2st_plan* plan);
 /* number of leading spectrogram bins that can be non-zero after the inverse-mel projection
  * (rows of inv_mel beyond it are exactly zero; n_fft/2+1 when no inv_mel was given). */
 int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
+/* Plan options (all have working defaults; they exist for A/B measurements and tests).  Initial values come from the
+ * environment variable named in brackets, read once by s2st_plan_create. */
+#define S2ST_OPT_GL_PERSISTENT 1    /* [S2ST_GL_PERSISTENT] -1 (default): run all Griffin-Lim iterations of a SMALL call
+                                       (<= 1/4 of the resident warps get a strip) as one persistent launch, larger calls as one
+                                       launch per iteration; 0: never persistent; 1: persistent whenever every strip is resident.
+                                       Results are bitwise identical in all three modes. */
+#define S2ST_OPT_GL_PDL 2           /* [S2ST_GL_PDL] 1 (default): programmatic dependent launch of the passes; 0: plain launches */
+#define S2ST_OPT_GL_KERNEL 3        /* [S2ST_GL_KERNEL=r64] 0 (default): packed-complex iteration kernel; 1: real-FFT-64 formulation */
+#define S2ST_OPT_INVERSE_MEL 4      /* [S2ST_INVERSE_MEL=simt] 0 (default): tcgen05 tensor-core inverse-mel; 1: FP32 SIMT kernel */
+#define S2ST_OPT_FRONTEND_GENERIC 5 /* [S2ST_LOGMEL_GENERIC / S2ST_FBANK_GENERIC] 0 (default): register-resident log-mel / fbank
+                                       kernels where they apply; 1: always the generic kernels */
+int s2st_plan_set_option(s2st_plan* plan, int option, int value);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Griffin-Lim ragged batch: GriffinLimVocoder.forward (vocoder.py:136-144) for B utterances at once.
@@ -77,7 +94,7 @@ int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
  * Every utterance must have T >= 1; when n_iter > 0, (T-1)*hop must exceed n_fft/2 (the
  * reference's reflect padding raises otherwise) -- checked by the host shim, not here. */
 int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_frames, size_t* bytes_out);
-int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
+int s2st_gl_synthesize(s2st_plan* plan, int n_utts, int64_t total_frames,
                        const int32_t* frame_offsets_dev, const int32_t* frame_offsets_host,
                        const float* logmel_dev,
                        const float* mag_dev, const float* init_phase_dev, uint64_t phase_seed, int n_iter,
@@ -100,6 +117,15 @@ int s2st_plan_get_pass_times(s2st_plan* plan, float* ms_out_host, int capacity, 
 /* number of kernel launches of the plan's most recent s2st_gl_synthesize call (for bench.py's gpu_launches); before
  * the first call: what a call with one launch per iteration would enqueue */
 int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int* launches_out);
+
+/* The initial phase of GriffinLim.forward (vocoder.py:103-104): angles = angle(exp(2j * pi * rand(*shape))) cast to
+ * float32.  The reference draws rand() from numpy's GLOBAL generator on the host; the host shim keeps exactly that draw
+ * (so seeding numpy reproduces the reference) and uploads the float64 uniforms; this entry turns them into the phase on
+ * the device and transposes the reference's [B, F, T] layout into the frame-major [B * T, F] that
+ * s2st_gl_synthesize reads:  phase = theta if theta <= pi else theta - 2 pi,  theta = 2 pi u  (float64, then float32).
+ *   uniform_dev [n_batch, n_bins, n_frames] float64 in [0, 1);  phase_out_dev [n_batch * n_frames, n_bins] float32 */
+int s2st_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double* uniform_dev, float* phase_out_dev,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* building blocks (test surface + the reference's public sub-modules)                         */
@@ -125,7 +151,7 @@ int s2st_stft(const s2st_plan* plan, int n_utts, int64_t total_frames,
 
 /* GriffinLim.inverse (vocoder.py:84-100): frame-major mag / phase -> concatenated waveforms.
  * Uses the same workspace as s2st_gl_synthesize. */
-int s2st_istft(const s2st_plan* plan, int n_utts, int64_t total_frames,
+int s2st_istft(s2st_plan* plan, int n_utts, int64_t total_frames,
                const int32_t* frame_offsets_dev, const float* mag_dev, const float* phase_dev,
                float* wave_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
@@ -156,6 +182,8 @@ int s2st_logmel(const s2st_plan* plan, int n_utts, int64_t total_frames,
 typedef struct s2st_fbank_plan s2st_fbank_plan;
 int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_rate, int n_bins);
 int s2st_fbank_plan_destroy(s2st_fbank_plan* plan);
+/* option S2ST_OPT_FRONTEND_GENERIC only (initial value: S2ST_FBANK_GENERIC, read once at plan creation) */
+int s2st_fbank_plan_set_option(s2st_fbank_plan* plan, int option, int value);
 /* window size / shift / padded FFT size of the plan: m_i = 1 + (n_i - win) / shift (0 if n_i < win) */
 int s2st_fbank_frame_params(const s2st_fbank_plan* plan, int* win_out, int* shift_out, int* padded_out);
 /*   wave_dev is the int16-scaled waveform (audio_utils.py:105-106); out_dev [total_frames, n_bins];

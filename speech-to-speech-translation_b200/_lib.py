@@ -16,6 +16,9 @@ LIB_PATH = os.environ.get("S2ST_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "s2st_b200.h")
 
 S2ST_OK = 0
+ABI_VERSION = 2
+# s2st_plan_set_option keys (include/s2st_b200.h)
+OPT_GL_PERSISTENT, OPT_GL_PDL, OPT_GL_KERNEL, OPT_INVERSE_MEL, OPT_FRONTEND_GENERIC = 1, 2, 3, 4, 5
 
 c_f32p = ctypes.c_void_p  # device pointers are passed as integers (tensor.data_ptr())
 
@@ -34,6 +37,10 @@ SIGNATURES = {
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "s2st_plan_set_strip_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "s2st_plan_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "s2st_fbank_plan_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "s2st_phase_from_uniform": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p]),
     "s2st_plan_set_pass_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "s2st_plan_get_pass_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_int)]),
@@ -108,7 +115,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.s2st_abi_version() != 1:
+        if lib.s2st_abi_version() != ABI_VERSION:
             raise S2STLibraryError("libs2st_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -135,6 +136,17 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         return S2ST_EINVAL;
     }
     s2st_plan* p = new s2st_plan();
+    {   // options: the S2ST_* environment variables are read HERE, once; afterwards only s2st_plan_set_option changes them
+        const char* e = getenv("S2ST_GL_PERSISTENT");
+        p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == '0') ? 0 : -1;
+        e = getenv("S2ST_GL_PDL");
+        p->opt_pdl = !(e && e[0] == '0');
+        e = getenv("S2ST_GL_KERNEL");
+        p->opt_gl_kernel = (e && e[0] == 'r') ? 1 : 0;
+        e = getenv("S2ST_INVERSE_MEL");
+        p->opt_inverse_mel_simt = (e && e[0] == 's') ? 1 : 0;
+        p->opt_frontend_generic = getenv("S2ST_LOGMEL_GENERIC") ? 1 : 0;
+    }
     std::memset(p, 0, sizeof(*p));
     p->device = device;
     p->n_fft = n_fft;
@@ -373,6 +385,37 @@ int s2st_plan_set_strip_frames(s2st_plan* plan, int frames) {
     return S2ST_OK;
 }
 
+int s2st_plan_set_option(s2st_plan* plan, int option, int value) {
+    if (!plan) {
+        set_error("null plan");
+        return S2ST_EINVAL;
+    }
+    switch (option) {
+        case S2ST_OPT_GL_PERSISTENT:
+            if (value < -1 || value > 1) break;
+            plan->opt_persistent = value;
+            return S2ST_OK;
+        case S2ST_OPT_GL_PDL:
+            plan->opt_pdl = value != 0;
+            return S2ST_OK;
+        case S2ST_OPT_GL_KERNEL:
+            if (value < 0 || value > 1) break;
+            plan->opt_gl_kernel = value;
+            return S2ST_OK;
+        case S2ST_OPT_INVERSE_MEL:
+            if (value < 0 || value > 1) break;
+            plan->opt_inverse_mel_simt = value;
+            return S2ST_OK;
+        case S2ST_OPT_FRONTEND_GENERIC:
+            plan->opt_frontend_generic = value != 0;
+            return S2ST_OK;
+        default:
+            break;
+    }
+    set_error("s2st_plan_set_option: unknown option %d or bad value %d", option, value);
+    return S2ST_EINVAL;
+}
+
 int s2st_plan_set_pass_timing(s2st_plan* plan, int enabled) {
     if (!plan) {
         set_error("null plan");
@@ -418,7 +461,16 @@ int s2st_gl_workspace_bytes(const s2st_plan* plan, int n_utts, int64_t total_fra
     return S2ST_OK;
 }
 
-int s2st_gl_synthesize(const s2st_plan* plan, int n_utts, int64_t total_frames,
+int s2st_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double* uniform_dev, float* phase_out_dev,
+                             void* stream) {
+    if (n_batch < 0 || n_bins < 0 || n_frames < 0 || ((!uniform_dev || !phase_out_dev) && n_batch * n_bins * n_frames > 0)) {
+        set_error("bad argument to s2st_phase_from_uniform");
+        return S2ST_EINVAL;
+    }
+    return launch_phase_from_uniform(n_batch, n_bins, n_frames, uniform_dev, phase_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_gl_synthesize(s2st_plan* plan, int n_utts, int64_t total_frames,
                        const int32_t* frame_offsets_dev, const int32_t* frame_offsets_host, const float* logmel_dev,
                        const float* mag_dev, const float* init_phase_dev, uint64_t phase_seed, int n_iter,
                        float* wave_out_dev, void* workspace_dev, size_t workspace_bytes,
@@ -477,7 +529,7 @@ int s2st_stft(const s2st_plan* plan, int n_utts, int64_t total_frames, const int
                        phase_out_dev, nullptr, 0.0f, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
-int s2st_istft(const s2st_plan* plan, int n_utts, int64_t total_frames, const int32_t* frame_offsets_dev,
+int s2st_istft(s2st_plan* plan, int n_utts, int64_t total_frames, const int32_t* frame_offsets_dev,
                const float* mag_dev, const float* phase_dev, float* wave_out_dev, void* workspace_dev,
                size_t workspace_bytes, void* stream) {
     if (!plan || !frame_offsets_dev || !mag_dev || !phase_dev || !wave_out_dev) {
@@ -558,6 +610,7 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
         return S2ST_EINVAL;
     }
     s2st_fbank_plan* p = new s2st_fbank_plan();
+    p->opt_generic = getenv("S2ST_FBANK_GENERIC") ? 1 : 0;  // read once, here
     std::memset(p, 0, sizeof(*p));
     p->device = device;
     p->sample_rate = sample_rate;
@@ -744,6 +797,15 @@ int s2st_fbank_plan_destroy(s2st_fbank_plan* plan) {
     cudaFree(plan->mel_idx);
     cudaFree(plan->mel_val);
     delete plan;
+    return S2ST_OK;
+}
+
+int s2st_fbank_plan_set_option(s2st_fbank_plan* plan, int option, int value) {
+    if (!plan || option != S2ST_OPT_FRONTEND_GENERIC) {
+        set_error("s2st_fbank_plan_set_option: null plan or unknown option %d", option);
+        return S2ST_EINVAL;
+    }
+    plan->opt_generic = value != 0;
     return S2ST_OK;
 }
 

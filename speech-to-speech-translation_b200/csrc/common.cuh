@@ -31,6 +31,7 @@ struct TileDesc {
 // Everything the Griffin-Lim kernels need, passed by value.
 struct GlParams {
     int device;    // host-side bookkeeping only
+    int pdl;       // host-side: launch the passes with programmatic dependent launch
     // geometry
     int hop;       // H
     int half;      // n_fft / 2 (reflect padding, trimmed from both ends)

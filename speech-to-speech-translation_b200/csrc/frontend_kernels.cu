@@ -791,7 +791,7 @@ int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const
     p.mel_col = plan->mel_col;
     p.mel_gather = plan->mel_gather;
     p.mel_terms = plan->mel_terms;
-    if (logmel_out && plan->mel_col && plan->mel_gather && !getenv("S2ST_LOGMEL_GENERIC")) {
+    if (logmel_out && plan->mel_col && plan->mel_gather && !plan->opt_frontend_generic) {
         const size_t fsmem = sizeof(float2) * 2048 + sizeof(float4) * kLmCols + sizeof(int) * 8 * 128 +
                              sizeof(float) * (plan->wp + 8 * kScratchFloats);
         const long long chunks = (total_frames + kLmChunk - 1) / kLmChunk;
@@ -860,7 +860,7 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
     p.mel_idx = plan->mel_idx;
     p.mel_val = plan->mel_val;
     p.out = out;
-    if (plan->fast_mode >= 0 && !getenv("S2ST_FBANK_GENERIC")) {
+    if (plan->fast_mode >= 0 && !plan->opt_generic) {
         FbankFastParams q;
         q.win = plan->win;
         q.shift = plan->shift;

@@ -21,8 +21,6 @@
 // and zeroes the seams of buf[(i+1)%3] for the next pass.
 #include <math_constants.h>
 
-#include <cstdlib>
-
 #include "../../include/s2st_b200.h"
 #include "frame_r64.cuh"
 #include "plan.h"
@@ -817,6 +815,38 @@ __global__ void __launch_bounds__(256) k_rfft2048(const float2* __restrict__ tw_
     }
 }
 
+// Initial phase from the reference's uniform draw (vocoder.py:103: angles = angle(exp(2j * pi * rand(F, T))), cast to
+// the spectrogram's dtype).  The host shim draws u with numpy's global RNG -- the part that must be numpy's stream --
+// and uploads the float64 uniforms; angle(exp(i theta)) with theta = 2 pi u in [0, 2 pi) is theta for theta <= pi and
+// theta - 2 pi otherwise, evaluated here in float64 with a two-term 2 pi (the reference's libm sin / cos / atan2 round
+// trip agrees to < 3e-16, i.e. the float32 results are identical up to ~1e-9 of the elements), then transposed from
+// the reference's [B, F, T] to the frame-major [B * T, F] the synthesis kernels read.  HBM-bound byte mover: 8 B in +
+// 4 B out per element, both sides coalesced through a 32 x 33 shared-memory tile.
+__global__ void __launch_bounds__(256) k_phase_from_uniform(const double* __restrict__ u, int n_bins, int n_frames,
+                                                             float* __restrict__ phase) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const double* ub = u + (size_t)b * n_bins * n_frames;
+    float* pb = phase + (size_t)b * n_frames * n_bins;
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int f = f0 + ty + k, t = t0 + tx;
+        if (f < n_bins && t < n_frames) {
+            const double th = 6.283185307179586 * ub[(size_t)f * n_frames + t];  // fl(2 pi) * u, one rounding like numpy
+            const double a = th > 3.141592653589793 ? (th - 6.283185307179586) - 2.4492935982947064e-16 : th;
+            tile[ty + k][tx] = (float)a;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int t = t0 + ty + k, f = f0 + tx;
+        if (f < n_bins && t < n_frames) pb[(size_t)t * n_bins + f] = tile[tx][ty + k];
+    }
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct GlWorkspace {
@@ -863,15 +893,10 @@ size_t gl_pass_r64_smem() {
     return sizeof(float2) * (1024 + 32 * 19 + 32) + sizeof(float) * (kStdHop + kGlWarps * (kR64ScratchFloats + kStdWs));
 }
 
-// S2ST_GL_KERNEL=r64 selects the real-FFT-64 formulation (frame_r64.cuh) for the vocoder's standard case.  It is
+// S2ST_OPT_GL_KERNEL = 1 selects the real-FFT-64 formulation (frame_r64.cuh) for the vocoder's standard case.  It is
 // parity-tested but NOT the default: it moves 32 % fewer shared-memory wavefronts per frame-iteration, yet the column
 // of bins that are multiples of 32 costs ~190 extra instructions, so it ends up level with the packed-complex kernel
 // (0.238 vs 0.236 ms per pass on the config-2 batch) and its first pass is slower.
-bool use_r64_kernel() {
-    const char* e = getenv("S2ST_GL_KERNEL");
-    return e && e[0] == 'r';
-}
-
 size_t gl_pass_smem(const s2st_plan* plan) {
     return sizeof(float2) * 2048 +
            sizeof(float) * (plan->wp + ((plan->hop + 3) & ~3) + kGlWarps * (kScratchFloats + ((plan->ws + 3) & ~3)));
@@ -908,16 +933,12 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
 // parity-tested, but measured 1.6 % SLOWER than one launch per iteration with programmatic dependent launch on the
 // config-2 batch (15.82 vs 15.57 ms per step): what the missing grid barrier saves (pass tails, launch ramp) is less
 // than what the per-strip waits, fences and L2-only waveform loads cost.  Hence opt-in.
-bool use_persistent() {
-    const char* e = getenv("S2ST_GL_PERSISTENT");
-    return e && e[0] == '1';
-}
-
-// S2ST_GL_PDL=0 launches the passes without programmatic dependent launch (A/B runs).
-bool use_pdl() {
-    const char* e = getenv("S2ST_GL_PDL");
-    return !(e && e[0] == '0');
-}
+// Persistent mode (S2ST_OPT_GL_PERSISTENT): -1 = automatic (default), 0 = never, 1 = whenever every strip is resident.
+// Automatic = persistent whenever the call is SMALL -- at most a quarter of the resident warps get a strip -- which is
+// the per-utterance shape of the reference's own call site (speech_generator_for_s2st.py:115-124): there a pass lasts a
+// few strip-frames (tens of microseconds), so the per-launch prologue (CTA start-up, 21 KB of constant tables, ring
+// clearing) and the launch gaps dominate, while the lightly loaded SMs make the neighbour waits cheap.  Results are
+// bitwise identical either way (test_persistent_mode_is_bitwise_identical).
 
 template <auto Kernel>
 int allow_dynamic_smem(size_t smem, int device) {
@@ -941,7 +962,7 @@ int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = use_pdl() ? 1 : 0;
+    cfg.numAttrs = p.pdl ? 1 : 0;
     S2ST_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gl_pass<NZ, FIRST, PRUNED, STD>, p));
     return S2ST_OK;
 }
@@ -965,10 +986,9 @@ int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* l
         return S2ST_EINVAL;
     }
     if (n_frames <= 0) return S2ST_OK;
-    // dense contraction -> tensor cores (tcgen05, 3xTF32) whenever the shape allows; S2ST_INVERSE_MEL=simt
+    // dense contraction -> tensor cores (tcgen05, 3xTF32) whenever the shape allows; S2ST_OPT_INVERSE_MEL = 1
     // selects the FP32 SIMT kernel (kept for other shapes and for A/B checks)
-    const char* mode_env = getenv("S2ST_INVERSE_MEL");
-    const bool force_simt = mode_env && mode_env[0] == 's';
+    const bool force_simt = plan->opt_inverse_mel_simt != 0;
     if (!force_simt && inverse_mel_tc_supported(plan) && ((uintptr_t)logmel & 15) == 0 &&
         (!slot_order || plan->inv_mel_tc_perm))
         return launch_inverse_mel_tc(plan, n_frames, logmel, is_log, mag, out_stride, n_out, stream,
@@ -1000,11 +1020,18 @@ int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* 
     return S2ST_OK;
 }
 
-int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const int32_t* frame_offsets,
+int launch_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double* u, float* phase, cudaStream_t stream) {
+    if (n_batch <= 0 || n_bins <= 0 || n_frames <= 0) return S2ST_OK;
+    dim3 grid((unsigned)((n_frames + 31) / 32), (unsigned)((n_bins + 31) / 32), (unsigned)n_batch);
+    k_phase_from_uniform<<<grid, 256, 0, stream>>>(u, n_bins, n_frames, phase);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
+
+int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* frame_offsets,
            const int32_t* frame_offsets_host, const float* logmel, const float* mag, int mag_kb, const float* phase,
            unsigned long long phase_seed, int n_iter, float* wave_out, void* workspace, size_t workspace_bytes,
            cudaStream_t stream) {
-    s2st_plan* plan = const_cast<s2st_plan*>(plan_c);  // only the profiling state is mutated
     if (n_utts <= 0 || total_frames < n_utts) {
         set_error("bad batch: n_utts=%d total_frames=%lld", n_utts, total_frames);
         return S2ST_EINVAL;
@@ -1025,6 +1052,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
 
     GlParams p;
     p.device = plan->device;
+    p.pdl = plan->opt_pdl;
     p.hop = plan->hop;
     p.half = plan->n_fft / 2;
     p.rot = plan->rot;
@@ -1050,7 +1078,7 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     // magnitude rows in its slot order; everything else keeps bin order and the packed-complex kernels
     const bool r64 = logmel && plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                      plan->n_fft == kNfft && plan->kb <= 32 * kPrunedRows && w.mag_stride == 32 * kPrunedRows &&
-                     plan->tw64 && plan->mag_perm && use_r64_kernel();
+                     plan->tw64 && plan->mag_perm && plan->opt_gl_kernel == 1;
     p.mag_perm = nullptr;
     if (logmel) {
         int rc = launch_inverse_mel(plan, total_frames, logmel, true, w.mag, w.mag_stride, w.mag_stride, stream, r64);
@@ -1079,12 +1107,13 @@ int gl_run(const s2st_plan* plan_c, int n_utts, long long total_frames, const in
     // resident warp of its own.  Needs the exact strip count, i.e. the host copy of the frame offsets.
     const bool std_geom0 = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                            plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
-    bool persist = std_geom0 && !r64 && n_iter >= 1 && frame_offsets_host && use_persistent();
+    const int pmode = plan->opt_persistent;
+    bool persist = std_geom0 && !r64 && n_iter >= 1 && frame_offsets_host && pmode != 0;
     plan->last_launches = 1 + (logmel ? 1 : 0) + (n_iter + 1);  // build_tiles, [inverse_mel], the passes
     if (persist) {
         long long strips = 0;
         for (int u = 0; u < n_utts; ++u) strips += (frame_offsets_host[u + 1] - frame_offsets_host[u] + S - 1) / S;
-        persist = strips <= (long long)grid * kGlWarps;
+        persist = pmode == 1 ? strips <= (long long)grid * kGlWarps : 4 * strips <= (long long)plan->num_sms * kGlWarps;
     }
     for (int it = 0; it <= n_iter; ++it) {
         p.in = ring[(it + 2) % 3];

@@ -41,6 +41,12 @@ struct s2st_plan {
     int mel_terms;
     // profiling aid (s2st_plan_set_pass_timing): CUDA events around every Griffin-Lim pass of the LAST call
     int strip_frames;             // 0 = choose per call (s2st_plan_set_strip_frames)
+    // options (s2st_plan_set_option; initialised ONCE at plan creation from the S2ST_* environment variables)
+    int opt_persistent;           // -1 = automatic, 0 = one launch per iteration, 1 = one persistent launch when possible
+    int opt_pdl;                  // programmatic dependent launch of the passes (default 1)
+    int opt_gl_kernel;            // 0 = packed-complex iteration kernel (default), 1 = real-FFT-64 formulation
+    int opt_inverse_mel_simt;     // 0 = tcgen05 inverse-mel (default), 1 = FP32 SIMT kernel
+    int opt_frontend_generic;     // 0 = register-resident log-mel kernel (default), 1 = generic k_stft path
     int last_launches;            // kernel launches of the last gl_run (0 before the first call)
     int timing_enabled;
     int timing_recorded;          // events recorded by the last gl_run (passes + 1), 0 if none
@@ -61,6 +67,7 @@ struct s2st_fbank_plan {
     // register-resident kernel (k_fbank_fast): -1 = not available for this rate, 0 = FFT 512 (one frame per
     // 256-point complex transform), 1 = FFT 256 (two frames per transform)
     int fast_mode;
+    int opt_generic;    // s2st_fbank_plan_set_option: 1 = run the generic kernel even where the fast one applies
     float2* tw16;       // [256] exp(-2 pi i k1 n2 / 256) at [k1 * 16 + n2]
     float2* vsplit;     // [256] -i exp(-2 pi i k / 512)
     float* winp;        // window in the kernel's register layout, zero padded (see FbankFastParams)
@@ -74,7 +81,7 @@ namespace s2st {
 
 // gl_kernels.cu
 size_t gl_workspace_bytes(const s2st_plan* plan, int n_utts, long long total_frames);
-int gl_run(const s2st_plan* plan, int n_utts, long long total_frames, const int32_t* frame_offsets,
+int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* frame_offsets,
            const int32_t* frame_offsets_host, const float* logmel, const float* mag, int mag_kb, const float* phase,
            unsigned long long phase_seed, int n_iter, float* wave_out, void* workspace, size_t workspace_bytes,
            cudaStream_t stream);
@@ -82,6 +89,7 @@ int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* l
                        int out_stride, int n_out, cudaStream_t stream, bool slot_order = false);
 int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* out, bool inverse,
                     cudaStream_t stream);
+int launch_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double* u, float* phase, cudaStream_t stream);
 
 // mel_tc.cu (tcgen05 tensor-core path of the inverse-mel projection)
 void build_inverse_mel_tc(const float* inv_mel, int kb, int K, float* out);

@@ -70,17 +70,22 @@ class StftPlan:
         kb = ctypes.c_int()
         _lib.check(lib.s2st_plan_active_bins(self.handle, ctypes.byref(kb)), "s2st_plan_active_bins")
         self.active_bins = kb.value
-        self._workspace = None
 
     def workspace(self, n_utts, total_frames):
+        """Scratch for ONE synthesis call (strip tables, magnitudes, two rotating waveform buffers), allocated per call
+        from torch's caching allocator on the caller's current stream.  The allocator hands a freed block back only to
+        work of the same stream, so calls on different streams / threads never share scratch, and a repeated call of
+        the same size gets its block back without a cudaMalloc."""
         lib = _lib.load()
         need = ctypes.c_size_t()
         _lib.check(lib.s2st_gl_workspace_bytes(self.handle, n_utts, total_frames, ctypes.byref(need)),
                    "s2st_gl_workspace_bytes")
-        if self._workspace is None or self._workspace.numel() < need.value:
-            self._workspace = None  # release before growing
-            self._workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
-        return self._workspace
+        with torch.cuda.device(self.device):
+            return torch.empty(need.value, dtype=torch.uint8, device=self.device)
+
+    def set_option(self, option, value):
+        """s2st_plan_set_option (keys: _lib.OPT_*)."""
+        _lib.check(_lib.load().s2st_plan_set_option(self.handle, int(option), int(value)), "s2st_plan_set_option")
 
     def gl_launch_count(self, n_iter, from_logmel=True):
         n = ctypes.c_int()
@@ -127,6 +132,10 @@ class FbankPlan:
         _lib.check(lib.s2st_fbank_frame_params(self.handle, ctypes.byref(w), ctypes.byref(s), ctypes.byref(p)),
                    "s2st_fbank_frame_params")
         self.win, self.shift, self.padded = w.value, s.value, p.value
+
+    def set_option(self, option, value):
+        _lib.check(_lib.load().s2st_fbank_plan_set_option(self.handle, int(option), int(value)),
+                   "s2st_fbank_plan_set_option")
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None

@@ -4,10 +4,11 @@ The reference shards synthesis with ``--num-shards N --shard-id i`` (independent
 examples/s2s_trans/generate_waveform.py:166-167) after sorting by source length
 (fairseq/data/audio/speech_to_text_dataset.py:358-366).  Here utterances are dealt by work
 (frames x iterations) with longest-processing-time-first, bucketed by length inside a rank, and the
-only exchange is the final ragged gather of waveforms (``gather_waveforms``), which works on any
-torch.distributed backend (NCCL on GPUs, gloo in the CPU tests).
+only exchange is the final ragged gather of waveforms to ONE rank (``gather_waveforms``: exact-size point-to-point
+messages in one group, no padded all-gather), which works on any torch.distributed backend (NCCL on GPUs, gloo in the
+CPU tests).
 """
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -31,12 +32,20 @@ def shard_utterances(n_frames: Sequence[int], world_size: int, n_iter: int = 64)
     return lpt_assign([t * (n_iter + 1) for t in n_frames], world_size)
 
 
-def length_buckets(n_frames: Sequence[int], indices: Sequence[int], max_frames: int) -> List[List[int]]:
-    """Sort ``indices`` by length and cut into batches of at most ``max_frames`` frames (>= 1 utterance)."""
+def length_buckets(n_frames: Sequence[int], indices: Sequence[int], max_frames: int, balanced: bool = False) -> List[List[int]]:
+    """Sort ``indices`` by length and cut into batches of at most ``max_frames`` frames (>= 1 utterance).
+
+    balanced: first fix the number of batches (ceil(total / max_frames)), then cut them to (nearly) equal frame
+    counts, so that no small remainder batch is left to under-fill the GPU."""
     order = sorted(indices, key=lambda i: (n_frames[i], i))
+    limit = max_frames
+    if balanced and order:
+        total = sum(n_frames[i] for i in order)
+        n_batches = max(1, -(-total // max_frames))
+        limit = min(max_frames, -(-total // n_batches) + max(n_frames[i] for i in order))
     batches, cur, cur_frames = [], [], 0
     for i in order:
-        if cur and cur_frames + n_frames[i] > max_frames:
+        if cur and cur_frames + n_frames[i] > limit:
             batches.append(cur)
             cur, cur_frames = [], 0
         cur.append(i)
@@ -47,46 +56,72 @@ def length_buckets(n_frames: Sequence[int], indices: Sequence[int], max_frames: 
 
 
 def gather_waveforms(local_ids: Sequence[int], local_waves: Sequence[torch.Tensor], n_total: int, dst: int = 0,
-                     group=None):
+                     group=None, stats: Optional[dict] = None):
     """Final ragged gather: rank ``dst`` receives every utterance's waveform in global order.
 
-    Lengths travel with an all_gather; the samples with one padded all_gather (a single collective,
-    96 KB per audio-second -- off the critical path).  Returns a list of n_total tensors on ``dst``,
-    ``None`` elsewhere.
-    """
+    The only exchange of the multi-GPU path (the reference's shards each write their own files,
+    generate_waveform.py:166-167).  Sizes travel with one small all_gather; the samples go point to point to ``dst``
+    ONLY -- every rank sends one exact-size payload (no padding), ``dst`` receives them into slices of one buffer, all
+    in one batched send/recv group (NCCL: ncclGroupStart/End; gloo in the CPU tests).  Returns a list of n_total
+    tensors (views into the receive buffer) on ``dst``, ``None`` elsewhere.  ``stats`` (optional dict) receives the
+    bytes that crossed the fabric."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    device = local_waves[0].device if len(local_waves) else torch.device(
-        "cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    meta = torch.tensor([len(local_ids), int(sum(w.numel() for w in local_waves))], dtype=torch.int64, device=device)
+    nccl = dist.get_backend(group) == "nccl"
+    device = local_waves[0].device if len(local_waves) else (
+        torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu"))
+    n_local = len(local_ids)
+    size_local = int(sum(w.numel() for w in local_waves))
+    meta = torch.tensor([n_local, size_local], dtype=torch.int64, device=device)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta, group=group)
     counts = [int(m[0]) for m in metas]
     sizes = [int(m[1]) for m in metas]
-    max_count, max_size = max(counts + [1]), max(sizes + [1])
-    idx = torch.full((2, max_count), -1, dtype=torch.int64, device=device)
-    if len(local_ids):
-        idx[0, : len(local_ids)] = torch.as_tensor(list(local_ids), dtype=torch.int64)
-        idx[1, : len(local_ids)] = torch.as_tensor([w.numel() for w in local_waves], dtype=torch.int64)
-    payload = torch.zeros(max_size, dtype=torch.float32, device=device)
-    if len(local_waves):
-        flat = torch.cat([w.reshape(-1).float() for w in local_waves])
-        payload[: flat.numel()] = flat
-    all_idx = [torch.zeros_like(idx) for _ in range(world)]
-    all_payload = [torch.zeros_like(payload) for _ in range(world)]
-    dist.all_gather(all_idx, idx, group=group)
-    dist.all_gather(all_payload, payload, group=group)
+    # (id, length) pairs are a second, tiny int64 message of the same group
+    idx = torch.empty(2, n_local, dtype=torch.int64, device=device)
+    if n_local:
+        idx[0] = torch.as_tensor(list(local_ids), dtype=torch.int64)
+        idx[1] = torch.as_tensor([w.numel() for w in local_waves], dtype=torch.int64)
+    flat = (torch.cat([w.reshape(-1).float() for w in local_waves]) if n_local
+            else torch.empty(0, dtype=torch.float32, device=device))
+    ops, recv_idx, recv_payload = [], {}, {}
+    if rank == dst:
+        for r in range(world):
+            if r == dst:
+                continue
+            recv_idx[r] = torch.empty(2, counts[r], dtype=torch.int64, device=device)
+            recv_payload[r] = torch.empty(sizes[r], dtype=torch.float32, device=device)
+            if counts[r]:
+                ops.append(dist.P2POp(dist.irecv, recv_idx[r], _global_rank(r, group), group))
+            if sizes[r]:
+                ops.append(dist.P2POp(dist.irecv, recv_payload[r], _global_rank(r, group), group))
+    else:
+        if n_local:
+            ops.append(dist.P2POp(dist.isend, idx, _global_rank(dst, group), group))
+        if size_local:
+            ops.append(dist.P2POp(dist.isend, flat, _global_rank(dst, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if stats is not None:
+        stats["bytes_to_dst"] = 4 * sum(sizes[r] for r in range(world) if r != dst)
+        stats["bytes_sent"] = 0 if rank == dst else 4 * size_local
     if rank != dst:
         return None
+    recv_idx[dst], recv_payload[dst] = idx, flat
     out = [None] * n_total
     for r in range(world):
-        ids = all_idx[r][0, : counts[r]].tolist()
-        lens = all_idx[r][1, : counts[r]].tolist()
+        ids = recv_idx[r][0].tolist()
+        lens = recv_idx[r][1].tolist()
         off = 0
         for i, n in zip(ids, lens):
-            out[i] = all_payload[r][off: off + n]
+            out[i] = recv_payload[r][off: off + n]
             off += n
     return out
+
+
+def _global_rank(group_rank: int, group) -> int:
+    return group_rank if group is None else dist.get_global_rank(group, group_rank)
 
 
 def imbalance(n_frames: Sequence[int], owned: List[List[int]]) -> float:

@@ -26,6 +26,25 @@ def draw_initial_phase(shape) -> np.ndarray:
     return np.angle(np.exp(2j * np.pi * np.random.rand(*shape))).astype(np.float32)
 
 
+def draw_initial_phase_device(shape, dev) -> torch.Tensor:
+    """The same draw with only the RNG on the host: ``np.random.rand(*shape)`` consumes numpy's GLOBAL generator
+    exactly like vocoder.py:103 (so ``np.random.seed(s)`` before ``forward`` reproduces the reference), the uniforms are
+    uploaded from pinned memory, and ``angle(exp(2j pi u))`` -- 40 of the 50 host milliseconds for a 500-frame utterance
+    -- becomes the closed form theta / theta - 2 pi in float64 on the device, written frame-major.
+    shape = (B,) F, T  ->  [B * T, F] float32 on ``dev``."""
+    u = np.random.rand(*shape)
+    B = shape[0] if len(shape) == 3 else 1
+    F, T = shape[-2], shape[-1]
+    staged = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
+    staged.numpy()[...] = u
+    phase = torch.empty(B * T, F, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        u_d = staged.to(dev, non_blocking=True)
+        rc = _lib.load().s2st_phase_from_uniform(B, F, T, _lib.ptr(u_d), _lib.ptr(phase), _lib.stream_ptr(dev))
+    _lib.check(rc, "s2st_phase_from_uniform")
+    return phase
+
+
 class PseudoInverseMelScale(torch.nn.Module):
     def __init__(self, n_stft, n_mels, sample_rate, f_min, f_max) -> None:
         super().__init__()
@@ -107,13 +126,12 @@ class GriffinLim(torch.nn.Module):
     def forward(self, specgram: torch.Tensor) -> torch.Tensor:
         """specgram [F, T] or [B, F, T] linear magnitudes -> waveform(s); random initial phase from the
         global numpy RNG exactly like the reference."""
-        angles = draw_initial_phase(specgram.shape)
         dev = require_cuda(specgram.device)
+        ph = draw_initial_phase_device(tuple(specgram.shape), dev)  # consumes numpy's global RNG first, like the reference
         spec = specgram.detach().reshape(-1, specgram.shape[-2], specgram.shape[-1])
         B, F, T = spec.shape
         _check_length(T, self.hop_length, self.n_fft, self.n_iter)
         mag = spec.to(dev, torch.float32).transpose(1, 2).reshape(B * T, F).contiguous()
-        ph = torch.from_numpy(np.ascontiguousarray(angles.reshape(B, F, T).transpose(0, 2, 1))).to(dev).reshape(B * T, F)
         wave = self._run(mag, ph, B, T, self.n_iter, dev)
         return wave.squeeze(0).to(specgram.device, specgram.dtype)
 
@@ -177,12 +195,11 @@ class GriffinLimVocoder(nn.Module):
         assert feats.shape[-1] == self.n_mels, (self.n_mels, feats.shape[-1])
         # initial phase: one draw of shape (B x) F x T from numpy's global RNG (vocoder.py:103)
         shape = ((B,) if batched else ()) + (g.n_fft // 2 + 1, T)
-        angles = draw_initial_phase(shape).reshape(B, g.n_fft // 2 + 1, T)
-        _check_length(T, g.hop_length, g.n_fft, g.n_iter)
         dev = self._device(feats)
-        phase_fm = torch.from_numpy(np.ascontiguousarray(angles.transpose(0, 2, 1)).reshape(B * T, -1))
+        phase_fm = draw_initial_phase_device(shape, dev)
+        _check_length(T, g.hop_length, g.n_fft, g.n_iter)
         waves = self._synthesize_flat(feats.reshape(B * T, self.n_mels).to(dev, torch.float32).contiguous(),
-                                      [T] * B, phase_fm.to(dev, non_blocking=True), g.n_iter, dev)
+                                      [T] * B, phase_fm, g.n_iter, dev)
         out = waves.view(B, -1)
         out = out.squeeze(0) if (not batched or B == 1) else out
         return out.to(x.device, x.dtype)

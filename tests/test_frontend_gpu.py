@@ -124,15 +124,18 @@ def test_fast_kernels_ragged_chunks_match_oracle_and_generic(pkg, built_lib, mon
     """The chunked kernels (k_fbank_fast: 16 frames per half-warp, two frames per transform at 8 kHz; k_logmel_fast:
     8 frames per warp) on batches whose utterances end inside chunks, have odd sample offsets (unaligned loads), odd
     frame counts and single frames -- against the oracle, and against the one-warp-per-frame kernels they replace."""
+    import importlib
+    plans = importlib.import_module(pkg.__name__ + ".plans")
     rng = np.random.RandomState(11)
     for sr, lens in ((8000, [200, 281, 8000, 199, 1000, 2763, 4001, 360]), (16000, [401, 7777, 400, 12345, 3001, 561])):
         waves = [(rng.randn(n) * 2000).astype(np.float32) for n in lens]
         mean, std = rng.randn(80).astype(np.float32), rng.uniform(0.5, 2, 80).astype(np.float32)
         outs = pkg.fbank_batch([torch.from_numpy(w) for w in waves], sr)
         fused = pkg.fbank_batch([torch.from_numpy(w) for w in waves], sr, cmvn_mean=mean, cmvn_std=std)
-        monkeypatch.setenv("S2ST_FBANK_GENERIC", "1")
+        fplan = plans.get_fbank_plan("cuda", sr, 80)
+        fplan.set_option(pkg._lib.OPT_FRONTEND_GENERIC, 1)
         generic = pkg.fbank_batch([torch.from_numpy(w) for w in waves], sr)
-        monkeypatch.delenv("S2ST_FBANK_GENERIC")
+        fplan.set_option(pkg._lib.OPT_FRONTEND_GENERIC, 0)
         for w, o, fo, g in zip(waves, outs, fused, generic):
             ref = ofe.kaldi_fbank(w, sr)
             assert o.shape == ref.shape == g.shape
@@ -143,9 +146,11 @@ def test_fast_kernels_ragged_chunks_match_oracle_and_generic(pkg, built_lib, mon
     lens = [1025, 3000, 1500, 24000, 2047, 7001, 1201]
     waves = [synth_audio(n, 24000, 30 + i) for i, n in enumerate(lens)]
     outs = pkg.logmel_batch([torch.from_numpy(w) for w in waves], f_min=20.0)
-    monkeypatch.setenv("S2ST_LOGMEL_GENERIC", "1")
+    lplan = plans.get_stft_plan("cuda", 2048, 1200, 300, 80, torch.hann_window(1200),
+                                mel=pkg.get_mel_filters(24000, 2048, 80, 20.0, 8000.0))
+    lplan.set_option(pkg._lib.OPT_FRONTEND_GENERIC, 1)
     generic = pkg.logmel_batch([torch.from_numpy(w) for w in waves], f_min=20.0)
-    monkeypatch.delenv("S2ST_LOGMEL_GENERIC")
+    lplan.set_option(pkg._lib.OPT_FRONTEND_GENERIC, 0)
     for w, o, g in zip(waves, outs, generic):
         ref = ofe.logmel_spectrogram(w)
         assert o.shape == ref.shape

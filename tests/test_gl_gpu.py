@@ -109,14 +109,14 @@ def test_inverse_mel_tensor_core_vs_simt_vs_oracle(pkg, voc, basis, monkeypatch)
         x = torch.cat([synth_logmel(n, 50 + n), ]).cuda()
         outs = {}
         for mode in ("simt", "tc"):
-            monkeypatch.setenv("S2ST_INVERSE_MEL", mode)
+            plan.set_option(pkg._lib.OPT_INVERSE_MEL, 1 if mode == "simt" else 0)
             out = torch.full((n, 1025), -1.0, device="cuda")
             rc = pkg._lib.load().s2st_inverse_mel(plan.handle, n, pkg._lib.ptr(x), 1, pkg._lib.ptr(out),
                                                   pkg._lib.stream_ptr(x.device))
             pkg._lib.check(rc, "s2st_inverse_mel")
             torch.cuda.synchronize()
             outs[mode] = out.cpu().numpy()
-        monkeypatch.delenv("S2ST_INVERSE_MEL")
+        plan.set_option(pkg._lib.OPT_INVERSE_MEL, 0)
         ref = ogl.inverse_mel(x.cpu().numpy(), basis).T
         for mode in ("simt", "tc"):
             assert np.all(outs[mode] >= 0) and np.all(outs[mode][:, 683:] == 0)
@@ -197,7 +197,7 @@ def test_ragged_batch_equals_per_utterance_and_oracle(pkg, voc, basis):
 
 
 def test_real_fft64_formulation_matches_golden_oracle_and_default_kernel(pkg, voc, basis, monkeypatch):
-    """S2ST_GL_KERNEL=r64 runs the iterations with the real-FFT-64 kernel (csrc/frame_r64.cuh: other transform
+    """S2ST_OPT_GL_KERNEL = 1 runs the iterations with the real-FFT-64 kernel (csrc/frame_r64.cuh: other transform
     factorisation, magnitudes kept in slot order, multiples-of-32 column split by the whole warp).  Same bar as
     the default kernel: golden vectors, oracle, ragged batch incl. strip seams and utterance edges, determinism."""
     g = load_golden("gl_small.npz")
@@ -205,7 +205,8 @@ def test_real_fft64_formulation_matches_golden_oracle_and_default_kernel(pkg, vo
     feats = [synth_logmel(T, 100 + i, "smooth" if i % 2 else "iid") for i, T in enumerate(frames)]
     phases = [seeded_phase(200 + i, T) for i, T in enumerate(frames)]
     base = voc.synthesize_batch([f.cuda() for f in feats], init_phase=phases, n_iter=16)
-    monkeypatch.setenv("S2ST_GL_KERNEL", "r64")
+    plan = voc._plan(torch.device("cuda", 0))
+    plan.set_option(pkg._lib.OPT_GL_KERNEL, 1)
     for case in ("c1", "c3"):
         x, n_iter, seed = g[case + "_logmel"], int(g[case + "_n_iter"]), int(g[case + "_seed"])
         voc.gl_transform.n_iter = n_iter
@@ -225,11 +226,12 @@ def test_real_fft64_formulation_matches_golden_oracle_and_default_kernel(pkg, vo
     # an all-silent utterance exercises the exact atan2(0, +-0) semantics in both the lanes and the column
     silent = torch.full((40, 80), -30.0)
     z = voc.synthesize_batch([silent.cuda()], init_phase=[seeded_phase(7, 40)], n_iter=4)[0]
+    plan.set_option(pkg._lib.OPT_GL_KERNEL, 0)
     assert torch.isfinite(z).all()
 
 
 def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
-    """S2ST_GL_PERSISTENT=1: all iterations in one cooperative launch, strips synchronising with their neighbours only
+    """Persistent mode: all iterations in one cooperative launch, strips synchronising with their neighbours only
     (no grid-wide barrier).  Same arithmetic, commuting seam reductions -> the waveforms must be bitwise equal to the
     default one-launch-per-iteration path, for ragged batches with single-strip, multi-strip and tail-strip utterances."""
     plan = voc._plan(torch.device("cuda", 0))
@@ -239,12 +241,14 @@ def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
     for strip in (0, 7):
         plan.set_strip_frames(strip)
         try:
+            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 0)
             base = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
-            monkeypatch.setenv("S2ST_GL_PERSISTENT", "1")
+            assert plan.gl_launch_count(12) == 2 + 13  # build_tiles, inverse_mel, 13 passes
+            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 1)
             pers = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
-            monkeypatch.delenv("S2ST_GL_PERSISTENT")
             assert plan.gl_launch_count(12) == 4  # build_tiles, inverse_mel, initial inverse, the persistent launch
         finally:
+            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, -1)
             plan.set_strip_frames(0)
         for a, b in zip(base, pers):
             assert torch.equal(a, b)
@@ -284,6 +288,94 @@ def test_full_size_properties_long_form(pkg, voc, basis):
     assert sc[0] > sc[1] > sc[2]
 
 
+@pytest.mark.parametrize("n_iter", [64, 256])
+def test_config5_long_form_vs_oracle(pkg, voc, basis, n_iter):
+    """BASELINE config 5: one 60 s utterance (4800 frames, ~185 strips) at 64 and at 256 iterations against the
+    oracle on the same seeded inputs -- the case that stresses overlap-add / window-sum normalisation and where seam
+    rounding could accumulate.  Tolerances are BASELINE.json's (waveform rel-L2 <= 1e-3, |dSC| <= 1e-4)."""
+    T = 4800
+    x = synth_logmel(T, 99)
+    phase = seeded_phase(7, T)
+    y = voc.synthesize_batch([x.cuda()], init_phase=[phase], n_iter=n_iter)[0].cpu().numpy()
+    ref = ogl.vocoder_forward(x.numpy(), phase, n_iter, basis=basis)
+    assert y.shape == ref.shape == ((T - 1) * 300,)
+    err = ogl.rel_l2(y, ref)
+    mag = ogl.inverse_mel(x.numpy(), basis)
+    d_sc = abs(ogl.spectral_convergence(y, mag, **CFG) - ogl.spectral_convergence(ref, mag, **CFG))
+    print(f"config5 n_iter={n_iter}: rel-L2 {err:.3e}, |dSC| {d_sc:.3e}")
+    assert err < 1e-3 and d_sc < 1e-4
+
+
+def _config2_picks(frames):
+    """(first frame, T) of the shortest, the median and the longest utterance of the length-sorted batch."""
+    fo = np.concatenate([[0], np.cumsum(frames)])
+    return [(i, int(fo[i]), frames[i]) for i in (0, len(frames) // 2, len(frames) - 1)]
+
+
+def test_config2_full_batch_vs_oracle(pkg, voc, basis):
+    """BASELINE config 2 at full shape: the real 256-utterance bench batch (bench.config2_batch), automatic strip
+    length, 64 iterations; the shortest, the median and the LONGEST utterance against the oracle -- through the
+    device-resident entry and through synthesize_host with the phase supplied from the host (the e2e path)."""
+    import bench
+    frames, logmel, phase = bench.config2_batch(0)
+    total = int(sum(frames))
+    assert len(frames) == 256 and frames[0] >= 56 and frames[-1] <= 400
+    wave = voc.synthesize_flat(torch.from_numpy(logmel).cuda(), frames, torch.from_numpy(phase).cuda(), n_iter=64)
+    wave_h = torch.zeros((total - len(frames)) * 300).pin_memory()
+    voc.synthesize_host(torch.from_numpy(logmel).pin_memory(), frames, wave_h, phase_host=torch.from_numpy(phase).pin_memory(),
+                        n_iter=64).synchronize()
+    assert torch.equal(wave.cpu(), wave_h)  # same kernels, same strip length: bitwise
+    wave = wave.cpu().numpy()
+    for i, f0, T in _config2_picks(frames):
+        w0 = (f0 - i) * 300
+        y = wave[w0: w0 + (T - 1) * 300]
+        x, ph = logmel[f0: f0 + T], np.ascontiguousarray(phase[f0: f0 + T].T)
+        ref = ogl.vocoder_forward(x, ph, 64, basis=basis)
+        mag = ogl.inverse_mel(x, basis)
+        err = ogl.rel_l2(y, ref)
+        d_sc = abs(ogl.spectral_convergence(y, mag, **CFG) - ogl.spectral_convergence(ref, mag, **CFG))
+        print(f"config2 utterance {i} (T={T}): rel-L2 {err:.3e}, |dSC| {d_sc:.3e}")
+        assert err < 1e-3 and d_sc < 1e-4, (i, T, err, d_sc)
+
+
+def test_config4_bucket_vs_oracle(pkg, voc, basis):
+    """BASELINE config 4: the 10k-utterance list is sharded and cut into length buckets (bench.run_gl_sharded); the
+    buckets that hold the shortest and the longest utterance of rank 0's shard at world size 8, synthesised exactly as
+    the bench does, against the oracle.  Also: an utterance's waveform does not depend on the sharding (world 8 vs 2)
+    beyond rounding noise (the automatic strip length follows the bucket)."""
+    import importlib
+
+    import bench
+    sh = importlib.import_module(pkg.__name__ + ".sharding")
+    frames_all = bench.sharded_frames(0)
+    owned8 = sh.shard_utterances(frames_all, 8, 64)
+    b8 = sh.length_buckets(frames_all, owned8[0], bench.BUCKET_FRAMES, balanced=True)
+
+    def run_bucket(b):
+        fr = [frames_all[i] for i in b]
+        xs, ps = zip(*(bench.sharded_utterance_inputs(i, frames_all[i]) for i in b))
+        w = voc.synthesize_flat(torch.from_numpy(np.concatenate(xs)).cuda(), fr, torch.from_numpy(np.concatenate(ps)).cuda(), n_iter=64)
+        return dict(zip(b, torch.split(w, [(T - 1) * 300 for T in fr])))
+
+    out8 = run_bucket(b8[0])
+    if len(b8) > 1:
+        out8.update(run_bucket(b8[-1]))
+    ids = sorted(out8, key=lambda i: (frames_all[i], i))
+    for i in (ids[0], ids[-1]):
+        x, p = bench.sharded_utterance_inputs(i, frames_all[i])
+        ref = ogl.vocoder_forward(x, np.ascontiguousarray(p.T), 64, basis=basis)
+        err = ogl.rel_l2(out8[i].cpu().numpy(), ref)
+        print(f"config4 utterance {i} (T={frames_all[i]}): rel-L2 {err:.3e}")
+        assert err < 1e-3
+    # the same utterance inside a different bucket (a 2-rank sharding puts it among other neighbours)
+    i = ids[-1]
+    owned2 = sh.shard_utterances(frames_all, 2, 64)
+    r = 0 if i in owned2[0] else 1
+    b2 = [b for b in sh.length_buckets(frames_all, owned2[r], bench.BUCKET_FRAMES, balanced=True) if i in b][0]
+    out2 = run_bucket(b2)
+    assert ogl.rel_l2(out2[i].cpu().numpy(), out8[i].cpu().numpy()) < 1e-4
+
+
 def test_device_drawn_initial_phase(pkg, voc, basis):
     """phase_fm=None: U[-pi, pi) drawn on the device.  Deterministic per seed, different across seeds, and
     statistically equivalent to the host draw: same spectral convergence after the iterations (it is a
@@ -309,6 +401,23 @@ def test_device_drawn_initial_phase(pkg, voc, basis):
     ph = torch.from_numpy(np.concatenate([seeded_phase(60 + i, T).T for i, T in enumerate(frames)])).cuda()
     e_host = float(voc.synthesize_flat(flat, frames, ph.contiguous(), n_iter=0).pow(2).mean())
     assert abs(e_dev - e_host) < 0.1 * e_host
+
+
+def test_initial_phase_on_device_equals_host_draw(pkg, voc):
+    """forward() keeps numpy's global RNG draw on the host and evaluates angle(exp(2j pi u)) on the device
+    (s2st_phase_from_uniform): same RNG consumption, bitwise the same float32 phases as vocoder.py:103, frame-major."""
+    import importlib
+    vm = importlib.import_module(pkg.__name__ + ".vocoder")
+    for shape in ((1025, 37), (2, 1025, 50), (3, 33, 5)):
+        np.random.seed(5)
+        host = vm.draw_initial_phase(shape)
+        after_host = np.random.rand()
+        np.random.seed(5)
+        dev = vm.draw_initial_phase_device(shape, torch.device("cuda", 0)).cpu().numpy()
+        assert np.random.rand() == after_host  # the same amount of the global stream was consumed
+        F, T = shape[-2], shape[-1]
+        want = host.reshape(-1, F, T).transpose(0, 2, 1).reshape(-1, F)
+        assert dev.shape == want.shape and np.array_equal(dev, want)
 
 
 def test_half_precision_io(pkg, voc):

@@ -39,6 +39,14 @@ def test_length_buckets(pkg):
     assert sorted(i for x in b for i in x) == list(range(6))
     assert all(sum(frames[i] for i in x) <= 500 or len(x) == 1 for x in b)
     assert [frames[i] for x in b for i in x] == sorted(frames)
+    # balanced: the number of batches is fixed first, then they are cut evenly (no small remainder batch)
+    rng = np.random.RandomState(1)
+    frames = rng.randint(56, 401, size=3000).tolist()
+    total = sum(frames)
+    b = sh.length_buckets(frames, range(3000), max_frames=300000, balanced=True)
+    sizes = [sum(frames[i] for i in x) for x in b]
+    assert len(b) == -(-total // 300000) and max(sizes) <= 300000 and min(sizes) > 0.9 * max(sizes)
+    assert sorted(i for x in b for i in x) == list(range(3000))
 
 
 def _worker(rank, world, port, q):
@@ -59,8 +67,68 @@ def _worker(rank, world, port, q):
         q.put(ok)
     else:
         assert out is None
+    # a rank with nothing to send, and a non-zero destination
+    mine2 = list(range(len(frames))) if rank == 0 else []
+    waves2 = [torch.full((frames[i],), float(i)) for i in mine2]
+    st = {}
+    out2 = sh.gather_waveforms(mine2, waves2, len(frames), dst=1, stats=st)
+    if rank == 1:
+        assert all(out2[i].numel() == frames[i] and float(out2[i][-1]) == float(i) for i in range(len(frames)))
+        assert st["bytes_to_dst"] == 4 * sum(frames)
+    else:
+        assert out2 is None and st["bytes_sent"] == 4 * sum(frames)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _nccl_worker(rank, world, port, q):
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    pkg = importlib.import_module(PKG)
+    sh = importlib.import_module(PKG + ".sharding")
+    from conftest import seeded_phase, synth_logmel
+    voc = pkg.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window, spec_bwd_max_iter=8).cuda()
+    frames = [40, 9, 77, 56, 120, 33, 64]
+    owned = sh.shard_utterances(frames, world, n_iter=8)
+    mine = owned[rank]
+    feats = [synth_logmel(frames[i], 700 + i).cuda() for i in mine]
+    phases = [seeded_phase(800 + i, frames[i]) for i in mine]
+    waves = voc.synthesize_batch(feats, init_phase=phases, n_iter=8)
+    out = sh.gather_waveforms(mine, waves, len(frames), dst=0)
+    if rank == 0:
+        # every utterance, wherever it was synthesised, must equal the single-GPU result bitwise (same strip length)
+        ok = True
+        for i, T in enumerate(frames):
+            alone = voc.synthesize_batch([synth_logmel(T, 700 + i).cuda()], init_phase=[seeded_phase(800 + i, T)], n_iter=8)[0]
+            ok = ok and out[i].is_cuda and out[i].shape == ((T - 1) * 300,) and bool(torch.equal(out[i], alone))
+        q.put(ok)
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_synthesis_and_gather_nccl_world2(built_lib):
+    """Two GPUs: LPT sharding -> per-rank ragged synthesis -> point-to-point gather over NCCL (needs >= 2 devices;
+    run with `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get() is True
 
 
 def test_gather_waveforms_gloo_world2():
