@@ -170,10 +170,10 @@ def test_product_never_imports_oracle():
 def test_closed_form_initial_phase_equals_reference_expression():
     """s2st_phase_from_uniform evaluates angle(exp(2j pi u)) (vocoder.py:103) as theta / theta - 2 pi in float64 with a
     two-term 2 pi; this numpy restatement of that arithmetic equals the reference expression after the float32 cast on
-    4 M draws (the float64 values differ by < 3e-16)."""
+    4 M draws (the float64 values differ by at most one ulp)."""
     u = np.random.RandomState(0).rand(4_000_000)
     ref64 = np.angle(np.exp(2j * np.pi * u))
     th = 6.283185307179586 * u
     cf64 = np.where(th > 3.141592653589793, (th - 6.283185307179586) - 2.4492935982947064e-16, th)
-    assert np.abs(cf64 - ref64).max() < 3e-16
+    assert np.abs(cf64 - ref64).max() < 5e-16  # one ulp at |phase| in [2, pi]
     assert int((cf64.astype(np.float32) != ref64.astype(np.float32)).sum()) == 0
