@@ -1,4 +1,5 @@
-"""Latency of small synthesis calls (config 1: one 500-frame utterance; one 60 s utterance), device-resident."""
+"""Latency of small synthesis calls (config 1: one 500-frame utterance; a 100-frame one; one 60 s utterance; 8 and 32
+utterances of ~230 frames), device-resident, one launch per iteration vs the persistent single launch vs automatic."""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -6,13 +7,25 @@ sys.path.insert(0, ROOT)
 import bench
 pkg = importlib.import_module(bench.PKG)
 voc = pkg.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window, spec_bwd_max_iter=64).cuda()
-for T in (100, 500, 4800):
-    x = torch.from_numpy(bench.synth_logmel_np(T, 1)).cuda()
-    for _ in range(3): voc.synthesize_flat(x, [T], None, seed=1)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): voc.synthesize_flat(x, [T], None, seed=1)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"T={T:5d}  {ms:.3f} ms per 64-iteration call  {(T - 1) * 300 / 24000 / (ms * 1e-3):.0f} audio-s/s  {ms / 65 * 1e3:.1f} us per pass")
+plan = voc._plan(torch.device("cuda", 0))
+cases = [("T=100", [100]), ("T=500", [500]), ("T=4800", [4800]), ("8x230", [230] * 8), ("32x230", [230] * 32), ("128x230", [230] * 128)]
+for name, frames in cases:
+    total = sum(frames)
+    x = torch.from_numpy(np.concatenate([bench.synth_logmel_np(T, 1 + i) for i, T in enumerate(frames)])).cuda()
+    ph = ((torch.rand(total, 1025, device="cuda") * 2 - 1) * np.pi).contiguous()
+    res, outs = [], []
+    for mode in (0, 1, -1):
+        plan.set_option(pkg._lib.OPT_GL_PERSISTENT, mode)
+        for _ in range(3): y = voc.synthesize_flat(x, frames, ph)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): y = voc.synthesize_flat(x, frames, ph)
+        e1.record(); torch.cuda.synchronize()
+        res.append((e0.elapsed_time(e1) / 10, plan.gl_launch_count(64)))
+        outs.append(y)
+    audio = (total - len(frames)) * 300 / 24000
+    print(f"{name:8s} per-iteration launches {res[0][0]:.3f} ms ({audio / res[0][0] * 1e3:.0f} audio-s/s) | persistent {res[1][0]:.3f} ms "
+          f"({audio / res[1][0] * 1e3:.0f}, {res[1][1]} launches) | auto {res[2][0]:.3f} ms ({res[2][1]} launches) | bitwise equal "
+          f"{bool(torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]))}")
+plan.set_option(pkg._lib.OPT_GL_PERSISTENT, -1)
