@@ -776,7 +776,7 @@ def run_frontend(args, ctx):
         o = torch.empty(total, 80, device=dev)
 
         def run(src=flat, dst=o):
-            check(lib.s2st_fbank(plan.handle, n, total, ptr(wo), ptr(fo), ptr(src), ptr(mean), ptr(std), ptr(dst),
+            check(lib.s2st_fbank(plan.handle, n, total, ptr(wo), ptr(fo), ptr(src), ptr(mean), ptr(std), None, ptr(dst),
                                  sptr(dev)), "s2st_fbank")
         return run, float(lens.sum()) / sr, total, flat, o
 
@@ -820,7 +820,7 @@ def run_frontend(args, ctx):
 
     def runl():
         check(lib.s2st_logmel(planl.handle, n_side, total, ptr(wo), ptr(fo), ptr(flat), 1e-5, ptr(mean), ptr(std),
-                              ptr(o), sptr(dev)), "s2st_logmel")
+                              None, ptr(o), sptr(dev)), "s2st_logmel")
     for _ in range(3):
         runl()
     msl, _ = ctx.timed(runl, max(3, args.steps // 2))
@@ -890,7 +890,7 @@ def frontend_e2e(ctx, lib, pkg, plans, flat_h, out_h, n_utts, sr, mean, std, n_c
             main.wait_stream(up)
             src.record_stream(main)
             dst = torch.empty(total, 80, device=dev)
-            check(lib.s2st_fbank(plan.handle, n, total, ptr(wo), ptr(fo), ptr(src), ptr(mean), ptr(std), ptr(dst),
+            check(lib.s2st_fbank(plan.handle, n, total, ptr(wo), ptr(fo), ptr(src), ptr(mean), ptr(std), None, ptr(dst),
                                  ctypes_stream(main)), "s2st_fbank")
             down.wait_stream(main)
             with torch.cuda.stream(down):

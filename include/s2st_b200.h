@@ -170,11 +170,16 @@ int s2st_window_sum_square(int n_frames, int hop_length, int win_length, int n_f
 /* logmelspec80: extract_logmel_spectrogram (examples/speech_synthesis/data_utils.py:46-76):
  *   out[t, m] = log(max(eps, sum_f mel[m, f] * |STFT(wave)|[t, f])), optionally followed by
  *   global CMVN (feature_transforms/global_cmvn.py:26-29) when cmvn_mean_dev != NULL.
- *   Same ragged layout as s2st_stft; out_dev [total_frames, n_mels]. */
+ *   Same ragged layout as s2st_stft; out_dev [total_frames, n_mels].
+ *   sums_dev (optional, NULL to skip): double [2, n_mels], the accumulators of get_global_cmvn
+ *   (examples/speech_synthesis/data_utils.py:190-220) fused into the extraction -- the kernel ADDS
+ *   (sum_t x, sum_t x^2) of the features it produces (before the CMVN, if any) to it, so the corpus is not
+ *   read a second time for its statistics.  The caller zeroes it once and finishes mean / std on the host
+ *   (double accumulation: the reference's float32 running sums are reproduced by s2st_utterance_sums). */
 int s2st_logmel(const s2st_plan* plan, int n_utts, int64_t total_frames,
                 const int64_t* wave_offsets_dev, const int32_t* frame_offsets_dev,
                 const float* wave_dev, float eps, const float* cmvn_mean_dev,
-                const float* cmvn_std_dev, float* out_dev, void* stream);
+                const float* cmvn_std_dev, double* sums_dev, float* out_dev, void* stream);
 
 /* fbank80: _get_torchaudio_fbank (audio_utils.py:136-149) == torchaudio.compliance.kaldi.fbank with
  * num_mel_bins = n_bins, sample_frequency = sample_rate and every other option at its default.
@@ -187,11 +192,11 @@ int s2st_fbank_plan_set_option(s2st_fbank_plan* plan, int option, int value);
 /* window size / shift / padded FFT size of the plan: m_i = 1 + (n_i - win) / shift (0 if n_i < win) */
 int s2st_fbank_frame_params(const s2st_fbank_plan* plan, int* win_out, int* shift_out, int* padded_out);
 /*   wave_dev is the int16-scaled waveform (audio_utils.py:105-106); out_dev [total_frames, n_bins];
- *   optional fused global CMVN as above. */
+ *   optional fused global CMVN and optional fused statistics (sums_dev double [2, n_bins]) as above. */
 int s2st_fbank(const s2st_fbank_plan* plan, int n_utts, int64_t total_frames,
                const int64_t* wave_offsets_dev, const int32_t* frame_offsets_dev,
                const float* wave_dev, const float* cmvn_mean_dev, const float* cmvn_std_dev,
-               float* out_dev, void* stream);
+               double* sums_dev, float* out_dev, void* stream);
 
 /* GlobalCMVN.__call__ (feature_transforms/global_cmvn.py:26-29): out = (x - mean) / std, and its
  * inverse gcmvn_denormalize (fairseq/speech_generator_for_s2st.py:21-29): out = x * std + mean.
@@ -214,6 +219,13 @@ int s2st_cmvn_accumulate(int64_t n_rows, int n_cols, const float* x_dev, double*
 int s2st_utterance_cmvn(int n_utts, int64_t total_rows, const int32_t* frame_offsets_dev, int n_cols,
                         const float* x_dev, int norm_means, int norm_vars, float* out_dev, float* stats_dev,
                         void* stream);
+/* The per-file terms of get_global_cmvn (examples/speech_synthesis/data_utils.py:197-208): for every utterance (= one
+ * .npy file of the feature directory) cur_mean_x = frames.sum(axis=0) and cur_mean_x2 = (frames ** 2).sum(axis=0),
+ * accumulated in float32 in row order without FMA contraction, exactly as numpy reduces a C-contiguous [T, n] array
+ * over axis 0: bit-identical to the reference.  sums_dev float32 [n_utts, 2, n_cols] = (sum, sum of squares); the host
+ * shim adds the files up in the reference's order (float32) and finishes mean / std. */
+int s2st_utterance_sums(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev,
+                        float* sums_dev, void* stream);
 /* Per-utterance sum of all elements (double): the "local mean" mask value of SpecAugmentTransform
  * (feature_transforms/specaugment.py:88-89) is sums_dev[u] / (T_u * n_cols). */
 int s2st_utterance_sum(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev,

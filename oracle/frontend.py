@@ -88,6 +88,29 @@ def global_cmvn_stats(feature_list):
     return {"mean": mean, "std": np.sqrt(np.maximum(var, 1e-10))}
 
 
+def get_global_cmvn(file_arrays):
+    """examples/speech_synthesis/data_utils.py:190-220, statement for statement, over the already loaded (and squeezed)
+    arrays in the order the reference's glob visited them: in-place float32 running sums, in-place divisions."""
+    mean_x, mean_x2, n_frames = None, None, 0
+    for frames in file_arrays:
+        frames = np.asarray(frames).squeeze()
+        n_frames += frames.shape[0]
+        cur_mean_x = frames.sum(axis=0)
+        if mean_x is None:
+            mean_x = cur_mean_x
+        else:
+            mean_x += cur_mean_x
+        cur_mean_x2 = (frames ** 2).sum(axis=0)
+        if mean_x2 is None:
+            mean_x2 = cur_mean_x2
+        else:
+            mean_x2 += cur_mean_x2
+    mean_x /= n_frames
+    mean_x2 /= n_frames
+    var_x = mean_x2 - mean_x ** 2
+    return {"mean": mean_x, "std": np.sqrt(np.maximum(var_x, 1e-10))}
+
+
 def utterance_cmvn(x, norm_means=True, norm_vars=True):
     """feature_transforms/utterance_cmvn.py:29-40, statement for statement (numpy float32 arithmetic)."""
     mean = x.mean(axis=0)

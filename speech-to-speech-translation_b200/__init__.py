@@ -20,7 +20,7 @@ from .feature_transforms.global_cmvn import GlobalCMVN, SRCGlobalCMVN, TGTGlobal
 from .feature_transforms.specaugment import SpecAugmentTransform  # noqa: F401
 from .feature_transforms.utterance_cmvn import UtteranceCMVN  # noqa: F401
 from .features import (extract_fbank_features, extract_logmel_spectrogram, gcmvn_denormalize,  # noqa: F401
-                       global_cmvn_stats, logmel_batch)
+                       get_global_cmvn, global_cmvn_from_sums, global_cmvn_stats, logmel_batch)
 from .vocoder import GriffinLim, GriffinLimVocoder, PseudoInverseMelScale, get_vocoder  # noqa: F401
 
 __version__ = "0.1.0"

@@ -73,6 +73,14 @@ def get_mel_filters(sample_rate: int, n_fft: int, n_mels: int, f_min: float, f_m
     return (tri * (2.0 / (right - left))).float()
 
 
+def _stats_ptr(stats, n_cols, dev):
+    if stats is None:
+        return None
+    assert stats.is_cuda and stats.dtype == torch.float64 and tuple(stats.shape) == (2, n_cols) and stats.is_contiguous()
+    assert stats.device == dev, "the statistics accumulator must live on the extraction device"
+    return _lib.ptr(stats)
+
+
 def _ragged_offsets(lengths, hop, device):
     """frame_offsets (int32) and wave_offsets (int64) device tensors for waveforms of ``lengths``."""
     frames = [1 + n // hop for n in lengths]
@@ -169,11 +177,13 @@ def get_waveform(path_or_fp: Union[str, BinaryIO], normalization: bool = True, m
     return waveform, sample_rate
 
 
-def fbank_batch(waveforms, sample_rate: int, n_bins: int = 80, cmvn_mean=None, cmvn_std=None, device=None):
+def fbank_batch(waveforms, sample_rate: int, n_bins: int = 80, cmvn_mean=None, cmvn_std=None, device=None, stats=None):
     """Kaldi fbank for a list of 1-D int16-scaled float waveforms (tensors on any device, or numpy).
 
     Returns a list of [m_i, n_bins] float32 CUDA tensors (m_i = 1 + (n_i - win) // shift, 0 if too short);
     optional fused global CMVN.  This is the batched (data-parallel) form of ``_get_torchaudio_fbank``.
+    ``stats``: optional float64 CUDA tensor [2, n_bins]; the kernel adds (sum, sum of squares) of the features (before
+    any CMVN) to it -- the accumulators of ``get_global_cmvn`` without a second pass over the corpus.
     """
     dev = require_cuda(device if device is not None else (waveforms[0].device if isinstance(waveforms[0], torch.Tensor) else None))
     plan = get_fbank_plan(dev, sample_rate, n_bins)
@@ -193,7 +203,8 @@ def fbank_batch(waveforms, sample_rate: int, n_bins: int = 80, cmvn_mean=None, c
         std_d = None if cmvn_std is None else torch.as_tensor(cmvn_std).to(dev, torch.float32).contiguous()
         with torch.cuda.device(dev):
             rc = _lib.load().s2st_fbank(plan.handle, len(waves), total, _lib.ptr(wo_d), _lib.ptr(fo_d), _lib.ptr(flat),
-                                        _lib.ptr(mean_d), _lib.ptr(std_d), _lib.ptr(out), _lib.stream_ptr(dev))
+                                        _lib.ptr(mean_d), _lib.ptr(std_d), _stats_ptr(stats, n_bins, dev), _lib.ptr(out),
+                                        _lib.stream_ptr(dev))
         _lib.check(rc, "s2st_fbank")
     return [out[fo[i]: fo[i + 1]] for i in range(len(waves))]
 

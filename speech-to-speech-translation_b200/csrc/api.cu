@@ -136,6 +136,7 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         return S2ST_EINVAL;
     }
     s2st_plan* p = new s2st_plan();
+    std::memset(p, 0, sizeof(*p));
     {   // options: the S2ST_* environment variables are read HERE, once; afterwards only s2st_plan_set_option changes them
         const char* e = getenv("S2ST_GL_PERSISTENT");
         p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == '0') ? 0 : -1;
@@ -147,7 +148,6 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         p->opt_inverse_mel_simt = (e && e[0] == 's') ? 1 : 0;
         p->opt_frontend_generic = getenv("S2ST_LOGMEL_GENERIC") ? 1 : 0;
     }
-    std::memset(p, 0, sizeof(*p));
     p->device = device;
     p->n_fft = n_fft;
     p->win_length = win_length;
@@ -578,14 +578,14 @@ int s2st_window_sum_square(int n_frames, int hop_length, int win_length, int n_f
 
 int s2st_logmel(const s2st_plan* plan, int n_utts, int64_t total_frames, const int64_t* wave_offsets_dev,
                 const int32_t* frame_offsets_dev, const float* wave_dev, float eps,
-                const float* cmvn_mean_dev, const float* cmvn_std_dev, float* out_dev, void* stream) {
+                const float* cmvn_mean_dev, const float* cmvn_std_dev, double* sums_dev, float* out_dev, void* stream) {
     if (!plan || !wave_offsets_dev || !frame_offsets_dev || !wave_dev || !out_dev || n_utts <= 0 ||
         ((cmvn_mean_dev == nullptr) != (cmvn_std_dev == nullptr))) {
         set_error("bad argument to s2st_logmel");
         return S2ST_EINVAL;
     }
     return launch_stft(plan, n_utts, total_frames, wave_offsets_dev, frame_offsets_dev, wave_dev, nullptr, nullptr,
-                       out_dev, eps, cmvn_mean_dev, cmvn_std_dev, static_cast<cudaStream_t>(stream));
+                       out_dev, eps, cmvn_mean_dev, cmvn_std_dev, static_cast<cudaStream_t>(stream), sums_dev);
 }
 
 int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_rate, int n_bins) {
@@ -610,8 +610,8 @@ int s2st_fbank_plan_create(s2st_fbank_plan** plan_out, int device, int sample_ra
         return S2ST_EINVAL;
     }
     s2st_fbank_plan* p = new s2st_fbank_plan();
-    p->opt_generic = getenv("S2ST_FBANK_GENERIC") ? 1 : 0;  // read once, here
     std::memset(p, 0, sizeof(*p));
+    p->opt_generic = getenv("S2ST_FBANK_GENERIC") ? 1 : 0;  // read once, here
     p->device = device;
     p->sample_rate = sample_rate;
     p->n_bins = n_bins;
@@ -822,14 +822,14 @@ int s2st_fbank_frame_params(const s2st_fbank_plan* plan, int* win_out, int* shif
 
 int s2st_fbank(const s2st_fbank_plan* plan, int n_utts, int64_t total_frames, const int64_t* wave_offsets_dev,
                const int32_t* frame_offsets_dev, const float* wave_dev, const float* cmvn_mean_dev,
-               const float* cmvn_std_dev, float* out_dev, void* stream) {
+               const float* cmvn_std_dev, double* sums_dev, float* out_dev, void* stream) {
     if (!plan || !wave_offsets_dev || !frame_offsets_dev || !wave_dev || !out_dev || n_utts <= 0 ||
         ((cmvn_mean_dev == nullptr) != (cmvn_std_dev == nullptr))) {
         set_error("bad argument to s2st_fbank");
         return S2ST_EINVAL;
     }
     return launch_fbank(plan, n_utts, total_frames, wave_offsets_dev, frame_offsets_dev, wave_dev, cmvn_mean_dev,
-                        cmvn_std_dev, out_dev, static_cast<cudaStream_t>(stream));
+                        cmvn_std_dev, out_dev, static_cast<cudaStream_t>(stream), sums_dev);
 }
 
 int s2st_cmvn_apply(int64_t n_rows, int n_cols, const float* x_dev, const float* mean_dev, const float* std_dev,
@@ -867,6 +867,15 @@ int s2st_utterance_cmvn(int n_utts, int64_t total_rows, const int32_t* frame_off
     }
     return launch_utterance_cmvn(n_utts, total_rows, frame_offsets_dev, n_cols, x_dev, out_dev, norm_means != 0,
                                  norm_vars != 0, stats_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2st_utterance_sums(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev, float* sums_dev,
+                        void* stream) {
+    if (n_utts < 0 || n_cols <= 0 || (n_utts > 0 && (!frame_offsets_dev || !x_dev || !sums_dev))) {
+        set_error("bad argument to s2st_utterance_sums");
+        return S2ST_EINVAL;
+    }
+    return launch_utterance_sums(n_utts, frame_offsets_dev, n_cols, x_dev, sums_dev, static_cast<cudaStream_t>(stream));
 }
 
 int s2st_utterance_sum(int n_utts, const int32_t* frame_offsets_dev, int n_cols, const float* x_dev, double* sums_dev,

@@ -60,6 +60,7 @@ struct StftParams {
     float eps;
     const float* cmvn_mean;
     const float* cmvn_std;
+    double* sums;           // optional [2][n_mels]: += (sum, sum of squares) of the features BEFORE the CMVN
     const int* mel_ptr;
     const int* mel_idx;
     const float* mel_val;
@@ -139,6 +140,10 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
                 for (int e = __ldg(p.mel_ptr + m); e < e1; ++e)
                     acc = fmaf(__ldg(p.mel_val + e), spec[__ldg(p.mel_idx + e)], acc);
                 float v = logf(fmaxf(acc, p.eps));
+                if (p.sums) {  // generic path: straight to the accumulators (the fast kernels keep per-warp partials)
+                    atomicAdd(p.sums + m, (double)v);
+                    atomicAdd(p.sums + p.n_mels + m, (double)v * (double)v);
+                }
                 if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
                 p.logmel_out[f * p.n_mels + m] = v;
             }
@@ -146,6 +151,48 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
         }
     }
 }
+
+// Fused global-CMVN statistics (get_global_cmvn, examples/speech_synthesis/data_utils.py:190-220, without re-reading
+// the corpus): a lane keeps float partial sums of the features it writes over one chunk of frames (8 or 16), folds them
+// into a per-block double accumulator in shared memory at the end of the chunk, and the block adds that to
+// sums[2][n] once at the end of the launch (one double atomicAdd per block and feature).
+constexpr int kMaxStatCols = 128;
+template <int N>
+struct FeatureSums {
+    float s[N], q[N];
+    __device__ __forceinline__ void init(double* s_sums) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i] = q[i] = 0.0f;
+        for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += blockDim.x) s_sums[i] = 0.0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void add(int i, float v) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (k == i) {
+                s[k] += v;
+                q[k] = fmaf(v, v, q[k]);
+            }
+    }
+    __device__ __forceinline__ void fold(double* s_sums, int first, int stride, int n) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int m = first + stride * i;
+            if (m < n) {
+                atomicAdd(s_sums + m, (double)s[i]);
+                atomicAdd(s_sums + kMaxStatCols + m, (double)q[i]);
+            }
+            s[i] = q[i] = 0.0f;
+        }
+    }
+    static __device__ __forceinline__ void flush(const double* s_sums, double* sums, int n) {
+        __syncthreads();
+        for (int m = threadIdx.x; m < n; m += blockDim.x) {
+            atomicAdd(sums + m, s_sums[m]);
+            atomicAdd(sums + n + m, s_sums[kMaxStatCols + m]);
+        }
+    }
+};
 
 // logmelspec80, fast path (mel bank confined to bins < 704 with pairwise-overlapping triangles, i.e. the
 // recipe's f_max = 8 kHz Slaney bank): a warp walks kLmChunk consecutive frames of the ragged batch (one
@@ -157,7 +204,7 @@ constexpr int kLmCols = 32 * kPrunedRows;      // 704 spectrum bins
 constexpr int kLmSlots = 17;                   // partial-sum slots per lane; slab[slot][lane] (lo, hi): a step's 32 stores hit 32 different bank pairs whatever the slots
 constexpr int kLmSlabFloats = 2 * 32 * kLmSlots + 4;  // + the always-zero float unused gather entries point at
 static_assert(kLmCols + 4 + kLmSlabFloats <= kScratchFloats, "spectrum + slab live in the warp scratch");
-template <int NZ>
+template <int NZ, bool SUMS>
 __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ StftParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
@@ -178,6 +225,9 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
     float* slab = scratch + kLmCols + 4;  // [17][32] (lo, hi) pairs, then the zero float unused gather entries read
     __syncthreads();
     const long long n_chunks = (p.total_frames + kLmChunk - 1) / kLmChunk;
+    FeatureSums<SUMS ? 4 : 1> fs;  // mel bins lane, lane + 32, ... (n_mels <= 128)
+    __shared__ double s_sums[SUMS ? 2 * kMaxStatCols : 1];
+    if constexpr (SUMS) fs.init(s_sums);
     for (long long chunk = (long long)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (long long)gridDim.x * 8) {
         long long f = chunk * kLmChunk;
         int u = find_utt(p.frame_offsets, p.n_utts, f);
@@ -262,15 +312,18 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
                 if (lane == 0) slab[2 * 32 * kLmSlots] = 0.0f;  // (the transposes use the whole scratch)
             }
             __syncwarp();
-            for (int m = lane; m < p.n_mels; m += 32) {
+            for (int m = lane, i = 0; m < p.n_mels; m += 32, ++i) {
                 const float acc = gather_sum(slab, reinterpret_cast<const int4*>(s_gather), m, p.n_mels, p.mel_terms);
                 float v = logf(fmaxf(acc, p.eps));
+                if constexpr (SUMS) fs.add(i, v);
                 if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
                 p.logmel_out[f * p.n_mels + m] = v;
             }
             __syncwarp();
         }
+        if constexpr (SUMS) fs.fold(s_sums, lane, 32, p.n_mels);
     }
+    if constexpr (SUMS) fs.flush(s_sums, p.sums, p.n_mels);
 }
 
 __global__ void __launch_bounds__(256) k_mel_project(long long n_frames, int n_mels, const float* __restrict__ spec,
@@ -304,6 +357,7 @@ struct FbankParams {
     const int* mel_idx;
     const float* mel_val;
     float* out;
+    double* sums;  // optional [2][n_bins] (see StftParams::sums)
 };
 
 constexpr int kFbankWarps = 8;
@@ -383,6 +437,10 @@ __global__ void __launch_bounds__(32 * kFbankWarps) k_fbank(const __grid_constan
             for (int e = __ldg(p.mel_ptr + m); e < e1; ++e)
                 acc = fmaf(__ldg(p.mel_val + e), power[__ldg(p.mel_idx + e)], acc);
             float v = logf(fmaxf(acc, 1.1920928955078125e-07f));
+            if (p.sums) {
+                atomicAdd(p.sums + m, (double)v);
+                atomicAdd(p.sums + p.n_bins + m, (double)v * (double)v);
+            }
             if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
             p.out[f * p.n_bins + m] = v;
         }
@@ -438,6 +496,7 @@ struct FbankFastParams {
     const int* mel_idx;
     const float* mel_val;
     float* out;
+    double* sums;           // optional [2][n_bins] (see StftParams::sums)
 };
 
 // 16 x 16 transpose inside a half-warp: out a[brev4(r)] = (sub-lane r's) a[sub].  Same XOR swizzle as
@@ -458,7 +517,7 @@ __device__ __forceinline__ void group_transpose16(float2 (&a)[16], char* scratch
     __syncwarp();
 }
 
-template <int MODE>
+template <int MODE, bool SUMS>
 __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_fbank_fast(const __grid_constant__ FbankFastParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);                 // 256
@@ -493,6 +552,9 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
     const int n_mel_iter = (p.n_bins + 15) >> 4;
 
     const long long n_chunks = (p.total_frames + kFbChunk - 1) / kFbChunk;
+    FeatureSums<SUMS ? 8 : 1> fs;  // mel bins sub, sub + 16, ... (n_bins <= 128)
+    __shared__ double s_sums[SUMS ? 2 * kMaxStatCols : 1];
+    if constexpr (SUMS) fs.init(s_sums);
     for (long long cp = (long long)blockIdx.x * kFbWarps + warp; 2 * cp < n_chunks; cp += (long long)gridDim.x * kFbWarps) {
         long long f = (2 * cp + grp) * kFbChunk;
         int u = find_utt(p.frame_offsets, p.n_utts, f < p.total_frames ? f : p.total_frames - 1);
@@ -691,6 +753,10 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
                     }
                     float v0 = logf(fmaxf(e0, 1.1920928955078125e-07f));
                     float v1 = MODE == 1 ? logf(fmaxf(macc[p.n_bins + 1 + m], 1.1920928955078125e-07f)) : 0.0f;
+                    if constexpr (SUMS) {
+                        if (valid[0]) fs.add(i, v0);
+                        if (MODE == 1 && valid[MODE]) fs.add(i, v1);
+                    }
                     if (p.cmvn_mean) {
                         const float mu = __ldg(p.cmvn_mean + m), sd = __ldg(p.cmvn_std + m);
                         v0 = (v0 - mu) / sd;
@@ -703,7 +769,9 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
             }
             __syncwarp();
         }
+        if constexpr (SUMS) fs.fold(s_sums, sub, 16, p.n_bins);
     }
+    if constexpr (SUMS) fs.flush(s_sums, p.sums, p.n_bins);
 }
 
 template <bool DENORM>
@@ -759,7 +827,7 @@ __global__ void __launch_bounds__(128) k_cmvn_accumulate(long long n_rows, int n
 int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const int64_t* wave_offsets,
                 const int32_t* frame_offsets, const float* wave, float* mag_out, float* phase_out,
                 float* logmel_out, float eps, const float* cmvn_mean, const float* cmvn_std,
-                cudaStream_t stream) {
+                cudaStream_t stream, double* sums) {
     if (total_frames <= 0) return S2ST_OK;
     if (logmel_out && !plan->mel_ptr) {
         set_error("plan was created without a mel filterbank");
@@ -785,6 +853,7 @@ int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const
     p.eps = eps;
     p.cmvn_mean = cmvn_mean;
     p.cmvn_std = cmvn_std;
+    p.sums = sums;
     p.mel_ptr = plan->mel_ptr;
     p.mel_idx = plan->mel_idx;
     p.mel_val = plan->mel_val;
@@ -796,13 +865,18 @@ int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const
                              sizeof(float) * (plan->wp + 8 * kScratchFloats);
         const long long chunks = (total_frames + kLmChunk - 1) / kLmChunk;
         const int fgrid = (int)min((long long)plan->num_sms * 2, (chunks + 7) / 8);
+#define S2ST_LAUNCH_LOGMEL(NZV, SUMSV)                                                                                \
+    do {                                                                                                             \
+        S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_logmel_fast<NZV, SUMSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)fsmem));                                                           \
+        k_logmel_fast<NZV, SUMSV><<<fgrid, 256, fsmem, stream>>>(p);                                                 \
+    } while (0)
         if (plan->nz == 19) {
-            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_logmel_fast<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k_logmel_fast<19><<<fgrid, 256, fsmem, stream>>>(p);
+            if (sums) S2ST_LAUNCH_LOGMEL(19, true); else S2ST_LAUNCH_LOGMEL(19, false);
         } else {
-            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_logmel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k_logmel_fast<32><<<fgrid, 256, fsmem, stream>>>(p);
+            if (sums) S2ST_LAUNCH_LOGMEL(32, true); else S2ST_LAUNCH_LOGMEL(32, false);
         }
+#undef S2ST_LAUNCH_LOGMEL
         S2ST_CUDA_CHECK(cudaGetLastError());
         return S2ST_OK;
     }
@@ -840,7 +914,7 @@ int launch_mel_project(const s2st_plan* plan, long long n_frames, const float* s
 
 int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames,
                  const int64_t* wave_offsets, const int32_t* frame_offsets, const float* wave,
-                 const float* cmvn_mean, const float* cmvn_std, float* out, cudaStream_t stream) {
+                 const float* cmvn_mean, const float* cmvn_std, float* out, cudaStream_t stream, double* sums) {
     if (total_frames <= 0) return S2ST_OK;
     FbankParams p;
     p.win = plan->win;
@@ -860,6 +934,7 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
     p.mel_idx = plan->mel_idx;
     p.mel_val = plan->mel_val;
     p.out = out;
+    p.sums = sums;
     if (plan->fast_mode >= 0 && !plan->opt_generic) {
         FbankFastParams q;
         q.win = plan->win;
@@ -884,6 +959,7 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
         q.mel_val = plan->mel_val;
         q.mel_nnz = plan->mel_nnz;
         q.out = out;
+        q.sums = sums;
         const size_t acc_floats = (size_t)(((plan->fast_mode + 1) * (plan->n_bins + 1) + 3) & ~3);
         const size_t tab = plan->fast_mode == 0 ? sizeof(float4) * 256 + sizeof(int) * (size_t)((8 * plan->n_bins + 3) & ~3)
                                                 : sizeof(int2) * ((plan->mel_nnz + 1) & ~1) + sizeof(int) * ((plan->n_bins + 1 + 3) & ~3);
@@ -891,13 +967,18 @@ int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames
         const size_t fsmem = sizeof(float2) * 512 + sizeof(float) * kFbRows * 32 + tab + (size_t)kFbWarps * 2 * region;
         const long long pair_chunks = ((total_frames + kFbChunk - 1) / kFbChunk + 1) / 2;
         const int fgrid = (int)min((long long)plan->num_sms * (plan->fast_mode == 0 ? kFbBlocks0 : 3), (pair_chunks + kFbWarps - 1) / kFbWarps);
+#define S2ST_LAUNCH_FBANK(MODEV, SUMSV)                                                                                \
+    do {                                                                                                               \
+        S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank_fast<MODEV, SUMSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)fsmem));                                                             \
+        k_fbank_fast<MODEV, SUMSV><<<fgrid, 32 * kFbWarps, fsmem, stream>>>(q);                                        \
+    } while (0)
         if (plan->fast_mode == 0) {
-            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k_fbank_fast<0><<<fgrid, 32 * kFbWarps, fsmem, stream>>>(q);
+            if (sums) S2ST_LAUNCH_FBANK(0, true); else S2ST_LAUNCH_FBANK(0, false);
         } else {
-            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_fbank_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k_fbank_fast<1><<<fgrid, 32 * kFbWarps, fsmem, stream>>>(q);
+            if (sums) S2ST_LAUNCH_FBANK(1, true); else S2ST_LAUNCH_FBANK(1, false);
         }
+#undef S2ST_LAUNCH_FBANK
         S2ST_CUDA_CHECK(cudaGetLastError());
         return S2ST_OK;
     }

@@ -102,12 +102,13 @@ int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float
 int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const int64_t* wave_offsets,
                 const int32_t* frame_offsets, const float* wave, float* mag_out, float* phase_out,
                 float* logmel_out, float eps, const float* cmvn_mean, const float* cmvn_std,
-                cudaStream_t stream);
+                cudaStream_t stream, double* sums = nullptr);
 int launch_mel_project(const s2st_plan* plan, long long n_frames, const float* spec, float* out,
                        cudaStream_t stream);
 int launch_fbank(const s2st_fbank_plan* plan, int n_utts, long long total_frames,
                  const int64_t* wave_offsets, const int32_t* frame_offsets, const float* wave,
-                 const float* cmvn_mean, const float* cmvn_std, float* out, cudaStream_t stream);
+                 const float* cmvn_mean, const float* cmvn_std, float* out, cudaStream_t stream,
+                 double* sums = nullptr);
 int launch_cmvn(long long n_rows, int n_cols, const float* x, const float* mean, const float* std,
                 float* out, bool denorm, cudaStream_t stream);
 int launch_cmvn_accumulate(long long n_rows, int n_cols, const float* x, double* sums, cudaStream_t stream);
@@ -116,6 +117,7 @@ int launch_cmvn_accumulate(long long n_rows, int n_cols, const float* x, double*
 // transform_kernels.cu
 int launch_utterance_cmvn(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const float* x, float* out,
                           bool norm_means, bool norm_vars, float* stats, cudaStream_t stream);
+int launch_utterance_sums(int n_utts, const int32_t* fo, int n_cols, const float* x, float* sums, cudaStream_t stream);
 int launch_utterance_sum(int n_utts, const int32_t* fo, int n_cols, const float* x, double* sums, cudaStream_t stream);
 int launch_fill_rects(int n_rects, const int32_t* rects, const float* values, int n_cols, float* x, cudaStream_t stream);
 

@@ -15,12 +15,16 @@ namespace {
 // accumulation per column: the same order and roundings are used here (no FMA contraction), which makes the result
 // bit-identical.  Lanes are consecutive columns: every row access of a warp is one coalesced segment; eight rows are
 // in flight per thread.  stats[u] = (mean[n_cols], std[n_cols]).
+template <bool RAW>  // RAW: stats[u] = (sum[n_cols], sum of squares[n_cols]) -- get_global_cmvn's per-file terms
 __global__ void __launch_bounds__(128) k_utterance_stats(const int32_t* __restrict__ fo, int n_cols,
                                                           const float* __restrict__ x, float* __restrict__ stats) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= n_cols) return;
     const int r0 = fo[blockIdx.x], T = fo[blockIdx.x + 1] - r0;
-    if (T <= 0) return;
+    if (T <= 0) {
+        if (RAW) stats[(size_t)blockIdx.x * 2 * n_cols + c] = stats[(size_t)blockIdx.x * 2 * n_cols + n_cols + c] = 0.0f;
+        return;
+    }
     const float* px = x + (size_t)r0 * n_cols + c;
     float s = 0.0f, s2 = 0.0f;
     int r = 0;
@@ -38,6 +42,11 @@ __global__ void __launch_bounds__(128) k_utterance_stats(const int32_t* __restri
         const float v = __ldg(px + (size_t)r * n_cols);
         s = __fadd_rn(s, v);
         s2 = __fadd_rn(s2, __fmul_rn(v, v));
+    }
+    if constexpr (RAW) {
+        stats[(size_t)blockIdx.x * 2 * n_cols + c] = s;
+        stats[(size_t)blockIdx.x * 2 * n_cols + n_cols + c] = s2;
+        return;
     }
     const float n = (float)T;
     const float mean = __fdiv_rn(s, n);
@@ -142,7 +151,7 @@ int launch_utterance_cmvn(int n_utts, long long n_rows, const int32_t* fo, int n
                           bool norm_means, bool norm_vars, float* stats, cudaStream_t stream) {
     if (n_utts <= 0 || n_rows <= 0) return S2ST_OK;
     dim3 grid((unsigned)n_utts, (unsigned)((n_cols + 127) / 128));
-    k_utterance_stats<<<grid, 128, 0, stream>>>(fo, n_cols, x, stats);
+    k_utterance_stats<false><<<grid, 128, 0, stream>>>(fo, n_cols, x, stats);
     S2ST_CUDA_CHECK(cudaGetLastError());
     const unsigned blocks = (unsigned)((n_rows + kApplyRows - 1) / kApplyRows);
     const bool vec = n_cols % 4 == 0 && n_cols / 4 <= 256 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
@@ -154,6 +163,14 @@ int launch_utterance_cmvn(int n_utts, long long n_rows, const int32_t* fo, int n
         set_error("s2st_utterance_cmvn supports at most 256 feature columns (got %d)", n_cols);
         return S2ST_EINVAL;
     }
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
+
+int launch_utterance_sums(int n_utts, const int32_t* fo, int n_cols, const float* x, float* sums, cudaStream_t stream) {
+    if (n_utts <= 0) return S2ST_OK;
+    dim3 grid((unsigned)n_utts, (unsigned)((n_cols + 127) / 128));
+    k_utterance_stats<true><<<grid, 128, 0, stream>>>(fo, n_cols, x, sums);
     S2ST_CUDA_CHECK(cudaGetLastError());
     return S2ST_OK;
 }

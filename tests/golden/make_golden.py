@@ -23,6 +23,10 @@ Outputs (float32 unless noted), all produced by reference code:
   fbank.npz        int16-scaled waveform -> _get_torchaudio_fbank features, 16 kHz and 8 kHz
   cmvn.npz         features, stats, GlobalCMVN output, gcmvn_denormalize output
   wss.npz          GriffinLim.get_window_sum_square for a few frame counts
+  gcmvn_stats.npz  get_global_cmvn (examples/speech_synthesis/data_utils.py:190-220) run on a directory of .npy
+                   feature files: the files' seeds / shapes, the order Path.glob returned them in, mean and std
+
+    python tests/golden/make_golden.py --only gcmvn     regenerates just that fixture
 """
 import importlib.util
 import os
@@ -103,7 +107,50 @@ def synth_audio(n, sr, seed):
     return np.clip(x, -1, 1).astype(np.float32)
 
 
+def gcmvn_files(root):
+    """The feature directory of the get_global_cmvn fixture: (name, T, seed) -> [T, 80] float32 .npy files (one of them
+    saved as [1, T, 80]: the reference squeezes).  Shared with tests/test_frontend_gpu.py through the fixture's
+    names / frames / seeds arrays."""
+    specs = [("utt_%02d" % i, T, 500 + i) for i, T in enumerate((1998, 7, 333, 812, 64, 1203, 2, 450))]
+    for k, (name, T, seed) in enumerate(specs):
+        rng = np.random.RandomState(seed)
+        x = (rng.randn(T, 80) * rng.uniform(0.2, 3.0, 80) + rng.uniform(-8, 2, 80)).astype(np.float32)
+        np.save(os.path.join(root, name + ".npy"), x[None] if k == 3 else x)
+    return specs
+
+
+def make_gcmvn():
+    """get_global_cmvn, the reference's own function (compiled by name from its file: the module imports the whole
+    fairseq example stack), on a temporary directory.  Path.glob order is directory order, i.e. arbitrary: the fixture
+    records the order the reference saw, because its float32 running sums depend on it in the last bits."""
+    import ast
+    import tempfile
+    from pathlib import Path
+    from typing import Optional
+    from tqdm import tqdm
+    src = open(os.path.join(REF, "examples/speech_synthesis/data_utils.py")).read()
+    mod = ast.Module([n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_global_cmvn"], [])
+    ns = {"np": np, "Path": Path, "Optional": Optional, "tqdm": tqdm}
+    exec(compile(mod, "data_utils.py", "exec"), ns)
+    with tempfile.TemporaryDirectory() as d:
+        specs = gcmvn_files(d)
+        order = [p.stem for p in Path(d).glob("*.npy")]
+        st = ns["get_global_cmvn"](Path(d))
+        out = os.path.join(d, "stats.npz")
+        ns["get_global_cmvn"](Path(d), Path(out))
+        saved = np.load(out)
+        assert np.array_equal(saved["mean"], st["mean"]) and np.array_equal(saved["std"], st["std"])
+    assert st["mean"].dtype == np.float32 and st["std"].dtype == np.float32
+    np.savez_compressed(os.path.join(HERE, "gcmvn_stats.npz"), names=np.array([n for n, _, _ in specs]),
+                        frames=np.array([t for _, t, _ in specs]), seeds=np.array([s for _, _, s in specs]),
+                        glob_order=np.array(order), mean=st["mean"], std=st["std"])
+    print("gcmvn ok: order", order, "mean[:3]", st["mean"][:3], "std[:3]", st["std"][:3])
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "gcmvn":
+        make_gcmvn()
+        return
     torch.set_num_threads(os.cpu_count())
     au, voc_mod, ft = load_reference()
     voc = voc_mod.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window,
@@ -263,6 +310,7 @@ def main():
         rets = ns["batch_mel_cepstral_distortion"](ya, yb, 24000, normalize_type=nt)
         dt["mcd_" + str(nt)] = np.asarray([float(r[0]) for r in rets], np.float64)
     dt.update(mcd_ya0=ya[0].numpy(), mcd_ya1=ya[1].numpy(), mcd_yb0=yb[0].numpy(), mcd_yb1=yb[1].numpy())
+    make_gcmvn()
     np.savez_compressed(os.path.join(HERE, "dtw.npz"), **dt)
     print("dtw ok", {k: v.shape for k, v in dt.items() if k.startswith("mcd_") and v.ndim == 1 and v.size == 2})
 

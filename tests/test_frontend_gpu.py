@@ -120,6 +120,59 @@ def test_cmvn_stats(pkg, built_lib):
     assert np.allclose(st["mean"], ref["mean"], atol=1e-5) and np.allclose(st["std"], ref["std"], atol=1e-5)
 
 
+def test_get_global_cmvn_drop_in_matches_reference_fixture(pkg, built_lib, tmp_path):
+    """get_global_cmvn(feature_root, output_path=None) -- the reference's signature -- against the fixture generated by
+    the reference's own function: bit-exact when the files are visited in the order the reference saw them (per-file
+    float32 sums on the GPU, s2st_utterance_sums, added in that order); through the public entry (Path.glob order of
+    THIS file system, which may differ) equal to float32 rounding of the running sums."""
+    import importlib
+    from test_oracle_golden import gcmvn_fixture_arrays
+    feats = importlib.import_module(pkg.__name__ + ".features")
+    g, arrays = gcmvn_fixture_arrays()
+    for name, a in arrays.items():
+        np.save(tmp_path / (name + ".npy"), a)
+    st = feats._global_cmvn_from_paths([tmp_path / (str(n) + ".npy") for n in g["glob_order"]], batch_bytes=700000)
+    assert st["mean"].dtype == np.float32 and st["std"].dtype == np.float32
+    assert np.array_equal(st["mean"], g["mean"]) and np.array_equal(st["std"], g["std"])
+    pub = pkg.get_global_cmvn(tmp_path)
+    assert np.allclose(pub["mean"], g["mean"], rtol=2e-6, atol=1e-6) and np.allclose(pub["std"], g["std"], rtol=2e-6, atol=1e-6)
+    out = tmp_path / "stats.npz"
+    assert pkg.get_global_cmvn(tmp_path, out) is None
+    saved = np.load(out)
+    assert np.array_equal(saved["mean"], pub["mean"]) and np.array_equal(saved["std"], pub["std"])
+    # the registry transform consumes exactly this file (global_cmvn.py:18-21)
+    t = pkg.GlobalCMVN.from_config_dict({"stats_npz_path": str(out)})
+    x = arrays["utt_01"]
+    assert np.array_equal(t(x), np.divide(np.subtract(x, pub["mean"]), pub["std"]))
+
+
+def test_fused_statistics_in_extraction_kernels(pkg, built_lib):
+    """Sum / sum of squares accumulated inside the fbank / log-mel kernels (fast and generic variants) equal the sums
+    over the features they return (float64), and give the statistics of a separate pass over the features."""
+    import importlib
+    plans = importlib.import_module(pkg.__name__ + ".plans")
+    rng = np.random.RandomState(3)
+    for sr, lens in ((16000, [401, 7777, 12345, 3001]), (8000, [281, 8000, 199, 2763]), (22050, [9000, 4000])):
+        waves = [torch.from_numpy((rng.randn(n) * 2000).astype(np.float32)) for n in lens]
+        for generic in (0, 1):
+            plans.get_fbank_plan("cuda", sr, 80).set_option(pkg._lib.OPT_FRONTEND_GENERIC, generic)
+            stats = torch.zeros(2, 80, dtype=torch.float64, device="cuda")
+            mean, std = rng.randn(80).astype(np.float32), rng.uniform(0.5, 2, 80).astype(np.float32)
+            pkg.fbank_batch(waves, sr, stats=stats, cmvn_mean=mean, cmvn_std=std)  # statistics are taken BEFORE the CMVN
+            feats = torch.cat(pkg.fbank_batch(waves, sr)).double()
+            assert torch.allclose(stats[0], feats.sum(0), rtol=1e-6, atol=1e-4), (sr, generic)
+            assert torch.allclose(stats[1], (feats ** 2).sum(0), rtol=1e-6, atol=1e-3), (sr, generic)
+        plans.get_fbank_plan("cuda", sr, 80).set_option(pkg._lib.OPT_FRONTEND_GENERIC, 0)
+    waves = [torch.from_numpy(synth_audio(n, 24000, 70 + i)) for i, n in enumerate((24000, 7001, 1201, 40000))]
+    stats = torch.zeros(2, 80, dtype=torch.float64, device="cuda")
+    feats = pkg.logmel_batch(waves, f_min=20.0, stats=stats)
+    allf = torch.cat(feats).double()
+    assert torch.allclose(stats[0], allf.sum(0), rtol=1e-6, atol=1e-4) and torch.allclose(stats[1], (allf ** 2).sum(0), rtol=1e-6, atol=1e-3)
+    st = pkg.global_cmvn_from_sums(stats, allf.shape[0])
+    ref = ofe.global_cmvn_stats([f.cpu().numpy() for f in feats])
+    assert np.allclose(st["mean"], ref["mean"], atol=1e-5) and np.allclose(st["std"], ref["std"], atol=1e-5)
+
+
 def test_fast_kernels_ragged_chunks_match_oracle_and_generic(pkg, built_lib, monkeypatch):
     """The chunked kernels (k_fbank_fast: 16 frames per half-warp, two frames per transform at 8 kHz; k_logmel_fast:
     8 frames per warp) on batches whose utterances end inside chunks, have odd sample offsets (unaligned loads), odd

@@ -118,6 +118,26 @@ def test_cmvn_stats_roundtrip():
     assert np.allclose(st["std"], allf.std(0), atol=1e-3)
 
 
+def gcmvn_fixture_arrays():
+    """The feature files of tests/golden/gcmvn_stats.npz regenerated from their seeds (make_golden.gcmvn_files)."""
+    g = load_golden("gcmvn_stats.npz")
+    arrays = {}
+    for k, (name, T, seed) in enumerate(zip(g["names"], g["frames"], g["seeds"])):
+        rng = np.random.RandomState(int(seed))
+        x = (rng.randn(int(T), 80) * rng.uniform(0.2, 3.0, 80) + rng.uniform(-8, 2, 80)).astype(np.float32)
+        arrays[str(name)] = x[None] if k == 3 else x
+    return g, arrays
+
+
+def test_get_global_cmvn_matches_reference_bit_exact():
+    """Oracle restatement of get_global_cmvn vs the fixture produced by the reference's own function, with the files in
+    the order the reference's Path.glob returned them (its float32 running sums depend on that order)."""
+    g, arrays = gcmvn_fixture_arrays()
+    st = fe.get_global_cmvn([arrays[str(n)] for n in g["glob_order"]])
+    assert st["mean"].dtype == np.float32
+    assert np.array_equal(st["mean"], g["mean"]) and np.array_equal(st["std"], g["std"])
+
+
 def test_utterance_cmvn_matches_reference_bit_exact():
     t = load_golden("transforms.npz")
     for name in "abcd":

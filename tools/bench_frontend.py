@@ -36,7 +36,7 @@ for name, sr in (("fbank80_16k", 16000), ("fbank80_8k", 8000)):
     lib = pkg._lib.load()
     def run():
         pkg._lib.check(lib.s2st_fbank(plan.handle, a.utts, total, pkg._lib.ptr(wo), pkg._lib.ptr(fo), pkg._lib.ptr(flat),
-                                      pkg._lib.ptr(mean), pkg._lib.ptr(std), pkg._lib.ptr(o), pkg._lib.stream_ptr(dev)), "fbank")
+                                      pkg._lib.ptr(mean), pkg._lib.ptr(std), None, pkg._lib.ptr(o), pkg._lib.stream_ptr(dev)), "fbank")
     ms = timeit(run, a.steps)
     audio = float(lens.sum()) / sr
     out[name] = {"audio_s_per_s": audio / (ms * 1e-3), "ms": ms, "frames": total,
@@ -55,7 +55,7 @@ o = torch.empty(total, 80, device=dev)
 lib = pkg._lib.load()
 def run():
     pkg._lib.check(lib.s2st_logmel(plan.handle, a.utts, total, pkg._lib.ptr(wo), pkg._lib.ptr(fo), pkg._lib.ptr(flat), 1e-5,
-                                   pkg._lib.ptr(mean), pkg._lib.ptr(std), pkg._lib.ptr(o), pkg._lib.stream_ptr(dev)), "logmel")
+                                   pkg._lib.ptr(mean), pkg._lib.ptr(std), None, pkg._lib.ptr(o), pkg._lib.stream_ptr(dev)), "logmel")
 ms = timeit(run, a.steps)
 out["logmelspec80_24k"] = {"audio_s_per_s": float(lens.sum()) / sr / (ms * 1e-3), "ms": ms, "frames": total,
                            "GBps_algorithmic": total * 1520 / (ms * 1e-3) / 1e9, "frac_of_hbm": total * 1520 / (ms * 1e-3) / 1e9 / hbm}

@@ -21,6 +21,6 @@ mean = torch.randn(80, device=dev) - 4; std = torch.rand(80, device=dev) * 1.5 +
 lib = pkg._lib.load()
 for _ in range(3):
     pkg._lib.check(lib.s2st_logmel(plan.handle, utts, total, pkg._lib.ptr(wo), pkg._lib.ptr(fo), pkg._lib.ptr(flat), 1e-5,
-                                   pkg._lib.ptr(mean), pkg._lib.ptr(std), pkg._lib.ptr(o), pkg._lib.stream_ptr(dev)), "logmel")
+                                   pkg._lib.ptr(mean), pkg._lib.ptr(std), None, pkg._lib.ptr(o), pkg._lib.stream_ptr(dev)), "logmel")
 torch.cuda.synchronize()
 print("ok frames", total, float(o.mean()))
