@@ -66,10 +66,10 @@ int s2st_plan_destroy(s2st_plan* plan);
 int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
 /* Plan options (all have working defaults; they exist for A/B measurements and tests).  Initial values come from the
  * environment variable named in brackets, read once by s2st_plan_create. */
-#define S2ST_OPT_GL_PERSISTENT 1    /* [S2ST_GL_PERSISTENT] -1 (default): run all Griffin-Lim iterations of a SMALL call
-                                       (<= 1/4 of the resident warps get a strip) as one persistent launch, larger calls as one
-                                       launch per iteration; 0: never persistent; 1: persistent whenever every strip is resident.
-                                       Results are bitwise identical in all three modes. */
+#define S2ST_OPT_GL_PERSISTENT 1    /* [S2ST_GL_PERSISTENT=1 | auto] 0 (default): one launch per Griffin-Lim iteration; 1: all
+                                       iterations as ONE persistent cooperative launch whenever every strip is resident; -1:
+                                       persistent for small calls only (<= 1/4 of the resident warps get a strip).  Results are
+                                       bitwise identical in all three modes; measured on B200 the persistent launch never wins. */
 #define S2ST_OPT_GL_PDL 2           /* [S2ST_GL_PDL] 1 (default): programmatic dependent launch of the passes; 0: plain launches */
 #define S2ST_OPT_GL_KERNEL 3        /* [S2ST_GL_KERNEL=r64] 0 (default): packed-complex iteration kernel; 1: real-FFT-64 formulation */
 #define S2ST_OPT_INVERSE_MEL 4      /* [S2ST_INVERSE_MEL=simt] 0 (default): tcgen05 tensor-core inverse-mel; 1: FP32 SIMT kernel */

@@ -139,7 +139,7 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
     std::memset(p, 0, sizeof(*p));
     {   // options: the S2ST_* environment variables are read HERE, once; afterwards only s2st_plan_set_option changes them
         const char* e = getenv("S2ST_GL_PERSISTENT");
-        p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == '0') ? 0 : -1;
+        p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == 'a') ? -1 : 0;
         e = getenv("S2ST_GL_PDL");
         p->opt_pdl = !(e && e[0] == '0');
         e = getenv("S2ST_GL_KERNEL");

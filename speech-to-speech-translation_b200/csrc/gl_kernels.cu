@@ -933,12 +933,14 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
 // parity-tested, but measured 1.6 % SLOWER than one launch per iteration with programmatic dependent launch on the
 // config-2 batch (15.82 vs 15.57 ms per step): what the missing grid barrier saves (pass tails, launch ramp) is less
 // than what the per-strip waits, fences and L2-only waveform loads cost.  Hence opt-in.
-// Persistent mode (S2ST_OPT_GL_PERSISTENT): -1 = automatic (default), 0 = never, 1 = whenever every strip is resident.
-// Automatic = persistent whenever the call is SMALL -- at most a quarter of the resident warps get a strip -- which is
-// the per-utterance shape of the reference's own call site (speech_generator_for_s2st.py:115-124): there a pass lasts a
-// few strip-frames (tens of microseconds), so the per-launch prologue (CTA start-up, 21 KB of constant tables, ring
-// clearing) and the launch gaps dominate, while the lightly loaded SMs make the neighbour waits cheap.  Results are
-// bitwise identical either way (test_persistent_mode_is_bitwise_identical).
+// Persistent mode (S2ST_OPT_GL_PERSISTENT): 0 = one launch per iteration (default), 1 = one cooperative launch whenever
+// every strip is resident, -1 = automatic (persistent for small calls: at most a quarter of the resident warps get a
+// strip).  Results are bitwise identical in all modes (test_persistent_mode_is_bitwise_identical).  Measured on B200
+// (tools/time_small.py, profiles/r02_small_calls.txt): the persistent launch is never faster -- one 500-frame utterance
+// 2.56 ms vs 2.36 ms, 8 x 230 frames 2.80 vs 2.46 ms, the config-2 batch 15.82 vs 15.57 ms -- because a small call is
+// bound by the latency of ONE warp running its 4-frame strip (~8 us per frame when a warp has an SM to itself, i.e.
+// ~34 us per iteration whatever the launch mechanism), not by launch gaps or the per-launch prologue; the neighbour
+// waits, fences and L2-only waveform loads of the persistent kernel cost more than those.  Hence opt-in.
 
 template <auto Kernel>
 int allow_dynamic_smem(size_t smem, int device) {

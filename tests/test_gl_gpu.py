@@ -248,7 +248,7 @@ def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
             pers = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
             assert plan.gl_launch_count(12) == 4  # build_tiles, inverse_mel, initial inverse, the persistent launch
         finally:
-            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, -1)
+            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 0)
             plan.set_strip_frames(0)
         for a, b in zip(base, pers):
             assert torch.equal(a, b)

@@ -28,4 +28,4 @@ for name, frames in cases:
     print(f"{name:8s} per-iteration launches {res[0][0]:.3f} ms ({audio / res[0][0] * 1e3:.0f} audio-s/s) | persistent {res[1][0]:.3f} ms "
           f"({audio / res[1][0] * 1e3:.0f}, {res[1][1]} launches) | auto {res[2][0]:.3f} ms ({res[2][1]} launches) | bitwise equal "
           f"{bool(torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]))}")
-plan.set_option(pkg._lib.OPT_GL_PERSISTENT, -1)
+plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 0)
