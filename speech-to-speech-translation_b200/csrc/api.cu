@@ -68,6 +68,8 @@ void to_csr(const float* dense, int rows, int cols, std::vector<int>& ptr, std::
 void free_plan_members(s2st_plan* p) {
     for (int i = 0; i <= kMaxTimedPasses; ++i)
         if (p->timing_events[i]) cudaEventDestroy(p->timing_events[i]);
+    cudaFree(p->gwin);
+    cudaFree(p->gtw);
     cudaFree(p->win_a);
     cudaFree(p->win_s);
     cudaFree(p->w2);
@@ -108,8 +110,13 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         return S2ST_EINVAL;
     }
     *plan_out = nullptr;
-    if (n_fft != kNfft) {
-        set_error("n_fft=%d is not supported by this build (only %d)", n_fft, kNfft);
+    if (n_fft != kNfft && (n_fft < 64 || n_fft > 4096 || (n_fft & (n_fft - 1)) != 0)) {
+        set_error("n_fft=%d is not supported: the STFT / log-mel / mel-projection entry points take any power of two in "
+                  "[64, 4096], Griffin-Lim synthesis takes n_fft = %d only", n_fft, kNfft);
+        return S2ST_EINVAL;
+    }
+    if (n_fft != kNfft && inv_mel_host) {
+        set_error("an inverse-mel basis (Griffin-Lim synthesis) needs n_fft = %d, got %d", kNfft, n_fft);
         return S2ST_EINVAL;
     }
     if (win_length < 1 || win_length > n_fft || hop_length < 1 || n_mels < 1) {
@@ -153,6 +160,47 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
     p->win_length = win_length;
     p->hop = hop_length;
     p->n_mels = n_mels;
+    p->n_bins = n_fft / 2 + 1;
+    if (n_fft != kNfft) {
+        // generic geometry: padded window, radix-2 twiddles, CSR mel bank; nothing of the 2048-point machinery
+        p->generic = 1;
+        p->kb = p->n_bins;
+        std::vector<float2> gtw(n_fft / 2);
+        for (int j = 0; j < n_fft / 2; ++j) {
+            const double a = -2.0 * 3.14159265358979323846 * (double)j / (double)n_fft;
+            gtw[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        int rc = S2ST_OK;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+            set_error("cudaGetDeviceProperties failed");
+            rc = S2ST_ECUDA;
+        } else {
+            p->num_sms = prop.multiProcessorCount;
+        }
+        if (rc == S2ST_OK) rc = upload(&p->gwin, w);
+        if (rc == S2ST_OK) rc = upload(&p->gtw, gtw);
+        if (rc == S2ST_OK && mel_host) {
+            std::vector<int> ptr, idx;
+            std::vector<float> val;
+            to_csr(mel_host, n_mels, p->n_bins, ptr, idx, val, &p->mel_max_row);
+            p->mel_nnz = (int)idx.size();
+            if (idx.empty()) {
+                idx.push_back(0);
+                val.push_back(0.0f);
+            }
+            rc = upload(&p->mel_ptr, ptr);
+            if (rc == S2ST_OK) rc = upload(&p->mel_idx, idx);
+            if (rc == S2ST_OK) rc = upload(&p->mel_val, val);
+        }
+        if (rc != S2ST_OK) {
+            free_plan_members(p);
+            delete p;
+            return rc;
+        }
+        *plan_out = p;
+        return S2ST_OK;
+    }
     // frames are processed circularly rotated so that the window support starts at sample 0; when it
     // fits in 19*64 samples the 13 structurally-zero inputs of every in-lane FFT are pruned.
     int rot = lo & ~1;
@@ -444,6 +492,11 @@ int s2st_plan_get_pass_times(s2st_plan* plan, float* ms_out_host, int capacity, 
 }
 
 static int check_gl_geometry(const s2st_plan* plan) {
+    if (plan->generic) {
+        set_error("Griffin-Lim synthesis / inverse STFT need n_fft = %d (this plan has n_fft = %d: STFT, log-mel and mel "
+                  "projection only)", kNfft, plan->n_fft);
+        return S2ST_EINVAL;
+    }
     if (plan->nphase > 64) {
         set_error("window support %d exceeds %d hops of %d samples: overlap factor not supported", plan->ws,
                   64, plan->hop);
@@ -505,6 +558,10 @@ int s2st_inverse_mel(const s2st_plan* plan, int64_t n_frames, const float* mel_d
         set_error("bad argument to s2st_inverse_mel");
         return S2ST_EINVAL;
     }
+    if (plan->generic) {
+        set_error("s2st_inverse_mel needs n_fft = %d (plan has %d)", kNfft, plan->n_fft);
+        return S2ST_EINVAL;
+    }
     return launch_inverse_mel(plan, n_frames, mel_dev, input_is_log != 0, mag_dev, kBins, kBins,
                               static_cast<cudaStream_t>(stream));
 }
@@ -547,12 +604,20 @@ int s2st_rfft2048(const s2st_plan* plan, int64_t n, const float* in_dev, float* 
         set_error("bad argument to s2st_rfft2048");
         return S2ST_EINVAL;
     }
+    if (plan->generic) {
+        set_error("s2st_rfft2048 needs a plan with n_fft = %d", kNfft);
+        return S2ST_EINVAL;
+    }
     return launch_rfft2048(plan, n, in_dev, out_dev, false, static_cast<cudaStream_t>(stream));
 }
 
 int s2st_irfft2048(const s2st_plan* plan, int64_t n, const float* in_dev, float* out_dev, void* stream) {
     if (!plan || !in_dev || !out_dev || n < 0) {
         set_error("bad argument to s2st_irfft2048");
+        return S2ST_EINVAL;
+    }
+    if (plan->generic) {
+        set_error("s2st_irfft2048 needs a plan with n_fft = %d", kNfft);
         return S2ST_EINVAL;
     }
     return launch_rfft2048(plan, n, in_dev, out_dev, true, static_cast<cudaStream_t>(stream));

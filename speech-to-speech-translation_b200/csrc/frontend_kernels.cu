@@ -326,12 +326,123 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
     if constexpr (SUMS) fs.flush(s_sums, p.sums, p.n_mels);
 }
 
-__global__ void __launch_bounds__(256) k_mel_project(long long n_frames, int n_mels, const float* __restrict__ spec,
+// ---------------------------------------------------------------------------------------------
+// STFT / log-mel for any power-of-two n_fft in [64, 4096] (the reference's extractors default to n_fft = 1024,
+// examples/speech_synthesis/data_utils.py:46-52; its dense-basis convolution takes any size).  One warp per frame:
+// reflect padding + window (audio_utils.py:259-263), the real frame packed as n_fft / 2 complex points, radix-2
+// Stockham FFT in two shared-memory ping-pong buffers, Hermitian split, then magnitude / phase rows or mel -> log ->
+// CMVN rows exactly like k_stft.  Not tuned: the 2048-point recipe geometry has its own register-resident kernels.
+struct StftGenericParams {
+    int n_fft, n_bins, hop, n_mels, n_utts;
+    long long total_frames;
+    const float* win;       // [n_fft]
+    const float2* tw;       // [n_fft / 2]
+    const int64_t* wave_offsets;
+    const int32_t* frame_offsets;
+    const float* wave;
+    float* mag_out;
+    float* phase_out;
+    float* logmel_out;
+    float eps;
+    const float* cmvn_mean;
+    const float* cmvn_std;
+    double* sums;
+    const int* mel_ptr;
+    const int* mel_idx;
+    const float* mel_val;
+};
+
+template <int MODE>
+__global__ void k_stft_generic(const __grid_constant__ StftGenericParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int half = p.n_fft >> 1;
+    float2* buf0 = reinterpret_cast<float2*>(smem_raw) + (size_t)warp * (2 * half + 2);
+    float2* buf1 = buf0 + half + 1;  // + 1: the spectrum (half + 1 values) is staged here in MODE 1
+    for (long long f = (long long)blockIdx.x * warps + warp; f < p.total_frames; f += (long long)gridDim.x * warps) {
+        const int u = find_utt(p.frame_offsets, p.n_utts, f);
+        const int t = (int)(f - p.frame_offsets[u]);
+        const long long woff = p.wave_offsets[u];
+        const int n = (int)(p.wave_offsets[u + 1] - woff);
+        const float* src = p.wave + woff;
+        const int base = t * p.hop - half;
+        float* y = reinterpret_cast<float*>(buf0);
+        for (int i = lane; i < p.n_fft; i += 32) {
+            int j = base + i;
+            j = j < 0 ? -j : j;
+            j = j >= n ? 2 * (n - 1) - j : j;
+            j = min(max(j, 0), n - 1);
+            y[i] = __ldg(src + j) * __ldg(p.win + i);
+        }
+        __syncwarp();
+        float2* in = buf0;
+        float2* outb = buf1;
+        for (int ns = 1; ns < half; ns <<= 1) {
+            const int tstride = p.n_fft / (2 * ns);  // W_{2 ns}^k = W_{n_fft}^{k * n_fft / (2 ns)}
+            for (int j = lane; j < (half >> 1); j += 32) {
+                const int k = j & (ns - 1);
+                const float2 w = __ldg(p.tw + k * tstride);
+                const float2 a = in[j];
+                const float2 b = cmul(in[j + (half >> 1)], w);
+                const int j0 = ((j - k) << 1) + k;
+                outb[j0] = make_float2(a.x + b.x, a.y + b.y);
+                outb[j0 + ns] = make_float2(a.x - b.x, a.y - b.y);
+            }
+            __syncwarp();
+            float2* tmp = in;
+            in = outb;
+            outb = tmp;
+        }
+        // X[k] = E + W^k O,  E = (Z[k] + conj Z[half - k]) / 2,  O = (Z[k] - conj Z[half - k]) / (2 i);  X[half] = Re Z[0] - Im Z[0]
+        float* spec = reinterpret_cast<float*>(outb);  // MODE 1: |X| for the mel projection (half + 1 floats fit)
+        for (int k = lane; k <= half; k += 32) {
+            float xr, xi;
+            if (k == half) {
+                xr = in[0].x - in[0].y;
+                xi = 0.0f;
+            } else {
+                const float2 z = in[k];
+                const float2 zp = in[(half - k) & (half - 1)];
+                const float2 w = __ldg(p.tw + k);
+                const float ex = 0.5f * (z.x + zp.x), ey = 0.5f * (z.y - zp.y);
+                const float ox = 0.5f * (z.y + zp.y), oy = -0.5f * (z.x - zp.x);
+                xr = ex + (w.x * ox - w.y * oy);
+                xi = ey + (w.x * oy + w.y * ox);
+            }
+            const float mag = sqrtf(fmaf(xr, xr, xi * xi));
+            if constexpr (MODE == 0) {
+                p.mag_out[f * p.n_bins + k] = mag;
+                if (p.phase_out) p.phase_out[f * p.n_bins + k] = atan2f(xi, xr);
+            } else {
+                spec[k] = mag;
+            }
+        }
+        __syncwarp();
+        if constexpr (MODE == 1) {
+            for (int m = lane; m < p.n_mels; m += 32) {
+                float acc = 0.0f;
+                const int e1 = __ldg(p.mel_ptr + m + 1);
+                for (int e = __ldg(p.mel_ptr + m); e < e1; ++e)
+                    acc = fmaf(__ldg(p.mel_val + e), spec[__ldg(p.mel_idx + e)], acc);
+                float v = logf(fmaxf(acc, p.eps));
+                if (p.sums) {
+                    atomicAdd(p.sums + m, (double)v);
+                    atomicAdd(p.sums + p.n_mels + m, (double)v * (double)v);
+                }
+                if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
+                p.logmel_out[f * p.n_mels + m] = v;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mel_project(long long n_frames, int n_mels, int n_bins, const float* __restrict__ spec,
                                                       const int* __restrict__ mel_ptr, const int* __restrict__ mel_idx,
                                                       const float* __restrict__ mel_val, float* __restrict__ out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long f = (long long)blockIdx.x * 8 + warp; f < n_frames; f += (long long)gridDim.x * 8) {
-        const float* row = spec + f * kBins;
+        const float* row = spec + f * n_bins;
         for (int m = lane; m < n_mels; m += 32) {
             float acc = 0.0f;
             const int e1 = mel_ptr[m + 1];
@@ -833,6 +944,43 @@ int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const
         set_error("plan was created without a mel filterbank");
         return S2ST_EINVAL;
     }
+    if (plan->generic) {
+        StftGenericParams g;
+        g.n_fft = plan->n_fft;
+        g.n_bins = plan->n_bins;
+        g.hop = plan->hop;
+        g.n_mels = plan->n_mels;
+        g.n_utts = n_utts;
+        g.total_frames = total_frames;
+        g.win = plan->gwin;
+        g.tw = plan->gtw;
+        g.wave_offsets = wave_offsets;
+        g.frame_offsets = frame_offsets;
+        g.wave = wave;
+        g.mag_out = mag_out;
+        g.phase_out = phase_out;
+        g.logmel_out = logmel_out;
+        g.eps = eps;
+        g.cmvn_mean = cmvn_mean;
+        g.cmvn_std = cmvn_std;
+        g.sums = sums;
+        g.mel_ptr = plan->mel_ptr;
+        g.mel_idx = plan->mel_idx;
+        g.mel_val = plan->mel_val;
+        const size_t per_warp = sizeof(float2) * (size_t)(plan->n_fft + 2);
+        const int warps = (int)max((size_t)1, min((size_t)8, (size_t)96 * 1024 / per_warp));
+        const size_t gsmem = per_warp * warps;
+        const int ggrid = (int)min((long long)plan->num_sms * max(1, (int)(200 * 1024 / gsmem)), (total_frames + warps - 1) / warps);
+        if (logmel_out) {
+            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_stft_generic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            k_stft_generic<1><<<ggrid, 32 * warps, gsmem, stream>>>(g);
+        } else {
+            S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_stft_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            k_stft_generic<0><<<ggrid, 32 * warps, gsmem, stream>>>(g);
+        }
+        S2ST_CUDA_CHECK(cudaGetLastError());
+        return S2ST_OK;
+    }
     StftParams p;
     p.hop = plan->hop;
     p.half = plan->n_fft / 2;
@@ -906,7 +1054,7 @@ int launch_mel_project(const s2st_plan* plan, long long n_frames, const float* s
     }
     if (n_frames <= 0) return S2ST_OK;
     const int grid = (int)min((long long)plan->num_sms * 8, (n_frames + 7) / 8);
-    k_mel_project<<<grid, 256, 0, stream>>>(n_frames, plan->n_mels, spec, plan->mel_ptr, plan->mel_idx,
+    k_mel_project<<<grid, 256, 0, stream>>>(n_frames, plan->n_mels, plan->n_bins, spec, plan->mel_ptr, plan->mel_idx,
                                             plan->mel_val, out);
     S2ST_CUDA_CHECK(cudaGetLastError());
     return S2ST_OK;

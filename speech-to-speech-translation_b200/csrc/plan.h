@@ -8,6 +8,12 @@ struct s2st_plan {
     int device;
     int n_fft, win_length, hop, n_mels;
     int rot, ws, wp, nz, nphase;
+    // generic geometry (n_fft != 2048, any power of two in [64, 4096]): STFT / log-mel / mel projection only, run by
+    // k_stft_generic (radix-2 Stockham FFT in shared memory); the warp-level 2048-point tables below are absent
+    int generic;
+    int n_bins;    // n_fft / 2 + 1
+    float* gwin;   // [n_fft] padded window (audio_utils.py:218-223)
+    float2* gtw;   // [n_fft / 2] exp(-2 pi i j / n_fft)
     int kb;        // active bins of the inverse-mel basis (kBins when none was given)
     int kb_pad;    // row pitch of inv_mel_t
     int num_sms;

@@ -25,6 +25,9 @@ def logmel_batch(waveforms: List, sample_rate: int = 24000, win_length: int = 12
     float32 CUDA tensors; optional fused global CMVN; ``stats`` (float64 CUDA [2, n_mels]) accumulates the sum and
     sum of squares of the features inside the extraction kernel (see ``global_cmvn_from_sums``)."""
     first = waveforms[0]
+    if n_fft < 64 or n_fft > 4096 or n_fft & (n_fft - 1):
+        raise ValueError(f"n_fft = {n_fft}: the CUDA front-end takes a power of two in [64, 4096] "
+                         "(2048 runs the register-resident kernels, the rest a generic shared-memory FFT)")
     dev = require_cuda(device if device is not None else (first.device if isinstance(first, torch.Tensor) else None))
     mel = get_mel_filters(sample_rate, n_fft, n_mels, f_min, f_max)
     plan = get_stft_plan(dev, n_fft, win_length, hop_length, n_mels, win_fn(win_length), mel=mel)
@@ -65,9 +68,9 @@ def extract_logmel_spectrogram(waveform: torch.Tensor, sample_rate: int, output_
         return
     assert waveform.dim() == 2 and waveform.shape[0] == 1
     feat = logmel_batch([waveform[0]], sample_rate, win_length, hop_length, n_fft, win_fn, n_mels, f_min, f_max, eps)[0]
-    feat = feat.cpu()
+    feat = feat.cpu().numpy()  # [T, n_mels] numpy like the reference (data_utils.py:68)
     if target_length is not None:
-        feat = _trim_or_pad(feat.numpy(), target_length)
+        feat = _trim_or_pad(feat, target_length)
     if output_path is not None:
         np.save(output_path.as_posix(), feat)
     else:

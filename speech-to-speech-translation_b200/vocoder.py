@@ -50,6 +50,7 @@ class PseudoInverseMelScale(torch.nn.Module):
         super().__init__()
         self.n_mels, self.n_stft = n_mels, n_stft
         self.n_fft = (n_stft - 1) * 2
+        _check_synthesis_geometry(self.n_fft)
         mel = get_mel_filters(sample_rate, self.n_fft, n_mels, f_min, f_max)
         self.register_buffer("basis", torch.pinverse(mel))  # F x F_mel, as the reference builds it
 
@@ -77,6 +78,7 @@ class PseudoInverseMelScale(torch.nn.Module):
 class GriffinLim(torch.nn.Module):
     def __init__(self, n_fft: int, win_length: int, hop_length: int, n_iter: int, window_fn=torch.hann_window):
         super().__init__()
+        _check_synthesis_geometry(n_fft)
         self.transform = TTSSpectrogram(n_fft, win_length, hop_length, window_fn=window_fn, return_phase=True)
         self.register_buffer("window", window_fn(win_length).float())
         self.n_fft, self.win_length, self.hop_length, self.n_iter = n_fft, win_length, hop_length, n_iter
@@ -134,6 +136,14 @@ class GriffinLim(torch.nn.Module):
         mag = spec.to(dev, torch.float32).transpose(1, 2).reshape(B * T, F).contiguous()
         wave = self._run(mag, ph, B, T, self.n_iter, dev)
         return wave.squeeze(0).to(specgram.device, specgram.dtype)
+
+
+def _check_synthesis_geometry(n_fft):
+    """Griffin-Lim synthesis (inverse-mel + fused STFT / iSTFT iterations) is built for the recipe's 2048-point
+    transform; the analysis side (TTSSpectrogram, TTSMelScale, log-mel extraction) takes any power of two."""
+    if n_fft != 2048:
+        raise ValueError(f"Griffin-Lim synthesis supports n_fft = 2048 only (got n_fft = {n_fft}); the STFT / log-mel / mel "
+                         "projection entry points accept any power-of-two n_fft in [64, 4096]")
 
 
 def _check_length(T, hop, n_fft, n_iter):

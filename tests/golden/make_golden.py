@@ -23,6 +23,7 @@ Outputs (float32 unless noted), all produced by reference code:
   fbank.npz        int16-scaled waveform -> _get_torchaudio_fbank features, 16 kHz and 8 kHz
   cmvn.npz         features, stats, GlobalCMVN output, gcmvn_denormalize output
   wss.npz          GriffinLim.get_window_sum_square for a few frame counts
+  logmel_default.npz  log-mel with the reference's default geometry (n_fft 1024) and an n_fft 512 STFT with phase
   gcmvn_stats.npz  get_global_cmvn (examples/speech_synthesis/data_utils.py:190-220) run on a directory of .npy
                    feature files: the files' seeds / shapes, the order Path.glob returned them in, mean and std
 
@@ -147,9 +148,32 @@ def make_gcmvn():
     print("gcmvn ok: order", order, "mean[:3]", st["mean"][:3], "std[:3]", st["std"][:3])
 
 
+def make_logmel_default():
+    """extract_logmel_spectrogram with the reference's OWN default geometry (win 1024, hop 256, n_fft 1024, f_min 0,
+    f_max 8000; examples/speech_synthesis/data_utils.py:46-52) at 22.05 kHz, and an n_fft = 512 STFT with phase: the
+    sizes the generic (non-2048) kernels serve.  Same modules as the logmel.npz section."""
+    au, _, _ = load_reference()
+    out = {}
+    spec_t = au.TTSSpectrogram(n_fft=1024, win_length=1024, hop_length=256, window_fn=torch.hann_window)
+    mel_t = au.TTSMelScale(n_mels=80, sample_rate=22050, f_min=0.0, f_max=8000, n_stft=513)
+    for i, n in enumerate((11025, 5000, 700)):
+        w = synth_audio(n, 22050, 140 + i)
+        with torch.no_grad():
+            f = torch.clamp(mel_t(spec_t(torch.from_numpy(w)[None])), min=1e-5).log().squeeze(0).t().numpy()
+        out["wave%d" % i] = w
+        out["feat%d" % i] = f
+        print("logmel default geometry", n, f.shape)
+    st = au.TTSSpectrogram(n_fft=512, win_length=400, hop_length=160, window_fn=torch.hamming_window, return_phase=True)
+    w = synth_audio(4000, 16000, 150)
+    with torch.no_grad():
+        mg, ph = st(torch.from_numpy(w)[None])
+    out.update(stft512_in=w, stft512_mag=mg[0].numpy(), stft512_phase=ph[0].numpy())
+    np.savez_compressed(os.path.join(HERE, "logmel_default.npz"), **out)
+
+
 def main():
-    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "gcmvn":
-        make_gcmvn()
+    if "--only" in sys.argv:
+        {"gcmvn": make_gcmvn, "logmel_default": make_logmel_default}[sys.argv[sys.argv.index("--only") + 1]]()
         return
     torch.set_num_threads(os.cpu_count())
     au, voc_mod, ft = load_reference()
@@ -311,6 +335,7 @@ def main():
         dt["mcd_" + str(nt)] = np.asarray([float(r[0]) for r in rets], np.float64)
     dt.update(mcd_ya0=ya[0].numpy(), mcd_ya1=ya[1].numpy(), mcd_yb0=yb[0].numpy(), mcd_yb1=yb[1].numpy())
     make_gcmvn()
+    make_logmel_default()
     np.savez_compressed(os.path.join(HERE, "dtw.npz"), **dt)
     print("dtw ok", {k: v.shape for k, v in dt.items() if k.startswith("mcd_") and v.ndim == 1 and v.size == 2})
 

@@ -25,7 +25,7 @@ def test_logmel_matches_reference_and_oracle(pkg, built_lib):
     # same-signature single-utterance extractor
     f1 = pkg.extract_logmel_spectrogram(torch.from_numpy(waves[0])[None], 24000, win_length=1200, hop_length=300,
                                         n_fft=2048, f_min=20.0, f_max=8000.0)
-    assert torch.equal(f1, feats[0].cpu())
+    assert isinstance(f1, np.ndarray) and np.array_equal(f1, feats[0].cpu().numpy())
     f2 = pkg.extract_logmel_spectrogram(torch.from_numpy(waves[0])[None], 24000, win_length=1200, hop_length=300,
                                         n_fft=2048, f_min=20.0, f_max=8000.0, target_length=50)
     assert f2.shape == (50, 80) and np.all(f2[41:] == 0)
@@ -118,6 +118,50 @@ def test_cmvn_stats(pkg, built_lib):
     st = pkg.global_cmvn_stats([torch.from_numpy(f).cuda() for f in feats])
     ref = ofe.global_cmvn_stats(feats)
     assert np.allclose(st["mean"], ref["mean"], atol=1e-5) and np.allclose(st["std"], ref["std"], atol=1e-5)
+
+
+def test_default_arguments_and_other_fft_sizes(pkg, built_lib):
+    """extract_logmel_spectrogram called with the reference's OWN defaults (win 1024 / hop 256 / n_fft 1024, f_min 0;
+    examples/speech_synthesis/data_utils.py:46-52) and TTSSpectrogram / TTSMelScale at n_fft 512 / 4096: the generic
+    kernels, against fixtures from the reference modules and the oracle."""
+    g = load_golden("logmel_default.npz")
+    for i in range(3):
+        w = torch.from_numpy(g["wave%d" % i])[None]
+        f = pkg.extract_logmel_spectrogram(w, 22050)  # every geometry argument at its default
+        assert isinstance(f, np.ndarray) and f.shape == g["feat%d" % i].shape
+        assert ogl.rel_l2(f, g["feat%d" % i]) < 1e-5
+        assert np.abs(f - g["feat%d" % i]).max() < 1e-4
+    st = pkg.TTSSpectrogram(512, 400, 160, window_fn=torch.hamming_window, return_phase=True)
+    mag, ph = st(torch.from_numpy(g["stft512_in"]).cuda()[None])
+    mag, ph = mag[0].cpu().numpy(), ph[0].cpu().numpy()
+    assert mag.shape == g["stft512_mag"].shape == (257, 26)
+    assert ogl.rel_l2(mag, g["stft512_mag"]) < 2e-6
+    d = np.angle(np.exp(1j * (ph.astype(np.float64) - g["stft512_phase"])))
+    assert np.sqrt((g["stft512_mag"] * d ** 2).sum() / g["stft512_mag"].sum()) < 1e-4
+    # a large transform, ragged batch, fused CMVN and statistics through the generic path
+    waves = [torch.from_numpy(synth_audio(n, 48000, 90 + i)) for i, n in enumerate((30000, 5000, 9001))]
+    mean, std = np.linspace(-5, -3, 64).astype(np.float32), np.linspace(0.5, 2, 64).astype(np.float32)
+    stats = torch.zeros(2, 64, dtype=torch.float64, device="cuda")
+    outs = pkg.logmel_batch(waves, 48000, 2400, 600, 4096, torch.hann_window, 64, 50.0, 12000.0, stats=stats)
+    fused = pkg.logmel_batch(waves, 48000, 2400, 600, 4096, torch.hann_window, 64, 50.0, 12000.0, cmvn_mean=mean, cmvn_std=std)
+    for w, o, fo in zip(waves, outs, fused):
+        ref = ofe.logmel_spectrogram(w.numpy(), 48000, 2400, 600, 4096, 64, 50.0, 12000.0)
+        assert o.shape == ref.shape and ogl.rel_l2(o.cpu().numpy(), ref) < 1e-5
+        assert np.abs(fo.cpu().numpy() - (o.cpu().numpy() - mean) / std).max() < 2e-5
+    allf = torch.cat(outs).double()
+    assert torch.allclose(stats[0], allf.sum(0), rtol=1e-6, atol=1e-4)
+    # mel projection module at another size
+    spec = torch.rand(2, 257, 9)
+    mel = pkg.TTSMelScale(40, 16000, 20.0, 7600.0, 257)
+    want = torch.matmul(mel.basis, spec)
+    assert torch.allclose(mel(spec.cuda()).cpu(), want, rtol=1e-5, atol=1e-6)
+    # what stays 2048-only says so, clearly, before any kernel runs
+    with pytest.raises(ValueError, match="n_fft"):
+        pkg.GriffinLim(1024, 1024, 256, 4)
+    with pytest.raises(ValueError, match="n_fft"):
+        pkg.GriffinLimVocoder(22050, 1024, 256, 1024, 80, 0, 8000, torch.hann_window)
+    with pytest.raises(ValueError, match="power of two"):
+        pkg.extract_logmel_spectrogram(torch.zeros(1, 4000), 22050, n_fft=1200, win_length=1200, hop_length=300)
 
 
 def test_get_global_cmvn_drop_in_matches_reference_fixture(pkg, built_lib, tmp_path):

@@ -118,6 +118,22 @@ def test_cmvn_stats_roundtrip():
     assert np.allclose(st["std"], allf.std(0), atol=1e-3)
 
 
+def test_generic_geometry_oracle_matches_reference():
+    """The reference's own default log-mel geometry (n_fft 1024 / hop 256 / win 1024, f_min 0, 22.05 kHz) and an
+    n_fft 512 hamming STFT with phase: oracle vs the fixtures produced by the reference modules."""
+    g = load_golden("logmel_default.npz")
+    for i in range(3):
+        f = fe.logmel_spectrogram(g["wave%d" % i], 22050, 1024, 256, 1024, 80, 0.0, 8000.0)
+        assert f.shape == g["feat%d" % i].shape
+        assert gl.rel_l2(f, g["feat%d" % i]) < 1e-5
+    n = np.arange(400, dtype=np.float64)
+    ham = (0.54 - 0.46 * np.cos(2 * np.pi * n / 400)).astype(np.float32)  # torch.hamming_window(400), periodic
+    mag, ph = gl.stft(g["stft512_in"], 512, 400, 160, window=ham)
+    assert gl.rel_l2(mag, g["stft512_mag"]) < 2e-6
+    d = np.angle(np.exp(1j * (ph.astype(np.float64) - g["stft512_phase"])))
+    assert np.sqrt((g["stft512_mag"] * d ** 2).sum() / g["stft512_mag"].sum()) < 1e-4
+
+
 def gcmvn_fixture_arrays():
     """The feature files of tests/golden/gcmvn_stats.npz regenerated from their seeds (make_golden.gcmvn_files)."""
     g = load_golden("gcmvn_stats.npz")
