@@ -246,6 +246,13 @@ int s2st_dtw(int bsz, int m, int n, const float* distance_dev, const int64_t* sh
  * x2_dev [n, d]. */
 int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev, float* out_dev, void* stream);
 
+/* The padded distance batch of batch_compute_distortion (s2s_translation.py:489-505) in one launch: pair b compares rows
+ * offsets1[b] .. offsets1[b+1] of x1_dev [sum M_b, d] with rows offsets2[b] .. offsets2[b+1] of x2_dev [sum N_b, d];
+ * out_dev [bsz, max_m, max_n] receives compute_rms_dist of the pair in its top-left M_b x N_b corner, zeros elsewhere
+ * (the reference pads and stacks the per-pair matrices on the host). */
+int s2st_rms_dist_batch(int bsz, int max_m, int max_n, int d, const float* x1_dev, const float* x2_dev,
+                        const int32_t* offsets1_dev, const int32_t* offsets2_dev, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

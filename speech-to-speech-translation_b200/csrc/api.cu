@@ -983,4 +983,15 @@ int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev,
     return launch_rms_dist(m, n, d, x1_dev, x2_dev, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int s2st_rms_dist_batch(int bsz, int max_m, int max_n, int d, const float* x1_dev, const float* x2_dev,
+                        const int32_t* offsets1_dev, const int32_t* offsets2_dev, float* out_dev, void* stream) {
+    if (bsz < 0 || max_m < 0 || max_n < 0 || d <= 0 ||
+        (bsz > 0 && (!x1_dev || !x2_dev || !offsets1_dev || !offsets2_dev || !out_dev))) {
+        set_error("bad argument to s2st_rms_dist_batch");
+        return S2ST_EINVAL;
+    }
+    return launch_rms_dist_batch(bsz, max_m, max_n, d, x1_dev, x2_dev, offsets1_dev, offsets2_dev, out_dev,
+                                 static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

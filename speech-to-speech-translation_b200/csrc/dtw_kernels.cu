@@ -98,7 +98,43 @@ __global__ void __launch_bounds__(256) k_rms_dist(int m, int n, int d, const flo
     out[idx] = sqrtf(acc / (float)d);
 }
 
+// The padded distance batch of batch_compute_distortion (s2s_translation.py:489-505) in ONE launch: pair b owns rows
+// off1[b] .. off1[b + 1] of x1 [sum M, d] and off2[b] .. off2[b + 1] of x2 [sum N, d]; out [bsz, max_m, max_n] gets
+// the pair's RMS distance matrix in its top-left corner and zeros elsewhere (what F.pad + torch.stack build on the
+// host in the reference, one matrix at a time).
+__global__ void __launch_bounds__(256) k_rms_dist_batch(int max_m, int max_n, int d, const float* __restrict__ x1,
+                                                         const float* __restrict__ x2, const int* __restrict__ off1,
+                                                         const int* __restrict__ off2, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int r1 = off1[b], m = off1[b + 1] - r1, r2 = off2[b], n = off2[b + 1] - r2;
+    const long long cells = (long long)max_m * max_n;
+    float* o = out + (size_t)b * cells;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < cells; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / max_n), j = (int)(idx - (long long)i * max_n);
+        float v = 0.0f;
+        if (i < m && j < n) {
+            float acc = 0.0f;
+            for (int k = 0; k < d; ++k) {
+                const float t = x1[(size_t)(r1 + i) * d + k] - x2[(size_t)(r2 + j) * d + k];
+                acc = fmaf(t, t, acc);
+            }
+            v = sqrtf(acc / (float)d);
+        }
+        o[idx] = v;
+    }
+}
+
 }  // namespace
+
+int launch_rms_dist_batch(int bsz, int max_m, int max_n, int d, const float* x1, const float* x2, const int* off1,
+                          const int* off2, float* out, cudaStream_t stream) {
+    if (bsz <= 0 || max_m <= 0 || max_n <= 0) return S2ST_OK;
+    const long long cells = (long long)max_m * max_n;
+    dim3 grid((unsigned)min((cells + 255) / 256, (long long)1024), (unsigned)bsz);
+    k_rms_dist_batch<<<grid, 256, 0, stream>>>(max_m, max_n, d, x1, x2, off1, off2, out);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
 
 int launch_dtw(int bsz, int m, int n, const float* dist, const long long* shapes, float* cum, int* bp, int* path,
                cudaStream_t stream) {

@@ -130,6 +130,8 @@ int launch_fill_rects(int n_rects, const int32_t* rects, const float* values, in
 // dtw_kernels.cu
 int launch_dtw(int bsz, int m, int n, const float* dist, const long long* shapes, float* cum, int* bp, int* path,
                cudaStream_t stream);
+int launch_rms_dist_batch(int bsz, int max_m, int max_n, int d, const float* x1, const float* x2, const int* off1,
+                          const int* off2, float* out, cudaStream_t stream);
 int launch_rms_dist(int m, int n, int d, const float* x1, const float* x2, float* out, cudaStream_t stream);
 
 }  // namespace s2st

@@ -9,11 +9,11 @@ host synchronisation per path step); the 13-dimensional MFCC front-end is torcha
 """
 from typing import List, Optional
 
+import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import _lib
-from .plans import require_cuda
+from .plans import require_cuda, upload_small
 
 
 def batch_dynamic_time_warping(distance: torch.Tensor, shapes: Optional[torch.Tensor] = None):
@@ -56,37 +56,70 @@ def compute_l2_dist(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     return compute_rms_dist(x1, x2).pow(2) * x1.size(1)
 
 
-def get_divisor(pathmap, normalize_type):
-    if normalize_type is None:
-        return 1
-    elif normalize_type == "len1":
-        return pathmap.size(0)
-    elif normalize_type == "len2":
-        return pathmap.size(1)
-    elif normalize_type == "path":
-        return pathmap.sum().item()
-    else:
+_DIVISORS = {
+    None: lambda pathmap, path_len: 1,
+    "len1": lambda pathmap, path_len: pathmap.size(0),
+    "len2": lambda pathmap, path_len: pathmap.size(1),
+    "path": lambda pathmap, path_len: path_len,
+}
+
+
+def get_divisor(pathmap, normalize_type, path_len=None):
+    """What the accumulated distance is divided by (s2s_translation.py:478-488): 1, the first / second sequence length,
+    or the number of cells on the warping path (``path_len``: supplied by the batched caller from one device-side
+    reduction; counted here when called on its own, like the reference does)."""
+    if normalize_type not in _DIVISORS:
         raise ValueError(f"normalize_type {normalize_type} not supported")
+    if normalize_type == "path" and path_len is None:
+        path_len = int(pathmap.sum())
+    return _DIVISORS[normalize_type](pathmap, path_len)
 
 
 def batch_compute_distortion(y1: List[torch.Tensor], y2: List[torch.Tensor], sr, feat_fn, dist_fn, normalize_type):
-    d, s, x1, x2 = [], [], [], []
-    for cur_y1, cur_y2 in zip(y1, y2):
-        assert cur_y1.ndim == 1 and cur_y2.ndim == 1
-        cur_x1, cur_x2 = feat_fn(cur_y1), feat_fn(cur_y2)
-        x1.append(cur_x1)
-        x2.append(cur_x2)
-        d.append(dist_fn(cur_x1, cur_x2))
-        s.append(d[-1].size())
-    max_m, max_n = max(ss[0] for ss in s), max(ss[1] for ss in s)
-    d = torch.stack([F.pad(dd, (0, max_n - dd.size(1), 0, max_m - dd.size(0))) for dd in d])
-    s = torch.LongTensor(s).to(d.device)
-    cumdists, backptrs, pathmaps = batch_dynamic_time_warping(d, s)
+    """Distortion of every (y1[b], y2[b]) pair after DTW alignment (s2s_translation.py:491-520), device-first:
+
+    * the features of all pairs are concatenated once; with the library's own ``compute_rms_dist`` as ``dist_fn`` the
+      zero-padded [bsz, max_M, max_N] distance batch is written by ONE kernel (``s2st_rms_dist_batch``) instead of one
+      distance launch, one ``F.pad`` and one ``stack`` slot per pair (any other ``dist_fn`` is applied per pair and
+      padded on the device);
+    * one DTW launch for the batch (``s2st_dtw``), one reduction for all path lengths, ONE host synchronisation for
+      the whole batch (the reference synchronises per pair through ``.item()``).
+
+    Returns the reference's structure: ``[(distortion, (x1, x2, dist, cumdist, backptr, pathmap)), ...]`` with the
+    matrices sliced to the pair's (M, N)."""
+    if normalize_type not in _DIVISORS:
+        raise ValueError(f"normalize_type {normalize_type} not supported")
+    assert len(y1) == len(y2) and len(y1) > 0
+    assert all(a.ndim == 1 and b.ndim == 1 for a, b in zip(y1, y2))
+    x1 = [feat_fn(a) for a in y1]
+    x2 = [feat_fn(b) for b in y2]
+    dev = require_cuda(x1[0].device if x1[0].is_cuda else None)
+    ms, ns = [int(x.shape[0]) for x in x1], [int(x.shape[0]) for x in x2]
+    bsz, max_m, max_n = len(x1), max(ms), max(ns)
+    if dist_fn is compute_rms_dist:
+        cat1 = torch.cat([x.to(dev, torch.float32) for x in x1]).contiguous()
+        cat2 = torch.cat([x.to(dev, torch.float32) for x in x2]).contiguous()
+        off1 = upload_small(np.concatenate([[0], np.cumsum(ms)]).astype(np.int32), dev)
+        off2 = upload_small(np.concatenate([[0], np.cumsum(ns)]).astype(np.int32), dev)
+        dist = torch.empty(bsz, max_m, max_n, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().s2st_rms_dist_batch(bsz, max_m, max_n, cat1.shape[1], _lib.ptr(cat1), _lib.ptr(cat2),
+                                                 _lib.ptr(off1), _lib.ptr(off2), _lib.ptr(dist), _lib.stream_ptr(dev))
+        _lib.check(rc, "s2st_rms_dist_batch")
+    else:
+        dist = torch.zeros(bsz, max_m, max_n, dtype=torch.float32, device=dev)
+        for b, (a, c) in enumerate(zip(x1, x2)):
+            dist[b, : ms[b], : ns[b]] = dist_fn(a, c).to(dev, torch.float32)
+    shapes = upload_small(np.stack([ms, ns], axis=1).astype(np.int64), dev)
+    cumdists, backptrs, pathmaps = batch_dynamic_time_warping(dist, shapes)
+    last = cumdists[torch.arange(bsz, device=dev), shapes[:, 0] - 1, shapes[:, 1] - 1]
+    path_lens = pathmaps.sum(dim=(1, 2)).tolist() if normalize_type == "path" else [None] * bsz  # the one synchronisation
     rets = []
-    for (m, n), cur_x1, cur_x2, dist, cumdist, backptr, pathmap in zip(s, x1, x2, d, cumdists, backptrs, pathmaps):
-        cumdist, backptr, pathmap = cumdist[:m, :n], backptr[:m, :n], pathmap[:m, :n]
-        distortion = cumdist[-1, -1] / get_divisor(pathmap, normalize_type)
-        rets.append((distortion, (cur_x1, cur_x2, dist, cumdist, backptr, pathmap)))
+    for b in range(bsz):
+        m, n = ms[b], ns[b]
+        pathmap = pathmaps[b, :m, :n]
+        distortion = last[b] / get_divisor(pathmap, normalize_type, path_lens[b])
+        rets.append((distortion, (x1[b], x2[b], dist[b], cumdists[b, :m, :n], backptrs[b, :m, :n], pathmap)))
     return rets
 
 

@@ -316,6 +316,7 @@ def test_specaugment_matches_reference(pkg, built_lib):
 
 
 def test_dtw_bit_exact_and_mcd_metric(pkg, built_lib):
+    rng = np.random.RandomState(17)
     """The MCD validation metric (examples/s2s_trans/tasks/s2s_translation.py:414-552): DTW recurrence, back pointers
     and path bit-identical to the reference's functions (ragged shapes, exact ties, full-size default), distance matrix
     within 1e-5, and the end-to-end distortion of two waveform pairs (torchaudio MFCC, as in the reference)."""
@@ -353,6 +354,19 @@ def test_dtw_bit_exact_and_mcd_metric(pkg, built_lib):
         assert np.allclose(got, d["mcd_" + str(nt)], rtol=2e-3), (nt, got, d["mcd_" + str(nt)])
     with pytest.raises(ValueError, match="not supported"):
         mcd.batch_mel_cepstral_distortion(ya, yb, 24000, normalize_type="bogus")
+    # the batched distance builder (one launch, padded on the device) == the per-pair matrices, bitwise; the returned
+    # structure is the reference's; a foreign dist_fn takes the per-pair route and gives the same numbers
+    feats = lambda y: y.reshape(-1, 13)[: y.numel() // 13]
+    za = [torch.from_numpy(rng.randn(13 * n).astype(np.float32)).cuda() for n in (37, 5, 64)]
+    zb = [torch.from_numpy(rng.randn(13 * n).astype(np.float32)).cuda() for n in (29, 9, 64)]
+    rets = mcd.batch_compute_distortion(za, zb, 0, feats, mcd.compute_rms_dist, "len2")
+    rets2 = mcd.batch_compute_distortion(za, zb, 0, feats, lambda a, b: mcd.compute_rms_dist(a, b), "len2")
+    for (dist, (x1, x2, dm, cum, bp, pm)), (dist2, other), a, b in zip(rets, rets2, za, zb):
+        m, n = a.numel() // 13, b.numel() // 13
+        assert dm.shape == (64, 64) and cum.shape == bp.shape == pm.shape == (m, n)
+        assert torch.equal(dm[:m, :n], mcd.compute_rms_dist(feats(a), feats(b))) and float(dm[m:].abs().sum() + dm[:, n:].abs().sum()) == 0
+        assert float(dist) == float(cum[-1, -1]) / n == float(dist2)
+        assert int(pm.sum()) >= max(m, n) and int(pm[0, 0]) == 1 and int(pm[-1, -1]) == 1
 
 
 def test_composite_chain_on_a_ragged_device_batch(pkg, built_lib, tmp_path):
