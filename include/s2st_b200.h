@@ -246,6 +246,11 @@ int s2st_dtw(int bsz, int m, int n, const float* distance_dev, const int64_t* sh
  * x2_dev [n, d]. */
 int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev, float* out_dev, void* stream);
 
+/* Waveform post-processing for file output (examples/s2s_trans/generate_waveform.py:115-124: sf.write of the float
+ * waveform, which soundfile stores as 16-bit PCM): pcm[i] = saturate_int16(lrint(wave[i] * 32767)), NaN -> 0.  Runs on
+ * the concatenated batch so the device-to-host copy carries 2 bytes per sample. */
+int s2st_wave_to_pcm16(int64_t n_samples, const float* wave_dev, int16_t* pcm_out_dev, void* stream);
+
 /* The padded distance batch of batch_compute_distortion (s2s_translation.py:489-505) in one launch: pair b compares rows
  * offsets1[b] .. offsets1[b+1] of x1_dev [sum M_b, d] with rows offsets2[b] .. offsets2[b+1] of x2_dev [sum N_b, d];
  * out_dev [bsz, max_m, max_n] receives compute_rms_dist of the pair in its top-left M_b x N_b corner, zeros elsewhere

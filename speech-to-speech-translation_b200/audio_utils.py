@@ -155,9 +155,26 @@ class TTSMelScale(torch.nn.Module):
         return out.reshape(shape[:-2] + (self.n_mels, shape[-1])).to(specgram.device, specgram.dtype)
 
 
+def convert_waveform(waveform, sample_rate: int, normalize_volume: bool = False, to_mono: bool = False,
+                     to_sample_rate: Optional[int] = None):
+    """The reference's convert_waveform (audio_utils.py:20-62) runs sox effects (``gain -n``, ``rate``, ``channels 1``)
+    through torchaudio.  Down-mixing is a channel mean and is done here; volume normalisation and resampling are sox's
+    own arithmetic and are not reproduced: requesting them raises ``NotImplementedError`` instead of silently returning
+    something else."""
+    if normalize_volume:
+        raise NotImplementedError("normalize_volume (sox 'gain -n') is not provided")
+    if to_sample_rate is not None and to_sample_rate != sample_rate:
+        raise NotImplementedError(f"resampling {sample_rate} -> {to_sample_rate} Hz (sox 'rate') is not provided")
+    if to_mono and waveform.shape[0] > 1:
+        waveform = waveform.mean(axis=0, keepdims=True)
+    return waveform, sample_rate
+
+
 def get_waveform(path_or_fp: Union[str, BinaryIO], normalization: bool = True, mono: bool = True,
-                 frames: int = -1, start: int = 0, always_2d: bool = True) -> Tuple[np.ndarray, int]:
-    """16-bit WAV/FLAC/OGG reader (file IO; adjacent to the hot path, audio_utils.py:65-109)."""
+                 frames: int = -1, start: int = 0, always_2d: bool = True, output_sample_rate: Optional[int] = None,
+                 normalize_volume: bool = False) -> Tuple[np.ndarray, int]:
+    """16-bit WAV/FLAC/OGG reader with the reference's full signature (audio_utils.py:65-109).  soundfile is used when
+    it is installed; without it 16-bit PCM WAV files are parsed directly (``io_utils.read_wav16``)."""
     if isinstance(path_or_fp, str):
         ext = Path(path_or_fp).suffix
         if ext not in SF_AUDIO_FILE_EXTENSIONS:
@@ -165,13 +182,24 @@ def get_waveform(path_or_fp: Union[str, BinaryIO], normalization: bool = True, m
     try:
         import soundfile as sf
     except ImportError:
-        raise ImportError("Please install soundfile: pip install soundfile")
-    waveform, sample_rate = sf.read(path_or_fp, dtype="float32", always_2d=True, frames=frames, start=start)
-    waveform = waveform.T
-    if mono and waveform.shape[0] > 1:
-        waveform = waveform.mean(axis=0, keepdims=True)
+        sf = None
+    if sf is not None:
+        waveform, sample_rate = sf.read(path_or_fp, dtype="float32", always_2d=True, frames=frames, start=start)
+        waveform = waveform.T  # T x C -> C x T
+    else:
+        from .io_utils import read_wav16
+        raw = path_or_fp.read() if hasattr(path_or_fp, "read") else path_or_fp
+        try:
+            waveform, sample_rate = read_wav16(raw)
+        except ValueError as e:
+            raise ImportError(f"Please install soundfile: pip install soundfile ({e})")
+        n = waveform.shape[1]
+        begin = start if start >= 0 else max(n + start, 0)
+        waveform = waveform[:, begin: n if frames < 0 else begin + frames]
+    waveform, sample_rate = convert_waveform(waveform, sample_rate, normalize_volume=normalize_volume, to_mono=mono,
+                                             to_sample_rate=output_sample_rate)
     if not normalization:
-        waveform = waveform * (2 ** 15)
+        waveform = waveform * (2 ** 15)  # denormalised to 16-bit signed integers
     if not always_2d:
         waveform = waveform.squeeze(axis=0)
     return waveform, sample_rate

@@ -983,6 +983,14 @@ int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev,
     return launch_rms_dist(m, n, d, x1_dev, x2_dev, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int s2st_wave_to_pcm16(int64_t n_samples, const float* wave_dev, int16_t* pcm_out_dev, void* stream) {
+    if (n_samples < 0 || (n_samples > 0 && (!wave_dev || !pcm_out_dev))) {
+        set_error("bad argument to s2st_wave_to_pcm16");
+        return S2ST_EINVAL;
+    }
+    return launch_wave_to_pcm16(n_samples, wave_dev, pcm_out_dev, static_cast<cudaStream_t>(stream));
+}
+
 int s2st_rms_dist_batch(int bsz, int max_m, int max_n, int d, const float* x1_dev, const float* x2_dev,
                         const int32_t* offsets1_dev, const int32_t* offsets2_dev, float* out_dev, void* stream) {
     if (bsz < 0 || max_m < 0 || max_n < 0 || d <= 0 ||

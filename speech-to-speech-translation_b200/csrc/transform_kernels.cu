@@ -145,7 +145,41 @@ __global__ void __launch_bounds__(256) k_fill_rects(const int4* __restrict__ rec
     }
 }
 
+// Waveform post-processing of generate_waveform.py:115-124 (soundfile writes float data to a WAV / FLAC file as 16-bit
+// PCM): sample = lrint(x * 32767) like libsndfile's float -> short conversion, saturated to the int16 range.  Done on
+// the device for the whole batch so the download is 2 bytes per sample instead of 4.  HBM-bound: 4 B in + 2 B out.
+__global__ void __launch_bounds__(256) k_wave_to_pcm16(long long n, const float* __restrict__ x, short* __restrict__ out) {
+    const long long n8 = n >> 3;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    auto cvt = [](float v) -> unsigned {
+        const float s = fminf(fmaxf(v * 32767.0f, -32768.0f), 32767.0f);
+        return (unsigned)(unsigned short)(short)__float2int_rn(s);  // NaN -> 0
+    };
+    if (vec) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(x) + 2 * i), b = __ldcs(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+            uint4 o;
+            o.x = cvt(a.x) | (cvt(a.y) << 16);
+            o.y = cvt(a.z) | (cvt(a.w) << 16);
+            o.z = cvt(b.x) | (cvt(b.y) << 16);
+            o.w = cvt(b.z) | (cvt(b.w) << 16);
+            __stcs(reinterpret_cast<uint4*>(out) + i, o);
+        }
+    }
+    const long long tail0 = vec ? n8 << 3 : 0;
+    for (long long i = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (short)cvt(x[i]);
+}
+
 }  // namespace
+
+int launch_wave_to_pcm16(long long n, const float* x, short* out, cudaStream_t stream) {
+    if (n <= 0) return S2ST_OK;
+    const int grid = (int)min((long long)148 * 8, (n / 8 + 255) / 256 + 1);
+    k_wave_to_pcm16<<<grid, 256, 0, stream>>>(n, x, out);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
 
 int launch_utterance_cmvn(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const float* x, float* out,
                           bool norm_means, bool norm_vars, float* stats, cudaStream_t stream) {
