@@ -142,6 +142,7 @@ def load_feature_batch(paths: Sequence[str], pin_memory: bool = True):
             if dtype == np.float32 and not fortran:
                 src = np.frombuffer(mm, dtype=np.float32, count=T * n_feat, offset=off + data_off)
                 dst[row: row + T] = src.reshape(T, n_feat)
+                del src  # the view pins the mapping: release it before the archive is closed
             else:
                 dst[row: row + T] = np.load(io.BytesIO(mm[off: off + size])).reshape(T, n_feat).astype(np.float32)
             row += T
