@@ -625,13 +625,13 @@ def run_gl_sharded(args, ctx):
     def synth():
         keep["waves"] = [voc.synthesize_flat(lm, fr, ph) for fr, lm, ph in devb]
 
+    ids_local = [i for b in buckets for i in b]
+    lens_local = [(frames_all[i] - 1) * HOP for i in ids_local]
+
     def gather():
-        local = []
-        for (fr, _, _), w in zip(devb, keep["waves"]):
-            local.extend(torch.split(w, [(T - 1) * HOP for T in fr]))
-        ids = [i for b in buckets for i in b]
+        flat = keep["waves"][0] if len(keep["waves"]) == 1 else torch.cat(keep["waves"])
         st = {}
-        keep["gathered"] = sh.gather_waveforms(ids, local, len(frames_all), dst=0, stats=st)
+        keep["gathered"] = sh.gather_waveforms(ids_local, flat, len(frames_all), dst=0, stats=st, local_lengths=lens_local)
         keep["gather_stats"] = st
 
     def step():

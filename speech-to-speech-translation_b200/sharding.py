@@ -55,8 +55,8 @@ def length_buckets(n_frames: Sequence[int], indices: Sequence[int], max_frames: 
     return batches
 
 
-def gather_waveforms(local_ids: Sequence[int], local_waves: Sequence[torch.Tensor], n_total: int, dst: int = 0,
-                     group=None, stats: Optional[dict] = None):
+def gather_waveforms(local_ids: Sequence[int], local_waves, n_total: int, dst: int = 0,
+                     group=None, stats: Optional[dict] = None, local_lengths: Optional[Sequence[int]] = None):
     """Final ragged gather: rank ``dst`` receives every utterance's waveform in global order.
 
     The only exchange of the multi-GPU path (the reference's shards each write their own files,
@@ -64,14 +64,23 @@ def gather_waveforms(local_ids: Sequence[int], local_waves: Sequence[torch.Tenso
     ONLY -- every rank sends one exact-size payload (no padding), ``dst`` receives them into slices of one buffer, all
     in one batched send/recv group (NCCL: ncclGroupStart/End; gloo in the CPU tests).  Returns a list of n_total
     tensors (views into the receive buffer) on ``dst``, ``None`` elsewhere.  ``stats`` (optional dict) receives the
-    bytes that crossed the fabric."""
+    bytes that crossed the fabric.  ``local_waves`` is a list of per-utterance tensors, or -- cheaper for thousands of
+    utterances -- ONE flat tensor with the utterances back to back and ``local_lengths`` giving their sizes (the form
+    ``GriffinLimVocoder.synthesize_flat`` returns)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     nccl = dist.get_backend(group) == "nccl"
-    device = local_waves[0].device if len(local_waves) else (
-        torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu"))
+    flat_in = isinstance(local_waves, torch.Tensor)
+    if flat_in:
+        assert local_lengths is not None and int(sum(local_lengths)) == local_waves.numel()
+        lens_local = [int(n) for n in local_lengths]
+        device = local_waves.device
+    else:
+        lens_local = [int(w.numel()) for w in local_waves]
+        device = local_waves[0].device if len(local_waves) else (
+            torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu"))
     n_local = len(local_ids)
-    size_local = int(sum(w.numel() for w in local_waves))
+    size_local = int(sum(lens_local))
     meta = torch.tensor([n_local, size_local], dtype=torch.int64, device=device)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta, group=group)
@@ -80,10 +89,12 @@ def gather_waveforms(local_ids: Sequence[int], local_waves: Sequence[torch.Tenso
     # (id, length) pairs are a second, tiny int64 message of the same group
     idx = torch.empty(2, n_local, dtype=torch.int64, device=device)
     if n_local:
-        idx[0] = torch.as_tensor(list(local_ids), dtype=torch.int64)
-        idx[1] = torch.as_tensor([w.numel() for w in local_waves], dtype=torch.int64)
-    flat = (torch.cat([w.reshape(-1).float() for w in local_waves]) if n_local
-            else torch.empty(0, dtype=torch.float32, device=device))
+        idx.copy_(torch.tensor([list(local_ids), lens_local], dtype=torch.int64))
+    if flat_in:
+        flat = local_waves.reshape(-1).float()
+    else:
+        flat = (torch.cat([w.reshape(-1).float() for w in local_waves]) if n_local
+                else torch.empty(0, dtype=torch.float32, device=device))
     ops, recv_idx, recv_payload = [], {}, {}
     if rank == dst:
         for r in range(world):
@@ -111,12 +122,12 @@ def gather_waveforms(local_ids: Sequence[int], local_waves: Sequence[torch.Tenso
     recv_idx[dst], recv_payload[dst] = idx, flat
     out = [None] * n_total
     for r in range(world):
-        ids = recv_idx[r][0].tolist()
-        lens = recv_idx[r][1].tolist()
-        off = 0
-        for i, n in zip(ids, lens):
-            out[i] = recv_payload[r][off: off + n]
-            off += n
+        if r == dst:
+            ids, lens = list(local_ids), lens_local
+        else:
+            ids, lens = recv_idx[r].tolist()  # one download per sending rank
+        for i, piece in zip(ids, torch.split(recv_payload[r], lens)):
+            out[i] = piece
     return out
 
 

@@ -67,6 +67,11 @@ def _worker(rank, world, port, q):
         q.put(ok)
     else:
         assert out is None
+    # the flat form (one tensor + lengths, what synthesize_flat returns) gives the same result
+    out_flat = sh.gather_waveforms(mine, torch.cat(waves) if waves else torch.empty(0), len(frames), dst=0,
+                                   local_lengths=[w.numel() for w in waves])
+    if rank == 0:
+        assert all(torch.equal(a, b) for a, b in zip(out, out_flat))
     # a rank with nothing to send, and a non-zero destination
     mine2 = list(range(len(frames))) if rank == 0 else []
     waves2 = [torch.full((frames[i],), float(i)) for i in mine2]
