@@ -75,6 +75,7 @@ int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
 #define S2ST_OPT_INVERSE_MEL 4      /* [S2ST_INVERSE_MEL=simt] 0 (default): tcgen05 tensor-core inverse-mel; 1: FP32 SIMT kernel */
 #define S2ST_OPT_FRONTEND_GENERIC 5 /* [S2ST_LOGMEL_GENERIC / S2ST_FBANK_GENERIC] 0 (default): register-resident log-mel / fbank
                                        kernels where they apply; 1: always the generic kernels */
+#define S2ST_OPT_MEL_PROJECT 6      /* 0 (default): tcgen05 tensor-core mel projection (s2st_mel_project); 1: FP32 SIMT CSR kernel */
 int s2st_plan_set_option(s2st_plan* plan, int option, int value);
 
 /* ------------------------------------------------------------------------------------------ */
@@ -138,7 +139,9 @@ int s2st_inverse_mel(const s2st_plan* plan, int64_t n_frames, const float* mel_d
                      float* mag_dev, void* stream);
 
 /* TTSMelScale.forward (audio_utils.py:284-285) on frame-major data:
- *   mel_out[t, m] = sum_f mel[m, f] * spec[t, f] */
+ *   mel_out[t, m] = sum_f mel[m, f] * spec[t, f]
+ * The dense [n_mels x n_bins] contraction runs on the tensor cores (tcgen05, 3 x TF32 split, fp32 accumulation in TMEM;
+ * ~1e-6 relative to an fp32 matmul) for filterbanks of up to 128 mel bins; S2ST_OPT_MEL_PROJECT selects the SIMT kernel. */
 int s2st_mel_project(const s2st_plan* plan, int64_t n_frames, const float* spec_dev,
                      float* mel_out_dev, void* stream);
 

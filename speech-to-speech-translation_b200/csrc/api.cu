@@ -65,6 +65,16 @@ void to_csr(const float* dense, int rows, int cols, std::vector<int>& ptr, std::
     }
 }
 
+// the mel filterbank in tensor-core form (mel_tc.cu); skipped for banks wider than the kernel's accumulator
+int upload_mel_tc(s2st_plan* p, const float* mel_host) {
+    if (p->n_mels > 128) return S2ST_OK;
+    p->mel_tc_chunks = mel_project_tc_chunks(mel_host, p->n_mels, p->n_bins);
+    if (p->mel_tc_chunks == 0) return S2ST_OK;
+    std::vector<float> tc(mel_project_tc_floats(p->n_mels, p->mel_tc_chunks));
+    build_mel_project_tc(mel_host, p->n_mels, p->n_bins, p->mel_tc_chunks, tc.data());
+    return upload(&p->mel_tc, tc);
+}
+
 void free_plan_members(s2st_plan* p) {
     for (int i = 0; i <= kMaxTimedPasses; ++i)
         if (p->timing_events[i]) cudaEventDestroy(p->timing_events[i]);
@@ -84,6 +94,7 @@ void free_plan_members(s2st_plan* p) {
     cudaFree(p->vp64);
     cudaFree(p->inv_mel_t);
     cudaFree(p->inv_mel_tc);
+    cudaFree(p->mel_tc);
     cudaFree(p->mel_ptr);
     cudaFree(p->mel_idx);
     cudaFree(p->mel_val);
@@ -192,6 +203,7 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
             rc = upload(&p->mel_ptr, ptr);
             if (rc == S2ST_OK) rc = upload(&p->mel_idx, idx);
             if (rc == S2ST_OK) rc = upload(&p->mel_val, val);
+            if (rc == S2ST_OK) rc = upload_mel_tc(p, mel_host);
         }
         if (rc != S2ST_OK) {
             free_plan_members(p);
@@ -333,6 +345,7 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         rc = upload(&p->mel_ptr, ptr);
         if (rc == S2ST_OK) rc = upload(&p->mel_idx, idx);
         if (rc == S2ST_OK) rc = upload(&p->mel_val, val);
+        if (rc == S2ST_OK) rc = upload_mel_tc(p, mel_host);
         // column view (k_logmel_fast): lane l owns bins 22 l .. 22 l + 21 and keeps one pair of partial sums per run
         // of bins that feed the same mel bin b ("slot"); see plan.h
         constexpr int kpl = 22, lanes = 32, max_slots = 17, max_terms = 8;
@@ -456,6 +469,9 @@ int s2st_plan_set_option(s2st_plan* plan, int option, int value) {
             return S2ST_OK;
         case S2ST_OPT_FRONTEND_GENERIC:
             plan->opt_frontend_generic = value != 0;
+            return S2ST_OK;
+        case S2ST_OPT_MEL_PROJECT:
+            plan->opt_mel_simt = value != 0;
             return S2ST_OK;
         default:
             break;

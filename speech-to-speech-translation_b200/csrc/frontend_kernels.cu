@@ -1053,6 +1053,8 @@ int launch_mel_project(const s2st_plan* plan, long long n_frames, const float* s
         return S2ST_EINVAL;
     }
     if (n_frames <= 0) return S2ST_OK;
+    // dense 80 x 1025 contraction -> tensor cores (tcgen05, 3 x TF32); S2ST_OPT_MEL_PROJECT = 1 keeps the SIMT CSR kernel
+    if (!plan->opt_mel_simt && mel_project_tc_supported(plan)) return launch_mel_project_tc(plan, n_frames, spec, out, stream);
     const int grid = (int)min((long long)plan->num_sms * 8, (n_frames + 7) / 8);
     k_mel_project<<<grid, 256, 0, stream>>>(n_frames, plan->n_mels, plan->n_bins, spec, plan->mel_ptr, plan->mel_idx,
                                             plan->mel_val, out);

@@ -192,7 +192,166 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward mel projection (TTSMelScale.forward, audio_utils.py:284-285) on the tensor cores:
+//   mel_out[t, m] = sum_f mel[m, f] * spec[t, f]      D[M = 128 frames, N = n_mels] = A[M, K = bins] * B[N, K]^T
+// the other dense contraction of the path (80 x 1025).  Same 3 x TF32 split as above.  K is walked in chunks of 64 bins:
+// the CTA stages the chunk of its 128 spectrogram rows (coalesced 128-byte row segments from global, hi / lo split,
+// canonical K-major layout) and the pre-split chunk of the filterbank (built once by the plan, L2 resident), one
+// elected thread issues 3 x 8 tcgen05.mma into ONE accumulator that stays in TMEM across all chunks, and after the
+// last chunk every thread reads its frame's n_mels sums back with tcgen05.ld.  104 KB of shared memory per CTA: two
+// CTAs per SM overlap one's loads with the other's MMAs.  Bins beyond the last non-zero filterbank column are skipped.
+constexpr int kMpKChunk = 64;
+constexpr int kMpMaxN = 128;
+
+struct MelProjParams {
+    const float* spec;      // [n_frames, n_bins]
+    const float* b_tc;      // [k_chunks][2 (hi, lo)][kMpKChunk / 4][n_pad / 8][8][4]
+    float* out;             // [n_frames, n_mels]
+    long long n_frames;
+    int n_bins, n_mels, n_pad, k_chunks;
+};
+
+__global__ void __launch_bounds__(128, 2) k_mel_project_tc(const __grid_constant__ MelProjParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int a_floats = kTcM * kMpKChunk;
+    const int b_floats = p.n_pad * kMpKChunk;
+    float* sA_hi = reinterpret_cast<float*>(smem_raw);
+    float* sA_lo = sA_hi + a_floats;
+    float* sB_hi = sA_lo + a_floats;
+    float* sB_lo = sB_hi + b_floats;
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long t0 = (long long)blockIdx.x * kTcM;
+    const int rows = (int)min((long long)kTcM, p.n_frames - t0);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kMpMaxN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    // D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+    const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (uint32_t)(p.n_pad / 8) * 128, sbo = 128;
+    uint32_t phase = 0, acc = 0;
+    for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int k0 = kc * kMpKChunk;
+        // A chunk: warp w stages rows w, w + 4, ...; a row segment is 64 consecutive floats (rows are 4-byte aligned only)
+        for (int row = warp; row < kTcM; row += 4) {
+            const float* src = p.spec + (t0 + row) * (long long)p.n_bins + k0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 32 * h + lane;
+                const float v = (row < rows && k0 + k < p.n_bins) ? __ldg(src + k) : 0.0f;
+                const float hi = tf32_round(v);
+                const int off = canon_off(row, k, kTcM / 8);
+                sA_hi[off] = hi;
+                sA_lo[off] = v - hi;
+            }
+        }
+        const float4* bsrc = reinterpret_cast<const float4*>(p.b_tc + (size_t)kc * 2 * b_floats);
+        float4* bdst = reinterpret_cast<float4*>(sB_hi);
+        for (int i = tid; i < 2 * b_floats / 4; i += 128) bdst[i] = __ldg(bsrc + i);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {
+                const uint32_t a_base = smem_u32(term == 2 ? sA_lo : sA_hi);
+                const uint32_t b_base = smem_u32(term == 1 ? sB_lo : sB_hi);
+                for (int ks = 0; ks < kMpKChunk / 8; ++ks) {
+                    mma_tf32(tmem, make_desc(a_base + ks * 2 * lbo_a, lbo_a, sbo), make_desc(b_base + ks * 2 * lbo_b, lbo_b, sbo), idesc, acc);
+                    acc = 1;
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+        }
+        mbar_wait(smem_u32(&s_bar), phase);  // the MMAs have read this chunk: its buffers may be refilled
+        phase ^= 1;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    float* orow = p.out + (t0 + tid) * (long long)p.n_mels;
+    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(lane_addr + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (tid < rows) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.n_mels) orow[c0 + j] = __uint_as_float(r[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kMpMaxN));
+}
+
 }  // namespace
+
+// Host: the mel filterbank [n_mels, n_bins] pre-split into TF32 head / tail, one canonical K-major tile of n_pad rows x
+// 64 bins per K chunk.  Returns the number of chunks that hold non-zero weights (bins beyond them are never read).
+int mel_project_tc_chunks(const float* mel, int n_mels, int n_bins) {
+    int last = -1;
+    for (int m = 0; m < n_mels; ++m)
+        for (int k = 0; k < n_bins; ++k)
+            if (mel[(size_t)m * n_bins + k] != 0.0f && k > last) last = k;
+    return last < 0 ? 0 : last / kMpKChunk + 1;
+}
+int mel_project_tc_npad(int n_mels) { return (n_mels + 15) & ~15; }
+size_t mel_project_tc_floats(int n_mels, int k_chunks) { return (size_t)k_chunks * 2 * mel_project_tc_npad(n_mels) * kMpKChunk; }
+void build_mel_project_tc(const float* mel, int n_mels, int n_bins, int k_chunks, float* out) {
+    const int n_pad = mel_project_tc_npad(n_mels), b_floats = n_pad * kMpKChunk;
+    for (size_t i = 0; i < mel_project_tc_floats(n_mels, k_chunks); ++i) out[i] = 0.0f;
+    for (int m = 0; m < n_mels; ++m)
+        for (int k = 0; k < n_bins && k < k_chunks * kMpKChunk; ++k) {
+            const float v = mel[(size_t)m * n_bins + k];
+            uint32_t u;
+            memcpy(&u, &v, 4);
+            uint32_t h = (u + 0x1000u) & 0xFFFFE000u;  // cvt.rna.tf32.f32
+            if ((u & 0x7F800000u) == 0x7F800000u) h = u;
+            float hi;
+            memcpy(&hi, &h, 4);
+            const int chunk = k / kMpKChunk, off = canon_off(m, k % kMpKChunk, n_pad / 8);
+            out[(size_t)(chunk * 2 + 0) * b_floats + off] = hi;
+            out[(size_t)(chunk * 2 + 1) * b_floats + off] = v - hi;
+        }
+}
+
+bool mel_project_tc_supported(const s2st_plan* plan) {
+    return plan->mel_tc != nullptr && plan->mel_tc_chunks > 0 && plan->n_mels <= kMpMaxN;
+}
+
+int launch_mel_project_tc(const s2st_plan* plan, long long n_frames, const float* spec, float* out, cudaStream_t stream) {
+    if (n_frames <= 0) return S2ST_OK;
+    MelProjParams p;
+    p.spec = spec;
+    p.b_tc = plan->mel_tc;
+    p.out = out;
+    p.n_frames = n_frames;
+    p.n_bins = plan->n_bins;
+    p.n_mels = plan->n_mels;
+    p.n_pad = mel_project_tc_npad(plan->n_mels);
+    p.k_chunks = plan->mel_tc_chunks;
+    const size_t smem = sizeof(float) * (size_t)(2 * kTcM * kMpKChunk + 2 * p.n_pad * kMpKChunk) + 1024;
+    S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_mel_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long blocks = (n_frames + kTcM - 1) / kTcM;
+    k_mel_project_tc<<<(unsigned)blocks, 128, smem, stream>>>(p);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
 
 // Host: pre-split the pseudo-inverse basis into TF32 head / tail in the canonical per-chunk layout.
 // inv_mel [n_bins_total, K] row-major (K-major), rows >= kb are zero.

@@ -32,6 +32,9 @@ struct s2st_plan {
     float* inv_mel_tc_perm;
     float* inv_mel_t;   // [n_mels, kb_pad] transposed pseudo-inverse (NULL if absent)
     float* inv_mel_tc;  // the same basis pre-split into TF32 head / tail in UMMA layout (mel_tc.cu), or NULL
+    float* mel_tc;      // the mel filterbank pre-split into TF32 head / tail in UMMA layout, per 64-bin K chunk (mel_tc.cu), or NULL
+    int mel_tc_chunks;  // K chunks that hold non-zero weights
+    int opt_mel_simt;   // 0 = tcgen05 mel projection (default), 1 = FP32 SIMT CSR kernel
     int* mel_ptr;       // CSR of the mel filterbank: [n_mels + 1]
     int* mel_idx;       // [nnz] bin indices, ascending per row
     float* mel_val;     // [nnz]
@@ -103,6 +106,12 @@ size_t inverse_mel_tc_floats(int K);
 bool inverse_mel_tc_supported(const s2st_plan* plan);
 int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float* mel, bool is_log, float* mag,
                           int out_stride, int n_out, cudaStream_t stream, const float* basis_tc = nullptr);
+
+int mel_project_tc_chunks(const float* mel, int n_mels, int n_bins);
+size_t mel_project_tc_floats(int n_mels, int k_chunks);
+void build_mel_project_tc(const float* mel, int n_mels, int n_bins, int k_chunks, float* out);
+bool mel_project_tc_supported(const s2st_plan* plan);
+int launch_mel_project_tc(const s2st_plan* plan, long long n_frames, const float* spec, float* out, cudaStream_t stream);
 
 // frontend_kernels.cu
 int launch_stft(const s2st_plan* plan, int n_utts, long long total_frames, const int64_t* wave_offsets,

@@ -120,6 +120,29 @@ def test_cmvn_stats(pkg, built_lib):
     assert np.allclose(st["mean"], ref["mean"], atol=1e-5) and np.allclose(st["std"], ref["std"], atol=1e-5)
 
 
+def test_mel_projection_tensor_core_vs_simt_vs_float64(pkg, built_lib):
+    """TTSMelScale.forward: the tcgen05 3 x TF32 kernel against the FP32 SIMT CSR kernel and a float64 matmul, incl. a
+    ragged last 128-frame tile, a single frame, and a bank that uses all 1025 bins (17 K chunks)."""
+    import importlib
+    plans = importlib.import_module(pkg.__name__ + ".plans")
+    rng = np.random.RandomState(4)
+    for n_mels, sr, f_max in ((80, 24000, 8000.0), (128, 24000, 12000.0), (40, 24000, 3000.0)):
+        mel = pkg.TTSMelScale(n_mels, sr, 20.0, f_max, 1025).cuda()
+        plan = plans.get_stft_plan("cuda", 2048, 2048, 512, n_mels, torch.ones(2048), mel=mel.basis)
+        for T in (1, 127, 300):
+            spec = torch.from_numpy(np.abs(rng.randn(1025, T)).astype(np.float32) * np.exp(rng.randn(1025, 1) * 2).astype(np.float32))
+            want = mel.basis.double().cpu() @ spec.double()
+            outs = {}
+            for mode in (0, 1):
+                plan.set_option(pkg._lib.OPT_MEL_PROJECT, mode)
+                outs[mode] = mel(spec.cuda()).cpu().double()
+            plan.set_option(pkg._lib.OPT_MEL_PROJECT, 0)
+            for mode in (0, 1):
+                assert outs[mode].shape == (n_mels, T)
+                assert float((outs[mode] - want).norm() / want.norm()) < 2e-6, (n_mels, T, mode)
+            assert float((outs[0] - outs[1]).abs().max() / want.abs().max()) < 2e-6
+
+
 def test_default_arguments_and_other_fft_sizes(pkg, built_lib):
     """extract_logmel_spectrogram called with the reference's OWN defaults (win 1024 / hop 256 / n_fft 1024, f_min 0;
     examples/speech_synthesis/data_utils.py:46-52) and TTSSpectrogram / TTSMelScale at n_fft 512 / 4096: the generic
