@@ -152,6 +152,28 @@ __global__ void __launch_bounds__(256, 2) k_stft(const __grid_constant__ StftPar
     }
 }
 
+// log of a positive normal float as MUFU.LG2 + one multiply (2 instructions instead of the ~13 of logf): absolute error
+// <= 2^-21.4 near 1, <= 3 ulp of the result elsewhere -- a few 1e-7 relative on features of magnitude 1 .. 16, inside the
+// 1e-5 feature tolerance with a wide margin.  The register-resident extraction kernels spend a third of their
+// instructions after the FFT; log and CMVN were 20 of the ~42 instructions per feature there.
+__device__ __forceinline__ float fast_log(float x) { return __logf(x); }
+
+// Fused global CMVN (feature_transforms/global_cmvn.py:26-29) inside the extraction kernels: (x - mean) / std evaluated
+// as fma(x, 1 / std, -mean / std) with the two constants per feature prepared once per block (identity when no
+// statistics are given).  Differs from the IEEE subtract-divide of the stand-alone kernel (which is bit-exact with
+// numpy) by at most ~1.5 ulp; the stand-alone s2st_cmvn_apply stays bit-exact.
+__device__ __forceinline__ void load_cmvn_table(float2* s_cm, const float* __restrict__ mean, const float* __restrict__ std, int n) {
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        float2 c = make_float2(1.0f, 0.0f);
+        if (mean) {
+            const float r = 1.0f / __ldg(std + m);
+            c = make_float2(r, -__ldg(mean + m) * r);
+        }
+        s_cm[m] = c;
+    }
+    __syncthreads();
+}
+
 // Fused global-CMVN statistics (get_global_cmvn, examples/speech_synthesis/data_utils.py:190-220, without re-reading
 // the corpus): a lane keeps float partial sums of the features it writes over one chunk of frames (8 or 16), folds them
 // into a per-block double accumulator in shared memory at the end of the chunk, and the block adds that to
@@ -227,6 +249,8 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
     const long long n_chunks = (p.total_frames + kLmChunk - 1) / kLmChunk;
     FeatureSums<SUMS ? 4 : 1> fs;  // mel bins lane, lane + 32, ... (n_mels <= 128)
     __shared__ double s_sums[SUMS ? 2 * kMaxStatCols : 1];
+    __shared__ float2 s_cm[kMaxStatCols];  // fused CMVN as one FMA per feature: (1 / std, -mean / std)
+    load_cmvn_table(s_cm, p.cmvn_mean, p.cmvn_std, p.n_mels);
     if constexpr (SUMS) fs.init(s_sums);
     for (long long chunk = (long long)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (long long)gridDim.x * 8) {
         long long f = chunk * kLmChunk;
@@ -303,21 +327,38 @@ __global__ void __launch_bounds__(256, 2) k_logmel_fast(const __grid_constant__ 
                 // padding float after bin 351 moves the upper half-warp by one bank: conflict-free reads
                 const float* sp = scratch + kPrunedRows * lane + (lane >> 4);
                 float2* my = reinterpret_cast<float2*>(slab) + lane;  // slab[slot][lane]: the table holds slot * 32
+                // two batches of 11 steps: all loads of a batch are issued before its first store -- written as one
+                // load / FMA / store loop the compiler must keep every load behind the previous step's slab store (same
+                // address space, possible alias) and each step waits a full shared-memory round trip: 22 exposed
+                // latencies per frame instead of 2
 #pragma unroll
-                for (int j = 0; j < kPrunedRows; ++j) {
-                    const float4 c = s_col[j * 32 + lane];
-                    lh = fma2(make_float2(c.x, c.y), bcast2(sp[j]), mul2(lh, bcast2(c.z)));
-                    my[__float_as_int(c.w)] = lh;
+                for (int h = 0; h < 2; ++h) {
+                    constexpr int kB = kPrunedRows / 2;
+                    float4 c[kB];
+                    float pv[kB];
+                    float2 run[kB];
+#pragma unroll
+                    for (int j = 0; j < kB; ++j) {
+                        c[j] = s_col[(h * kB + j) * 32 + lane];
+                        pv[j] = sp[h * kB + j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < kB; ++j) {
+                        lh = fma2(make_float2(c[j].x, c[j].y), bcast2(pv[j]), mul2(lh, bcast2(c[j].z)));
+                        run[j] = lh;
+                    }
+#pragma unroll
+                    for (int j = 0; j < kB; ++j) my[__float_as_int(c[j].w)] = run[j];
                 }
                 if (lane == 0) slab[2 * 32 * kLmSlots] = 0.0f;  // (the transposes use the whole scratch)
             }
             __syncwarp();
             for (int m = lane, i = 0; m < p.n_mels; m += 32, ++i) {
                 const float acc = gather_sum(slab, reinterpret_cast<const int4*>(s_gather), m, p.n_mels, p.mel_terms);
-                float v = logf(fmaxf(acc, p.eps));
+                float v = fast_log(fmaxf(acc, p.eps));
                 if constexpr (SUMS) fs.add(i, v);
-                if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + m)) / __ldg(p.cmvn_std + m);
-                p.logmel_out[f * p.n_mels + m] = v;
+                const float2 cm = s_cm[m];
+                p.logmel_out[f * p.n_mels + m] = fmaf(v, cm.x, cm.y);
             }
             __syncwarp();
         }
@@ -665,6 +706,8 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
     const long long n_chunks = (p.total_frames + kFbChunk - 1) / kFbChunk;
     FeatureSums<SUMS ? 8 : 1> fs;  // mel bins sub, sub + 16, ... (n_bins <= 128)
     __shared__ double s_sums[SUMS ? 2 * kMaxStatCols : 1];
+    __shared__ float2 s_cm[kMaxStatCols];  // fused CMVN as one FMA per feature: (1 / std, -mean / std)
+    load_cmvn_table(s_cm, p.cmvn_mean, p.cmvn_std, p.n_bins);
     if constexpr (SUMS) fs.init(s_sums);
     for (long long cp = (long long)blockIdx.x * kFbWarps + warp; 2 * cp < n_chunks; cp += (long long)gridDim.x * kFbWarps) {
         long long f = (2 * cp + grp) * kFbChunk;
@@ -823,11 +866,25 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
                 // behind the power spectrum.
                 float2 lh = make_float2(0.0f, 0.0f);  // (lo, hi) as one packed pair: 2 instructions per step
                 float2* slab2 = reinterpret_cast<float2*>(pwr + kFbPwrFloats);
-#pragma unroll 4
-                for (int j = 0; j < 16; ++j) {
-                    const float4 c = s_col[j * 16 + sub];
-                    lh = fma2(make_float2(c.x, c.y), bcast2(pwr[j * 17 + sub]), mul2(lh, bcast2(c.z)));  // bin 16 sub + j
-                    slab2[__float_as_int(c.w)] = lh;
+                // two batches of 8 steps, loads first: a load / FMA / store loop serialises on the slab stores (possible
+                // alias with the next step's loads), i.e. one exposed shared-memory round trip per step
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float4 c[8];
+                    float pv[8];
+                    float2 run[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        c[j] = s_col[(8 * h + j) * 16 + sub];
+                        pv[j] = pwr[(8 * h + j) * 17 + sub];  // bin 16 sub + 8 h + j
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        lh = fma2(make_float2(c[j].x, c[j].y), bcast2(pv[j]), mul2(lh, bcast2(c[j].z)));
+                        run[j] = lh;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) slab2[__float_as_int(c[j].w)] = run[j];
                 }
                 if (sub == 0) pwr[kFbPwrFloats + p.mel_zero] = 0.0f;  // the float unused gather entries point at
             } else {
@@ -862,17 +919,15 @@ __global__ void __launch_bounds__(32 * kFbWarps, MODE == 0 ? kFbBlocks0 : 3) k_f
                     } else {
                         e0 = macc[m];
                     }
-                    float v0 = logf(fmaxf(e0, 1.1920928955078125e-07f));
-                    float v1 = MODE == 1 ? logf(fmaxf(macc[p.n_bins + 1 + m], 1.1920928955078125e-07f)) : 0.0f;
+                    float v0 = fast_log(fmaxf(e0, 1.1920928955078125e-07f));
+                    float v1 = MODE == 1 ? fast_log(fmaxf(macc[p.n_bins + 1 + m], 1.1920928955078125e-07f)) : 0.0f;
                     if constexpr (SUMS) {
                         if (valid[0]) fs.add(i, v0);
                         if (MODE == 1 && valid[MODE]) fs.add(i, v1);
                     }
-                    if (p.cmvn_mean) {
-                        const float mu = __ldg(p.cmvn_mean + m), sd = __ldg(p.cmvn_std + m);
-                        v0 = (v0 - mu) / sd;
-                        v1 = (v1 - mu) / sd;
-                    }
+                    const float2 cm = s_cm[m];
+                    v0 = fmaf(v0, cm.x, cm.y);
+                    v1 = fmaf(v1, cm.x, cm.y);
                     const long long f0 = f - (MODE + 1);
                     if (valid[0]) p.out[f0 * p.n_bins + m] = v0;
                     if (MODE == 1 && valid[MODE]) p.out[(f0 + 1) * p.n_bins + m] = v1;

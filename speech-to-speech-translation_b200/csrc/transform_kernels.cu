@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256) k_wave_to_pcm16(long long n, const float*
     const long long n8 = n >> 3;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     auto cvt = [](float v) -> unsigned {
-        const float s = fminf(fmaxf(v * 32767.0f, -32768.0f), 32767.0f);
-        return (unsigned)(unsigned short)(short)__float2int_rn(s);  // NaN -> 0
+        const float s = v == v ? fminf(fmaxf(v * 32767.0f, -32768.0f), 32767.0f) : 0.0f;  // NaN -> 0
+        return (unsigned)(unsigned short)(short)__float2int_rn(s);
     };
     if (vec) {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
