@@ -229,20 +229,23 @@ def synth_audio_np(n, sr, seed):
     return np.clip(x, -1, 1).astype(np.float32)
 
 
-def frontend_cpu_time(durations_s, sr, threads):
+def frontend_cpu_time(durations_s, sr, threads, min_seconds=10.0):
     """The reference's own fbank80 + global CMVN path on the host cores: torchaudio.compliance.kaldi.fbank
-    (audio_utils.py:141-147) then (x - mean) / std in numpy (global_cmvn.py:26-29), one utterance per call."""
+    (audio_utils.py:141-147) then (x - mean) / std in numpy (global_cmvn.py:26-29), one utterance per call.  The
+    utterances of the sample are processed again and again until ``min_seconds`` of CPU work have been timed."""
     import torch
     import torchaudio.compliance.kaldi as ta_kaldi
     torch.set_num_threads(threads)
     rng = np.random.RandomState(7)
     mean, std = (rng.randn(80) - 4).astype(np.float32), rng.uniform(0.5, 2, 80).astype(np.float32)
     waves = [torch.from_numpy(synth_audio_np(int(d * sr), sr, 300 + i) * (2 ** 15))[None] for i, d in enumerate(durations_s)]
-    t0 = time.perf_counter()
-    for w in waves:
-        f = ta_kaldi.fbank(w, num_mel_bins=80, sample_frequency=sr).numpy()
-        np.divide(np.subtract(f, mean), std)
-    return float(sum(durations_s)), time.perf_counter() - t0
+    audio, t0 = 0.0, time.perf_counter()
+    while time.perf_counter() - t0 < min_seconds:
+        for w, d in zip(waves, durations_s):
+            f = ta_kaldi.fbank(w, num_mel_bins=80, sample_frequency=sr).numpy()
+            np.divide(np.subtract(f, mean), std)
+            audio += float(d)
+    return audio, time.perf_counter() - t0
 
 
 def run_reference_arm(args):
@@ -265,7 +268,7 @@ def run_reference_arm(args):
         durs = list(np.random.RandomState(0).uniform(8, 20, 10000)[:24])
         times, audio = [], 0.0
         for step in range(args.warmup + args.steps):
-            audio, dt = frontend_cpu_time(durs, 16000, cores)
+            audio, dt = frontend_cpu_time(durs, 16000, cores, min_seconds=5.0)
             if step >= args.warmup:
                 times.append(dt)
         ms = 1e3 * float(np.mean(times))
@@ -276,8 +279,8 @@ def run_reference_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_FRONTEND, "sample_rate": 16000, "n_bins": 80},
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "reference",
-                             "sample": f"the first {len(durs)} utterances of the list ({audio:.0f} audio-s), torchaudio "
-                                       "compliance.kaldi.fbank + numpy global CMVN, one utterance per call"},
+                             "sample": f"the first {len(durs)} utterances of the list, repeated ({audio:.0f} audio-s per step), "
+                                       "torchaudio compliance.kaldi.fbank + numpy global CMVN, one utterance per call"},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -592,6 +595,33 @@ def gl_extras(ctx, voc):
         c5[f"{n_iter}_iters"] = {"ms": ms, "audio_s_per_s": audio / (ms * 1e-3),
                                  "hbm_frac": (ALGO_BYTES_PER_FRAME_ITER * n_iter + ALGO_BYTES_PER_FRAME_ONCE) * T / (ms * 1e-3) / 1e9 / peaks()[0]}
     out["config5"] = c5
+    # the two dense contractions of the path on the tensor cores (north_star job 4): device time of the stand-alone
+    # entries on the config-2 batch, algorithmic FLOPs (2 * n_mels * n_bins per frame) against the measured bf16 peak;
+    # the 3 x TF32 split executes three times those FLOPs at the TF32 rate (half the bf16 rate)
+    frames, logmel_np, _ = config2_batch(0)
+    total = int(sum(frames))
+    lm = torch.from_numpy(logmel_np).to(dev)
+    lib, ptr, sptr = ctx.pkg._lib.load(), ctx.pkg._lib.ptr, ctx.pkg._lib.stream_ptr
+    plan = voc._plan(dev)
+    mag = torch.empty(total, N_BINS, device=dev)
+    ms_inv = timeit(lambda: ctx.pkg._lib.check(lib.s2st_inverse_mel(plan.handle, total, ptr(lm), 1, ptr(mag), sptr(dev)), "s2st_inverse_mel"), 20)
+    plans = importlib.import_module(PKG + ".plans")
+    mplan = plans.get_stft_plan(dev, N_FFT, N_FFT, N_FFT // 4, N_MELS, torch.ones(N_FFT),
+                                mel=ctx.pkg.get_mel_filters(SR, N_FFT, N_MELS, F_MIN, F_MAX))
+    mel_out = torch.empty(total, N_MELS, device=dev)
+    ms_mel = timeit(lambda: ctx.pkg._lib.check(lib.s2st_mel_project(mplan.handle, total, ptr(mag), ptr(mel_out), sptr(dev)), "s2st_mel_project"), 20)
+    tpeak, tsrc = tensor_peak()
+    flops = 2.0 * N_MELS * N_BINS * total
+    out["tensor"] = {
+        "peak_tflops": tpeak, "peak_source": tsrc, "frames": total,
+        "note": "3 x TF32 split: executed tensor FLOPs = 3 x algorithmic, at the TF32 rate (half the bf16 peak); both kernels "
+                "are bound by their HBM traffic, not by the tensor pipe (ncu sm__pipe_tensor_cycles_active in profiles/)",
+        "inverse_mel": {"kernel": "k_inverse_mel_tc (tcgen05 kind::tf32, exp + pinv[1025x80] + clamp)", "ms": ms_inv,
+                        "algorithmic_tflops": flops / (ms_inv * 1e-3) / 1e12, "frac_of_peak": flops / (ms_inv * 1e-3) / 1e12 / tpeak,
+                        "hbm_frac": total * (320 + 4 * N_BINS) / (ms_inv * 1e-3) / 1e9 / peaks()[0]},
+        "mel_project": {"kernel": "k_mel_project_tc (tcgen05 kind::tf32, mel[80x1025])", "ms": ms_mel,
+                        "algorithmic_tflops": flops / (ms_mel * 1e-3) / 1e12, "frac_of_peak": flops / (ms_mel * 1e-3) / 1e12 / tpeak,
+                        "hbm_frac": total * (320 + 4 * N_BINS) / (ms_mel * 1e-3) / 1e9 / peaks()[0]}}
     return out
 
 
@@ -852,8 +882,9 @@ def run_frontend(args, ctx):
                      "launch_ms": ms16},
         "cpu_baseline": None if world > 1 else {
             "value": cpu_audio / cpu_s, "unit": "audio-s/s", "cores": cores, "kind": "reference",
-            "sample": f"the first {len(durs)} utterances ({cpu_audio:.0f} audio-s): torchaudio compliance.kaldi.fbank + numpy "
-                      f"CMVN (the reference's own code path, audio_utils.py:141-147, global_cmvn.py:26-29), {cpu_s:.1f} s"},
+            "sample": f"the first {len(durs)} utterances of the list, repeated for {cpu_s:.1f} s ({cpu_audio:.0f} audio-s): "
+                      "torchaudio compliance.kaldi.fbank + numpy CMVN (the reference's own code path, audio_utils.py:141-147, "
+                      "global_cmvn.py:26-29)"},
         "clocks": clocks,
         "fbank80_cmvn_16k": res16,
     }
