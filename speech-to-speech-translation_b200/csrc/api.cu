@@ -86,12 +86,6 @@ void free_plan_members(s2st_plan* p) {
     cudaFree(p->inv_wss);
     cudaFree(p->tw);
     cudaFree(p->vtab);
-    cudaFree(p->tw64);
-    cudaFree(p->mag_perm);
-    cudaFree(p->inv_mel_t_perm);
-    cudaFree(p->inv_mel_tc_perm);
-    cudaFree(p->win_pair);
-    cudaFree(p->vp64);
     cudaFree(p->inv_mel_t);
     cudaFree(p->inv_mel_tc);
     cudaFree(p->mel_tc);
@@ -160,8 +154,6 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == 'a') ? -1 : 0;
         e = getenv("S2ST_GL_PDL");
         p->opt_pdl = !(e && e[0] == '0');
-        e = getenv("S2ST_GL_KERNEL");
-        p->opt_gl_kernel = (e && e[0] == 'r') ? 1 : 0;
         e = getenv("S2ST_INVERSE_MEL");
         p->opt_inverse_mel_simt = (e && e[0] == 's') ? 1 : 0;
         p->opt_frontend_generic = getenv("S2ST_LOGMEL_GENERIC") ? 1 : 0;
@@ -273,27 +265,6 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
     if (rc == S2ST_OK) rc = upload(&p->inv_wss, inv_wss);
     if (rc == S2ST_OK) rc = upload(&p->tw, tw);
     if (rc == S2ST_OK) rc = upload(&p->vtab, vtab);
-    if (rc == S2ST_OK && p->nz == 19) {
-        // tables of the real-FFT-64 formulation (frame_r64.cuh)
-        std::vector<float2> tw64(1024), win_pair(32 * 19);
-        for (int m = 0; m < 32; ++m)
-            for (int l = 0; l < 32; ++l) {
-                // W2048^(l m) * W32^(-11 l): the second factor moves output q of lane m's FFT-32 to slot q + 11 (mod 32)
-                const double a = -2.0 * pi * (double)((m * l - 11 * 64 * l) % 2048) / 2048.0;
-                tw64[m * 32 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
-            }
-        for (int r = 0; r < 19; ++r)
-            for (int l = 0; l < 32; ++l) win_pair[r * 32 + l] = make_float2(win_a[l + 64 * r], win_a[l + 32 + 64 * r]);
-        std::vector<float2> vp64(32);
-        for (int l = 0; l < 32; ++l) {
-            const double a = 2.0 * pi * (double)l / 64.0;  // -i exp(-i a) = (-sin a, -cos a)
-            vp64[l] = make_float2((float)(-std::sin(a)), (float)(-std::cos(a)));
-        }
-        rc = upload(&p->tw64, tw64);
-        if (rc == S2ST_OK) rc = upload(&p->win_pair, win_pair);
-        if (rc == S2ST_OK) rc = upload(&p->vp64, vp64);
-    }
-
     p->kb = kBins;
     if (rc == S2ST_OK && inv_mel_host) {
         int last = 0;
@@ -310,27 +281,6 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
             std::vector<float> tc(inverse_mel_tc_floats(n_mels));
             build_inverse_mel_tc(inv_mel_host, p->kb, n_mels, tc.data());
             rc = upload(&p->inv_mel_tc, tc);
-        }
-        if (rc == S2ST_OK && p->tw64 && p->kb <= 704) {
-            // the same basis with its rows in the slot order of the real-FFT-64 kernel (frame_r64.cuh): the projection
-            // then writes the magnitudes where that kernel's lanes read them, [frame][slot][lane]
-            std::vector<int> perm(704);
-            std::vector<float> pm((size_t)704 * n_mels, 0.0f), t((size_t)n_mels * 704, 0.0f);
-            for (int pos = 0; pos < 704; ++pos) {
-                const int slot = pos / 32, lane = pos % 32;
-                const int bin = lane == 0 ? 32 * slot : slot <= 10 ? 64 * (11 - slot) - lane : 64 * (slot - 11) + lane;
-                perm[bin] = pos;
-                if (bin < p->kb)
-                    for (int m = 0; m < n_mels; ++m)
-                        pm[(size_t)pos * n_mels + m] = t[(size_t)m * 704 + pos] = inv_mel_host[(size_t)bin * n_mels + m];
-            }
-            rc = upload(&p->mag_perm, perm);
-            if (rc == S2ST_OK) rc = upload(&p->inv_mel_t_perm, t);
-            if (rc == S2ST_OK && p->inv_mel_tc) {
-                std::vector<float> tc(inverse_mel_tc_floats(n_mels));
-                build_inverse_mel_tc(pm.data(), 704, n_mels, tc.data());
-                rc = upload(&p->inv_mel_tc_perm, tc);
-            }
         }
     }
     if (rc == S2ST_OK && mel_host) {
@@ -458,10 +408,6 @@ int s2st_plan_set_option(s2st_plan* plan, int option, int value) {
             return S2ST_OK;
         case S2ST_OPT_GL_PDL:
             plan->opt_pdl = value != 0;
-            return S2ST_OK;
-        case S2ST_OPT_GL_KERNEL:
-            if (value < 0 || value > 1) break;
-            plan->opt_gl_kernel = value;
             return S2ST_OK;
         case S2ST_OPT_INVERSE_MEL:
             if (value < 0 || value > 1) break;

@@ -48,16 +48,12 @@ struct GlParams {
     float inv_nfft;          // 1 / n_fft (a power of two: the scaling is exact wherever it is applied)
     const float2* tw;        // [32*32] exp(-2 pi i r l / 1024)
     const float2* vtab;      // [1024]  -i exp(-2 pi i k / 2048)
-    const float2* tw64;      // [32*32] exp(-2 pi i m l / 2048)                       (k_gl_pass_r64)
-    const float2* vp64;      // [32]   -i exp(-2 pi i p / 64): split factors of the multiples-of-32 column (frame_r64.cuh)
-    const float2* win_pair;  // [19*32] (w[l + 64 r], w[l + 32 + 64 r]) at [r*32 + l]  (k_gl_pass_r64; NULL if n/a)
     // batch tables (workspace)
     const UttDesc* utts;
     const TileDesc* tiles;
     const int* n_tiles;
     // data
     const float* mag;        // [total_frames, mag_stride]
-    const int* mag_perm;     // NULL: rows in bin order; else position of bin k (< 704) in a row (slot order of frame_r64.cuh)
     const float* phase;      // [total_frames, phase_stride] (first pass only); NULL -> device RNG
     unsigned long long phase_seed;
     const float* in;         // normalised waveforms written by the previous pass

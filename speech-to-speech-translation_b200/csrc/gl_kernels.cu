@@ -22,7 +22,7 @@
 #include <math_constants.h>
 
 #include "../../include/s2st_b200.h"
-#include "frame_r64.cuh"
+#include "frame_fft.cuh"
 #include "plan.h"
 
 namespace s2st {
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                             for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
                                 const int k = 32 * r + lane;
                                 if (k < kb) {
-                                    const float m = __ldg(magrow + (p.mag_perm ? __ldg(p.mag_perm + k) : k));
+                                    const float m = __ldg(magrow + k);
                                     // the caller's phase refers to the un-rotated frame; frames are processed
                                     // rotated by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048).  The
                                     // rotation angle (an exact multiple of pi / 1024, reduced to [-pi, pi)) is added
@@ -443,209 +443,6 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
             if (lane == 0) st_release(p.done + strip, it);
         }
       }
-    }
-}
-
-// ---- the iteration kernel for the vocoder's standard geometry, real-FFT-64 formulation (frame_r64.cuh) --------
-// Same strip / ring / seam machinery as k_gl_pass<19, false, true, true>; the transform keeps the real-signal
-// symmetry in-lane, so a frame-iteration moves 284 fewer shared-memory wavefronts (no pair exchanges, no split
-// factor table).  Lane l owns samples l + 32 j of the rotated frame (4-byte coalesced loads / ring updates).
-__device__ __noinline__ void load_frame_edge_r64(float* __restrict__ scratch, const float* __restrict__ y, int jf,
-                                                 int L, int lane) {
-    // reflect padding (audio_utils.py:262-263): stage the 1216 samples of the frame in the warp's scratch
-    for (int i = lane; i < 64 * 19; i += 32) {
-        int j = jf + i;
-        j = j < 0 ? -j : j;
-        j = j >= L ? 2 * (L - 1) - j : j;
-        j = min(max(j, 0), L - 1);  // only reachable where the window is zero
-        scratch[i] = y[j];
-    }
-    __syncwarp();
-}
-
-__global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass_r64(const __grid_constant__ GlParams p) {
-    constexpr int NZ = 19, hop = kStdHop, ws = kStdWs, rot_half = kStdRot - kNfft / 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* s_tw = reinterpret_cast<float2*>(smem_raw);            // 1024: exp(-2 pi i m l / 2048) at [m * 32 + l]
-    float2* s_win = s_tw + 1024;                                   // 32 * NZ: (w[l + 64 r], w[l + 32 + 64 r]) at [r * 32 + l]
-    float2* s_vp = s_win + 32 * NZ;                                // 32
-    float* s_inv_wss = reinterpret_cast<float*>(s_vp + 32);        // hop
-    float* s_warp = s_inv_wss + hop;                               // per warp: scratch + ring + column buffer
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* scratch = s_warp + warp * (kR64ScratchFloats + ws);
-    float* ring = scratch + kR64ScratchFloats;
-    const R64Ctx ctx{s_tw, s_vp, scratch};
-    for (int i = tid; i < 32; i += kGlThreads) s_vp[i] = p.vp64[i];
-    for (int i = tid; i < 1024; i += kGlThreads) s_tw[i] = p.tw64[i];
-    for (int i = tid; i < 32 * NZ; i += kGlThreads) s_win[i] = p.win_pair[i];
-    for (int i = tid; i < hop; i += kGlThreads) s_inv_wss[i] = p.inv_wss[i];
-    for (int i = lane; i < ws; i += 32) ring[i] = 0.0f;
-    __syncthreads();  // the only block-wide barrier: constant tables are in place
-
-    const int n_strips = *p.n_tiles;
-    for (int strip = blockIdx.x + gridDim.x * warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
-        const TileDesc td = p.tiles[strip];
-        const int T = td.n_frames, L = (T - 1) * hop;
-        const int j_base = td.f0 * hop + rot_half;  // output sample index of strip-relative sample 0
-        float* out = p.out + td.wave_off;
-        float* znext = p.zero_next + td.wave_off;
-        const float* y = p.in + td.wave_off;
-        const float* magrow = p.mag + ((size_t)td.frame_off + td.f0) * p.mag_stride;
-
-        float2 a[32];
-        int slot0 = 0;  // ring slot of strip-relative sample f * hop
-#pragma unroll 1
-        for (int f = -1; f < td.nf; ++f) {
-            if (f >= 0) {
-                float mg[kR64Live];
-                {
-                    const float2* w = s_win + lane;
-#pragma unroll
-                    for (int r = 0; r < NZ; ++r) a[brev5(r)] = mul2(a[brev5(r)], w[32 * r]);
-                }
-                // target magnitudes (22 lines per frame, slot order): lane p < 22 fetches bin 32 p, the one it re-imposes
-                // in r64_column_mid -- this touches all 22 lines, so the row loads after the forward transform (into
-                // the registers that slots 22..31 free up) find them on their way or in cache
-                const float mcol = lane < kR64Live ? __ldg(magrow + 32 * lane) : 0.0f;
-                r64_analysis(a, ctx, lane);
-                r64_column_mid(a, ctx.scratch, ctx.vp, mcol, lane);
-                {
-                    const float* m0 = magrow + lane;
-#pragma unroll
-                    for (int rho = 0; rho < kR64Live; ++rho) mg[rho] = __ldcs(m0 + 32 * rho);
-                }
-                {
-                    // magnitude re-imposition (see k_gl_pass): scale factors first, degenerate spectra only flagged
-                    bool degenerate = false;
-#pragma unroll
-                    for (int rho = 0; rho < kR64Live; ++rho) {
-                        const float2 v = a[rho];
-                        const float r2 = fmaf(v.x, v.x, v.y * v.y);
-                        float rs;
-                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
-                        mg[rho] *= rs;
-                        degenerate |= !(r2 >= 1.1754944e-38f);
-                    }
-                    if (lane == 0) degenerate = false;  // lane 0's slots are replaced by r64_column_reload
-
-                    if (__builtin_expect(__any_sync(0xffffffffu, degenerate), 0)) {
-#pragma unroll 1
-                        for (int rho = 0; rho < kR64Live; ++rho) {
-                            const float m = __ldg(magrow + lane + 32 * rho);
-                            float2 v = make_float2(0.0f, 0.0f);
-                            float sc = 0.0f;
-#pragma unroll
-                            for (int q = 0; q < kR64Live; ++q)
-                                if (q == rho) {
-                                    v = a[q];
-                                    sc = mg[q];
-                                }
-                            const float r2 = fmaf(v.x, v.x, v.y * v.y);
-                            v = r2 >= 1.1754944e-38f ? mul2(v, bcast2(sc)) : make_float2(copysignf(m, v.x), 0.0f);
-#pragma unroll
-                            for (int q = 0; q < kR64Live; ++q)
-                                if (q == rho) a[q] = v;
-                        }
-                    } else {
-#pragma unroll
-                        for (int rho = 0; rho < kR64Live; ++rho) a[rho] = mul2(a[rho], bcast2(mg[rho]));
-                    }
-                }
-                magrow += p.mag_stride;
-                r64_synthesis(a, ctx, lane);
-                {
-                    // window and overlap-add into the private ring.  Samples past the window support have zero
-                    // weight: they wrap onto a live slot and add +0, so every row accumulates without a bounds test
-                    const float2* w = s_win + lane;
-                    const int first = slot0 + lane;
-#pragma unroll
-                    for (int r = 0; r < NZ; ++r) {
-                        const float2 ww = w[32 * r];
-                        int i0 = first + 64 * r, i1 = first + 64 * r + 32;
-                        i0 -= i0 >= ws ? ws : 0;
-                        i1 -= i1 >= ws ? ws : 0;
-                        ring[i0] = fmaf(a[r].x, ww.x, ring[i0]);
-                        ring[i1] = fmaf(a[r].y, ww.y, ring[i1]);
-                    }
-                }
-            }
-            // fetch the next frame (the loads fly while the finished hop is written out)
-            if (f + 1 < td.nf) {
-                const int jf = j_base + (f + 1) * hop;  // first sample of the frame
-                if (jf >= 0 && jf + 64 * NZ <= L) {
-                    const float* src = y + jf + lane;
-#pragma unroll
-                    for (int r = 0; r < NZ; ++r) a[brev5(r)] = make_float2(src[64 * r], src[64 * r + 32]);
-                    // the hop the frame after that adds is not in cache yet: ask L2 for it now (11 lines)
-                    const int jp = jf + 64 * NZ - 16 + 32 * lane;
-                    if (lane < 11 && jp < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + jp));
-                } else {
-                    __syncwarp();
-                    load_frame_edge_r64(scratch, y, jf, L, lane);
-                    const float* src = scratch + lane;
-#pragma unroll
-                    for (int r = 0; r < NZ; ++r) a[brev5(r)] = make_float2(src[64 * r], src[64 * r + 32]);
-                    __syncwarp();
-                }
-            }
-            if (f >= 0) {
-                __syncwarp();
-                // hop f of the strip is final: normalise, store, clear its ring slots
-                const int i0 = f * hop;
-                const int j0 = j_base + i0;
-                if (i0 >= ws - hop && j0 >= 0 && j0 + hop <= L) {
-                    // steady state: no seam, no edge -> 16-byte wide, straight stores
-                    float4* dst = reinterpret_cast<float4*>(out + j0);
-                    float4* rg = reinterpret_cast<float4*>(ring + slot0);
-                    const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
-                    for (int q = lane; q < (hop >> 2); q += 32) {
-                        const float4 v = rg[q], wv = iw[q];
-                        rg[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        const float2 lo = mul2(make_float2(v.x, v.y), make_float2(wv.x, wv.y));
-                        const float2 hi = mul2(make_float2(v.z, v.w), make_float2(wv.z, wv.w));
-                        dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                    }
-                } else if (td.f0 > 0 && i0 < ws - hop && j0 + hop <= L && i0 + hop <= (T - td.f0) * hop) {
-                    // left seam of an interior strip, steady-state window sum: two contributions onto a zeroed
-                    // location commute -> deterministic
-                    float4* dst = reinterpret_cast<float4*>(out + j0);
-                    float4* rg = reinterpret_cast<float4*>(ring + slot0);
-                    const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
-                    for (int q = lane; q < (hop >> 2); q += 32) {
-                        const float4 v = rg[q], wv = iw[q];
-                        rg[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        atomicAdd(dst + q, make_float4(v.x * wv.x, v.y * wv.y, v.z * wv.z, v.w * wv.w));
-                    }
-                } else {
-                    emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, i0, hop, slot0, lane);
-                }
-                slot0 += hop;
-                if (slot0 >= ws) slot0 -= ws;
-                __syncwarp();
-            }
-        }
-        // the tail of the last frame: [nf*hop, (nf-1)*hop + ws)
-        if (T - td.f0 - td.nf >= 3) {
-            const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
-#pragma unroll 1
-            for (int h = 0; h < (kStdWs - kStdHop) / kStdHop; ++h) {
-                const int j0 = j_base + (td.nf + h) * hop;
-                float4* dst = reinterpret_cast<float4*>(out + j0);
-                float4* zn = reinterpret_cast<float4*>(znext + j0);
-                float4* rg = reinterpret_cast<float4*>(ring + slot0);
-                for (int q = lane; q < (hop >> 2); q += 32) {
-                    const float4 v = rg[q], wv = iw[q];
-                    rg[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    atomicAdd(dst + q, make_float4(v.x * wv.x, v.y * wv.y, v.z * wv.z, v.w * wv.w));
-                    zn[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                }
-                slot0 += hop;
-                if (slot0 >= ws) slot0 -= ws;
-            }
-        } else {
-            emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
-        }
-        __syncwarp();
     }
 }
 
@@ -889,14 +686,6 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
     return w;
 }
 
-size_t gl_pass_r64_smem() {
-    return sizeof(float2) * (1024 + 32 * 19 + 32) + sizeof(float) * (kStdHop + kGlWarps * (kR64ScratchFloats + kStdWs));
-}
-
-// S2ST_OPT_GL_KERNEL = 1 selects the real-FFT-64 formulation (frame_r64.cuh) for the vocoder's standard case.  It is
-// parity-tested but NOT the default: it moves 32 % fewer shared-memory wavefronts per frame-iteration, yet the column
-// of bins that are multiples of 32 costs ~190 extra instructions, so it ends up level with the packed-complex kernel
-// (0.238 vs 0.236 ms per pass on the config-2 batch) and its first pass is slower.
 size_t gl_pass_smem(const s2st_plan* plan) {
     return sizeof(float2) * 2048 +
            sizeof(float) * (plan->wp + ((plan->hop + 3) & ~3) + kGlWarps * (kScratchFloats + ((plan->ws + 3) & ~3)));
@@ -982,8 +771,8 @@ size_t gl_workspace_bytes(const s2st_plan* plan, int n_utts, long long total_fra
 }
 
 int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* logmel, bool is_log, float* mag,
-                       int out_stride, int n_out, cudaStream_t stream, bool slot_order) {
-    if (!plan->inv_mel_t || (slot_order && !plan->inv_mel_t_perm)) {
+                       int out_stride, int n_out, cudaStream_t stream) {
+    if (!plan->inv_mel_t) {
         set_error("plan was created without an inverse-mel basis");
         return S2ST_EINVAL;
     }
@@ -991,17 +780,11 @@ int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* l
     // dense contraction -> tensor cores (tcgen05, 3xTF32) whenever the shape allows; S2ST_OPT_INVERSE_MEL = 1
     // selects the FP32 SIMT kernel (kept for other shapes and for A/B checks)
     const bool force_simt = plan->opt_inverse_mel_simt != 0;
-    if (!force_simt && inverse_mel_tc_supported(plan) && ((uintptr_t)logmel & 15) == 0 &&
-        (!slot_order || plan->inv_mel_tc_perm))
-        return launch_inverse_mel_tc(plan, n_frames, logmel, is_log, mag, out_stride, n_out, stream,
-                                     slot_order ? plan->inv_mel_tc_perm : nullptr);
+    if (!force_simt && inverse_mel_tc_supported(plan) && ((uintptr_t)logmel & 15) == 0)
+        return launch_inverse_mel_tc(plan, n_frames, logmel, is_log, mag, out_stride, n_out, stream);
     const long long blocks = (n_frames + kImFrames - 1) / kImFrames;
-    if (slot_order)
-        k_inverse_mel<<<(unsigned)blocks, 256, sizeof(float) * kImFrames * plan->n_mels, stream>>>(
-            logmel, is_log, n_frames, plan->n_mels, plan->inv_mel_t_perm, 704, 704, mag, out_stride, n_out);
-    else
-        k_inverse_mel<<<(unsigned)blocks, 256, sizeof(float) * kImFrames * plan->n_mels, stream>>>(
-            logmel, is_log, n_frames, plan->n_mels, plan->inv_mel_t, plan->kb, plan->kb_pad, mag, out_stride, n_out);
+    k_inverse_mel<<<(unsigned)blocks, 256, sizeof(float) * kImFrames * plan->n_mels, stream>>>(
+        logmel, is_log, n_frames, plan->n_mels, plan->inv_mel_t, plan->kb, plan->kb_pad, mag, out_stride, n_out);
     S2ST_CUDA_CHECK(cudaGetLastError());
     return S2ST_OK;
 }
@@ -1067,28 +850,18 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
     p.inv_wss = plan->inv_wss;
     p.tw = plan->tw;
     p.vtab = plan->vtab;
-    p.tw64 = plan->tw64;
-    p.win_pair = plan->win_pair;
-    p.vp64 = plan->vp64;
     p.utts = w.utts;
     p.tiles = w.tiles;
     p.n_tiles = w.n_tiles;
     p.phase = phase;
     p.phase_seed = phase_seed;
     p.phase_stride = kBins;
-    // the vocoder's own case (log-mel in, standard geometry) runs the real-FFT-64 iteration kernel, which wants the
-    // magnitude rows in its slot order; everything else keeps bin order and the packed-complex kernels
-    const bool r64 = logmel && plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
-                     plan->n_fft == kNfft && plan->kb <= 32 * kPrunedRows && w.mag_stride == 32 * kPrunedRows &&
-                     plan->tw64 && plan->mag_perm && plan->opt_gl_kernel == 1;
-    p.mag_perm = nullptr;
     if (logmel) {
-        int rc = launch_inverse_mel(plan, total_frames, logmel, true, w.mag, w.mag_stride, w.mag_stride, stream, r64);
+        int rc = launch_inverse_mel(plan, total_frames, logmel, true, w.mag, w.mag_stride, w.mag_stride, stream);
         if (rc != S2ST_OK) return rc;
         p.mag = w.mag;
         p.mag_stride = w.mag_stride;
         p.kb = plan->kb;
-        if (r64) p.mag_perm = plan->mag_perm;
     } else {
         p.mag = mag;
         p.mag_stride = kBins;
@@ -1110,7 +883,7 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
     const bool std_geom0 = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                            plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
     const int pmode = plan->opt_persistent;
-    bool persist = std_geom0 && !r64 && n_iter >= 1 && frame_offsets_host && pmode != 0;
+    bool persist = std_geom0 && n_iter >= 1 && frame_offsets_host && pmode != 0;
     plan->last_launches = 1 + (logmel ? 1 : 0) + (n_iter + 1);  // build_tiles, [inverse_mel], the passes
     if (persist) {
         long long strips = 0;
@@ -1161,18 +934,9 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
         // the iteration kernel specialised for the vocoder's standard geometry, else the generic one
         const bool std_geom = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                               plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
-        int rc;
-        if (it > 0 && r64) {
-            const size_t smem64 = gl_pass_r64_smem();
-            if (int rc2 = allow_dynamic_smem<k_gl_pass_r64>(smem64, p.device)) return rc2;
-            k_gl_pass_r64<<<grid, kGlThreads, smem64, stream>>>(p);
-            S2ST_CUDA_CHECK(cudaGetLastError());
-            rc = S2ST_OK;
-        } else {
-            rc = (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
-                 : (plan->nz == 19)   ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
-                                      : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
-        }
+        const int rc = (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
+                       : (plan->nz == 19)   ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
+                                            : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
         if (rc != S2ST_OK) return rc;
     }
     if (timed) {

@@ -24,12 +24,6 @@ struct s2st_plan {
     float* inv_wss;
     float2* tw;
     float2* vtab;
-    float2* tw64;       // real-FFT-64 formulation (frame_r64.cuh): exp(-2 pi i m l / 2048) at [m * 32 + l]
-    float2* vp64;       // r64_column_mid split factors
-    float2* win_pair;   // rotated window as (w[l + 64 r], w[l + 32 + 64 r]) at [r * 32 + l]; NULL unless nz == 19
-    int* mag_perm;          // [704] bin -> position in the slot-ordered magnitude rows of k_gl_pass_r64 (or NULL)
-    float* inv_mel_t_perm;  // inv_mel_t / inv_mel_tc with the basis rows in that order ([n_mels, 704]), or NULL
-    float* inv_mel_tc_perm;
     float* inv_mel_t;   // [n_mels, kb_pad] transposed pseudo-inverse (NULL if absent)
     float* inv_mel_tc;  // the same basis pre-split into TF32 head / tail in UMMA layout (mel_tc.cu), or NULL
     float* mel_tc;      // the mel filterbank pre-split into TF32 head / tail in UMMA layout, per 64-bin K chunk (mel_tc.cu), or NULL
@@ -53,7 +47,6 @@ struct s2st_plan {
     // options (s2st_plan_set_option; initialised ONCE at plan creation from the S2ST_* environment variables)
     int opt_persistent;           // -1 = automatic, 0 = one launch per iteration, 1 = one persistent launch when possible
     int opt_pdl;                  // programmatic dependent launch of the passes (default 1)
-    int opt_gl_kernel;            // 0 = packed-complex iteration kernel (default), 1 = real-FFT-64 formulation
     int opt_inverse_mel_simt;     // 0 = tcgen05 inverse-mel (default), 1 = FP32 SIMT kernel
     int opt_frontend_generic;     // 0 = register-resident log-mel kernel (default), 1 = generic k_stft path
     int last_launches;            // kernel launches of the last gl_run (0 before the first call)
@@ -95,7 +88,7 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
            unsigned long long phase_seed, int n_iter, float* wave_out, void* workspace, size_t workspace_bytes,
            cudaStream_t stream);
 int launch_inverse_mel(const s2st_plan* plan, long long n_frames, const float* logmel, bool is_log, float* mag,
-                       int out_stride, int n_out, cudaStream_t stream, bool slot_order = false);
+                       int out_stride, int n_out, cudaStream_t stream);
 int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* out, bool inverse,
                     cudaStream_t stream);
 int launch_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double* u, float* phase, cudaStream_t stream);

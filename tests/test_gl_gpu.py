@@ -196,40 +196,6 @@ def test_ragged_batch_equals_per_utterance_and_oracle(pkg, voc, basis):
     assert all(torch.equal(a, b) for a, b in zip(outs, again))
 
 
-def test_real_fft64_formulation_matches_golden_oracle_and_default_kernel(pkg, voc, basis, monkeypatch):
-    """S2ST_OPT_GL_KERNEL = 1 runs the iterations with the real-FFT-64 kernel (csrc/frame_r64.cuh: other transform
-    factorisation, magnitudes kept in slot order, multiples-of-32 column split by the whole warp).  Same bar as
-    the default kernel: golden vectors, oracle, ragged batch incl. strip seams and utterance edges, determinism."""
-    g = load_golden("gl_small.npz")
-    frames = [5, 8, 9, 31, 56, 64, 65, 100, 257]
-    feats = [synth_logmel(T, 100 + i, "smooth" if i % 2 else "iid") for i, T in enumerate(frames)]
-    phases = [seeded_phase(200 + i, T) for i, T in enumerate(frames)]
-    base = voc.synthesize_batch([f.cuda() for f in feats], init_phase=phases, n_iter=16)
-    plan = voc._plan(torch.device("cuda", 0))
-    plan.set_option(pkg._lib.OPT_GL_KERNEL, 1)
-    for case in ("c1", "c3"):
-        x, n_iter, seed = g[case + "_logmel"], int(g[case + "_n_iter"]), int(g[case + "_seed"])
-        voc.gl_transform.n_iter = n_iter
-        np.random.seed(seed)
-        y = voc(torch.from_numpy(x).cuda()).cpu().numpy()
-        voc.gl_transform.n_iter = 64
-        assert ogl.rel_l2(y, g[case + "_wave"]) < 1e-3
-        assert abs(ogl.spectral_convergence(y, ogl.inverse_mel(x, basis), **CFG) - float(g[case + "_sc"])) < 1e-4
-    outs = voc.synthesize_batch([f.cuda() for f in feats], init_phase=phases, n_iter=16)
-    again = voc.synthesize_batch([f.cuda() for f in feats], init_phase=phases, n_iter=16)
-    for i, T in enumerate(frames):
-        assert outs[i].numel() == (T - 1) * 300 and torch.equal(outs[i], again[i])
-        assert ogl.rel_l2(outs[i].cpu().numpy(), base[i].cpu().numpy()) < 1e-4
-    for i in (0, 3, 8):
-        ref = ogl.vocoder_forward(feats[i].numpy(), phases[i], 16, basis=basis)
-        assert ogl.rel_l2(outs[i].cpu().numpy(), ref) < 1e-3
-    # an all-silent utterance exercises the exact atan2(0, +-0) semantics in both the lanes and the column
-    silent = torch.full((40, 80), -30.0)
-    z = voc.synthesize_batch([silent.cuda()], init_phase=[seeded_phase(7, 40)], n_iter=4)[0]
-    plan.set_option(pkg._lib.OPT_GL_KERNEL, 0)
-    assert torch.isfinite(z).all()
-
-
 def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
     """Persistent mode: all iterations in one cooperative launch, strips synchronising with their neighbours only
     (no grid-wide barrier).  Same arithmetic, commuting seam reductions -> the waveforms must be bitwise equal to the
