@@ -154,6 +154,8 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == 'a') ? -1 : 0;
         e = getenv("S2ST_GL_PDL");
         p->opt_pdl = !(e && e[0] == '0');
+        e = getenv("S2ST_GL_TEAM");
+        p->opt_team = !(e && e[0] == '0');
         e = getenv("S2ST_INVERSE_MEL");
         p->opt_inverse_mel_simt = (e && e[0] == 's') ? 1 : 0;
         p->opt_frontend_generic = getenv("S2ST_LOGMEL_GENERIC") ? 1 : 0;
@@ -408,6 +410,9 @@ int s2st_plan_set_option(s2st_plan* plan, int option, int value) {
             return S2ST_OK;
         case S2ST_OPT_GL_PDL:
             plan->opt_pdl = value != 0;
+            return S2ST_OK;
+        case S2ST_OPT_GL_TEAM:
+            plan->opt_team = value != 0;
             return S2ST_OK;
         case S2ST_OPT_INVERSE_MEL:
             if (value < 0 || value > 1) break;

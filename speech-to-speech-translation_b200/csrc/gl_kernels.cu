@@ -130,11 +130,21 @@ __device__ __forceinline__ void st_release(int* ptr, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 
+constexpr int kTeam = 4;  // warps per strip in team mode (small calls)
 constexpr unsigned kPersistSleepNs = 100;  // back-off of the neighbour wait (20 ns measured the same)
 
-template <int NZ, bool FIRST, bool PRUNED, bool STD, bool PERSIST = false>
+// TEAM > 1 (small calls): TEAM consecutive warps share ONE strip.  The frames of the strip are dealt round-robin to the
+// team's warps, so their transforms -- all of a frame's latency, ~8 us when a warp has an SM nearly to itself -- run in
+// parallel; only the overlap-add into the (now team-shared) ring and the write-out of the finished hop are serialised,
+// in frame order, through a turn counter in shared memory.  The order of the additions is therefore exactly the one
+// of the single-warp strip: results are bitwise identical (test_team_mode_is_bitwise_identical).  A small call is
+// bound by the latency of one warp walking its 4-frame strip (profiles/r02_small_calls.txt); with TEAM = 4 a pass
+// lasts one frame plus four short ordered sections.
+template <int NZ, bool FIRST, bool PRUNED, bool STD, bool PERSIST = false, int TEAM = 1>
 __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant__ GlParams p) {
     static_assert(!PERSIST || (!FIRST && STD), "persistent mode is the standard-geometry iteration only");
+    static_assert(TEAM == 1 || (!PERSIST && kGlWarps % TEAM == 0), "team mode: whole teams per CTA, no persistent mode");
+    __shared__ int s_turn[kGlWarps];  // TEAM > 1: s_turn[team] = next frame of the team's strip whose ordered section may run
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);            // 1024
     float2* s_vtab = s_tw + 1024;                                  // 1024
@@ -146,8 +156,10 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
     const int ring_floats = (ws + 3) & ~3;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int team = warp / TEAM, member = warp % TEAM;  // TEAM == 1: team = warp, member = 0
     float* scratch = s_warp + warp * (kScratchFloats + ring_floats);
-    float* ring = scratch + kScratchFloats;
+    float* ring = s_warp + (team * TEAM) * (kScratchFloats + ring_floats) + kScratchFloats;  // the team's first warp's ring
+    if (TEAM > 1 && tid < kGlWarps) s_turn[tid] = 0;
     for (int i = tid; i < 1024; i += kGlThreads) {
         s_tw[i] = p.tw[i];
         s_vtab[i] = p.vtab[i];
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
 
     // strips are dealt to SMs first, then to warps: a small batch spreads one warp per SM (a lone warp runs a frame
     // about twice as fast as one of 16 sharing the SM) instead of filling a few SMs
-    for (int strip = blockIdx.x + gridDim.x * warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
+    for (int strip = blockIdx.x + gridDim.x * team; strip < n_strips; strip += gridDim.x * (kGlWarps / TEAM)) {
         const TileDesc td = p.tiles[strip];
         UttDesc ud;
         ud.wave_off = td.wave_off;
@@ -191,15 +203,32 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
         float* out = (PERSIST ? p.bufs[it % 3] : p.out) + ud.wave_off;
         float* znext = (PERSIST ? p.bufs[(it + 1) % 3] : p.zero_next) + ud.wave_off;
         const float* y = (PERSIST ? p.bufs[(it + 2) % 3] : p.in) + ud.wave_off;
-        const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0) * p.mag_stride;
-        const float* phrow = (FIRST && p.phase) ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
+        const int f_first = TEAM > 1 ? member : 0;  // first frame of the strip this warp runs
+        const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0 + f_first) * p.mag_stride;
+        const float* phrow = (FIRST && p.phase) ? p.phase + ((size_t)ud.frame_off + td.f0 + f_first) * p.phase_stride : nullptr;
 
         float2 a[32];
         int slot0 = 0;  // ring slot of strip-relative sample f * hop
         // f = -1 only fetches frame 0; iteration f processes frame f and fetches frame f + 1, so the
         // (single) copy of the load code overlaps with the write-out of the previous hop.
+        // the frame load (one copy of the code): TEAM == 1 fetches frame f + 1 while hop f is written out, a team member
+        // fetches its own next frame at the top of its iteration
+        auto fetch_frame = [&](int fi) {
+            const int jf = j_base + fi * hop;  // first sample of the frame (lane 0)
+            if (aligned && jf >= 0 && jf + 64 * NZ <= L) {
+                const float2* src = reinterpret_cast<const float2*>(y + jf) + lane;
+#pragma unroll
+                for (int r = 0; r < NZ; ++r) a[brev5(r)] = PERSIST ? __ldcg(src + 32 * r) : src[32 * r];
+                // the hop the frame after that adds is not in cache yet: ask L2 for it now (11 lines)
+                const int jp = jf + 64 * NZ - 16 + 32 * lane;
+                if (lane < 11 && jp < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + jp));
+            } else {
+                load_frame_edge<NZ, PERSIST>(a, y, jf + 2 * lane, L);
+            }
+        };
 #pragma unroll 1
-        for (int f = FIRST ? 0 : -1; f < td.nf; ++f) {
+        for (int f = TEAM > 1 ? member : (FIRST ? 0 : -1); f < td.nf; f += TEAM) {
+            if constexpr (TEAM > 1 && !FIRST) fetch_frame(f);
             if (f >= 0) {
                 float ynyq = 0.0f;
                 float mg[kPrunedRows];
@@ -256,7 +285,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                                 const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + 1024;
                                 ynyq = __ldg(magrow + 1024) * (p.phase ? cosf(__ldg(phrow + 1024)) : cospif(2.0f * uniform01(p.phase_seed, e) - 1.0f));
                             }
-                            if (p.phase) phrow += p.phase_stride;
+                            if (p.phase) phrow += TEAM * p.phase_stride;
                         }
                         inv_merge<PRUNED, true, true>(a, ynyq, scratch, s_vtab, lane);
                     }
@@ -323,7 +352,15 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                         }
                     }
                 }
-                magrow += p.mag_stride;
+                magrow += TEAM * p.mag_stride;
+                if constexpr (TEAM > 1) {
+                    // ordered section: frames add into the team's ring in frame order
+                    if (lane == 0)
+                        while (*reinterpret_cast<volatile int*>(&s_turn[team]) != f) {
+                        }
+                    __syncwarp();
+                    slot0 = (f * hop) % ws;
+                }
                 // a[] holds the synthesis frame with the parts swapped (.y = even sample, .x = odd sample):
                 // window and overlap-add into the private ring
                 const float* w = s_win_a + 2 * lane;
@@ -362,20 +399,8 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                 }
             }
             // fetch the next frame (the loads fly while the finished hop is written out)
-            if constexpr (!FIRST) {
-                if (f + 1 < td.nf) {
-                    const int jf = j_base + (f + 1) * hop;  // first sample of the frame (lane 0)
-                    if (aligned && jf >= 0 && jf + 64 * NZ <= L) {
-                        const float2* src = reinterpret_cast<const float2*>(y + jf) + lane;
-#pragma unroll
-                        for (int r = 0; r < NZ; ++r) a[brev5(r)] = PERSIST ? __ldcg(src + 32 * r) : src[32 * r];
-                        // the hop the frame after that adds is not in cache yet: ask L2 for it now (11 lines)
-                        const int jp = jf + 64 * NZ - 16 + 32 * lane;
-                        if (lane < 11 && jp < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + jp));
-                    } else {
-                        load_frame_edge<NZ, PERSIST>(a, y, jf + 2 * lane, L);
-                    }
-                }
+            if constexpr (!FIRST && TEAM == 1) {
+                if (f + 1 < td.nf) fetch_frame(f + 1);
             }
             if (f >= 0) {
                 __syncwarp();
@@ -411,10 +436,17 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                 slot0 += hop;
                 if (slot0 >= ws) slot0 -= ws;
                 __syncwarp();
+                if constexpr (TEAM > 1) {
+                    if (f + 1 < td.nf) {  // (the owner of the last frame still has the tail to write)
+                        __threadfence_block();
+                        if (lane == 0) *reinterpret_cast<volatile int*>(&s_turn[team]) = f + 1;
+                    }
+                }
             }
         }
-        // the tail of the last frame: [nf*hop, (nf-1)*hop + ws)
-        if (STD && T - td.f0 - td.nf >= 3) {
+        // the tail of the last frame: [nf*hop, (nf-1)*hop + ws) -- in team mode written by the warp that ran the last frame
+        if (TEAM > 1 && member != (td.nf - 1) % TEAM) {
+        } else if (STD && T - td.f0 - td.nf >= 3) {
             // right seam of an interior strip (the next strip has at least three frames, so the window sum is the
             // steady one): add our part, and clear the same samples of the buffer the NEXT pass accumulates into
             const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
@@ -437,6 +469,14 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
             emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
         }
         __syncwarp();
+        if constexpr (TEAM > 1) {
+            // end of the strip: the ring is all zero again; reset the turn counter for the team's next strip
+            if (member == (td.nf - 1) % TEAM) {
+                __threadfence_block();
+                if (lane == 0) *reinterpret_cast<volatile int*>(&s_turn[team]) = 0;
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(32 * TEAM) : "memory");
+        }
         if constexpr (PERSIST) {
             __threadfence();  // every lane's stores / reductions of this iteration, before the strip is published
             __syncwarp();
@@ -741,9 +781,9 @@ int allow_dynamic_smem(size_t smem, int device) {
     return S2ST_OK;
 }
 
-template <int NZ, bool FIRST, bool PRUNED, bool STD = false>
+template <int NZ, bool FIRST, bool PRUNED, bool STD = false, int TEAM = 1>
 int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream) {
-    if (int rc = allow_dynamic_smem<k_gl_pass<NZ, FIRST, PRUNED, STD>>(smem, p.device)) return rc;
+    if (int rc = allow_dynamic_smem<k_gl_pass<NZ, FIRST, PRUNED, STD, false, TEAM>>(smem, p.device)) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGlThreads);
@@ -754,7 +794,7 @@ int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.pdl ? 1 : 0;
-    S2ST_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gl_pass<NZ, FIRST, PRUNED, STD>, p));
+    S2ST_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gl_pass<NZ, FIRST, PRUNED, STD, false, TEAM>, p));
     return S2ST_OK;
 }
 
@@ -934,9 +974,13 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
         // the iteration kernel specialised for the vocoder's standard geometry, else the generic one
         const bool std_geom = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                               plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
-        const int rc = (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
-                       : (plan->nz == 19)   ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
-                                            : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
+        // small calls (every strip gets a team of kTeam warps): the team kernels -- same arithmetic, same order
+        const bool team = std_geom && plan->opt_team != 0 && strips_ub <= (long long)plan->num_sms * (kGlWarps / kTeam);
+        const int rc = team ? (it > 0 ? launch_pass_t<19, false, true, true, kTeam>(p, grid, smem, stream)
+                                      : launch_pass_t<19, true, true, false, kTeam>(p, grid, smem, stream))
+                       : (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
+                       : (plan->nz == 19)     ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
+                                              : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
         if (rc != S2ST_OK) return rc;
     }
     if (timed) {

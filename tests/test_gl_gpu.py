@@ -220,6 +220,37 @@ def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
             assert torch.equal(a, b)
 
 
+def test_team_mode_is_bitwise_identical(pkg, voc, basis):
+    """Small calls run four warps per strip (k_gl_pass TEAM = 4: frames of a strip transformed in parallel, overlap-add
+    serialised in frame order).  Same additions in the same order -> bitwise equal to the one-warp-per-strip kernels, for
+    single utterances of every tail shape, ragged small batches, the initial inverse alone, and pinned strip lengths."""
+    plan = voc._plan(torch.device("cuda", 0))
+    cases = [[5], [6], [7], [8], [9], [37], [500], [5, 9, 31, 64, 65, 100, 257, 400], [56] * 30]
+    try:
+        for strip in (0, 7):
+            plan.set_strip_frames(strip)
+            for frames in cases:
+                feats = [synth_logmel(T, 900 + i, "smooth" if i % 2 else "iid").cuda() for i, T in enumerate(frames)]
+                phases = [seeded_phase(950 + i, T) for i, T in enumerate(frames)]
+                for n_iter in (0, 5):
+                    plan.set_option(pkg._lib.OPT_GL_TEAM, 0)
+                    base = voc.synthesize_batch(feats, init_phase=phases, n_iter=n_iter)
+                    plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
+                    team = voc.synthesize_batch(feats, init_phase=phases, n_iter=n_iter)
+                    for a, b in zip(base, team):
+                        assert torch.equal(a, b), (strip, frames, n_iter)
+        # the device-drawn initial phase goes through the same first pass
+        x = synth_logmel(300, 1).cuda()
+        plan.set_option(pkg._lib.OPT_GL_TEAM, 0)
+        a = voc.synthesize_flat(x, [300], None, n_iter=3, seed=11)
+        plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
+        assert torch.equal(a, voc.synthesize_flat(x, [300], None, n_iter=3, seed=11))
+    finally:
+        plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
+        plan.set_strip_frames(0)
+    ref = ogl.vocoder_forward(synth_logmel(37, 905, "smooth").numpy(), seeded_phase(955, 37), 5, basis=basis)
+
+
 def test_config1_500_frames_64_iters(pkg, voc, basis):
     """BASELINE config 1: one 500-frame utterance, 64 iterations, seeded phase."""
     x = synth_logmel(500, 1234)
