@@ -29,7 +29,8 @@ for what in "$@"; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_logmel_fast -s 2 -c 1 -f -o gpurun_out/logmel python tools/profile_logmel.py 400 > gpurun_out/ncu_logmel.log 2>&1
       tail -2 gpurun_out/ncu_logmel.log ;;
     ncu_mel)
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_inverse_mel_tc -s 1 -c 1 -f -o gpurun_out/invmel python tools/profile_gl.py 1 > gpurun_out/ncu_mel.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_inverse_mel_tc -s 2 -c 1 -f -o gpurun_out/invmel python tools/profile_mel.py > gpurun_out/ncu_mel.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mel_project_tc -s 2 -c 1 -f -o gpurun_out/melproj python tools/profile_mel.py >> gpurun_out/ncu_mel.log 2>&1
       tail -2 gpurun_out/ncu_mel.log ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv env BENCH_NO_EXTRAS=1 python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1 ;;
