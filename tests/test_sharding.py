@@ -71,7 +71,15 @@ def _worker(rank, world, port, q):
     out_flat = sh.gather_waveforms(mine, torch.cat(waves) if waves else torch.empty(0), len(frames), dst=0,
                                    local_lengths=[w.numel() for w in waves])
     if rank == 0:
-        assert all(torch.equal(a, b) for a, b in zip(out, out_flat))
+        assert all(torch.equal(a, b) for a, b in zip(out, out_flat)) and len(out_flat.to_list()) == len(frames)
+    # layout known to every rank (deterministic sharding): no metadata exchange; asynchronous start, wait() later
+    layout = [(owned[r], [(frames[i] - 1) * 3 for i in owned[r]]) for r in range(world)]
+    h = sh.gather_waveforms(mine, torch.cat(waves), len(frames), dst=0, local_lengths=layout[rank][1], layout=layout, async_op=True)
+    res = h.wait()
+    if rank == 0:
+        assert all(torch.equal(res[i], out[i]) for i in range(len(frames)))
+    else:
+        assert res is None
     # a rank with nothing to send, and a non-zero destination
     mine2 = list(range(len(frames))) if rank == 0 else []
     waves2 = [torch.full((frames[i],), float(i)) for i in mine2]
