@@ -87,6 +87,23 @@ class CompositeAudioFeatureTransform(AudioFeatureTransform):
             x = t.apply_cuda(x, frames)
         return x
 
+    def apply_cuda_from_host(self, feats, device=None):
+        """The post-collate entry for DataLoader pipelines: ``feats`` is the list of per-utterance ``[T_i, n_feat]`` numpy
+        arrays a transform-free dataset produced in its (forked) workers.  They are concatenated into one pinned buffer,
+        uploaded once, run through the whole chain on the device (``apply_cuda``) and returned as a list of CUDA tensors
+        (views of one buffer) -- the numpy ``__call__`` per utterance inside the workers is not needed at all."""
+        import numpy as np
+        import torch
+
+        from ..plans import require_cuda
+        dev = require_cuda(device)
+        frames = [int(f.shape[0]) for f in feats]
+        n_feat = int(feats[0].shape[1])
+        staged = torch.empty(sum(frames), n_feat, dtype=torch.float32, pin_memory=True)
+        np.concatenate([np.asarray(f, np.float32) for f in feats], out=staged.numpy())
+        x = self.apply_cuda(staged.to(dev, non_blocking=True), frames)
+        return list(torch.split(x, frames))
+
     def __repr__(self):
         lines = [self.__class__.__name__ + "("] + [f"    {t!r}" for t in self.transforms] + [")"]
         return "\n".join(lines)

@@ -27,6 +27,15 @@ def _np_ptr(a):
 
 
 def require_cuda(device=None):
+    if torch.cuda._is_in_bad_fork():
+        # the reference runs its numpy transforms in FORKED DataLoader workers; a forked child cannot use the CUDA context
+        # of its parent.  Fail with the two supported set-ups instead of CUDA's "Cannot re-initialize CUDA in forked
+        # subprocess": (1) keep the dataset transform-free and run CompositeAudioFeatureTransform.apply_cuda_from_host on
+        # the collated batch in the main process (one launch per transform per batch: the fast way), or (2) start the
+        # workers with DataLoader(..., multiprocessing_context="spawn").  INTEGRATION.md, "DataLoader workers".
+        raise RuntimeError("s2st_b200 was called in a forked worker process after CUDA was initialised in the parent. Apply "
+                           "the feature transforms after collation (CompositeAudioFeatureTransform.apply_cuda_from_host) "
+                           "or create the DataLoader with multiprocessing_context='spawn'; see INTEGRATION.md")
     if not torch.cuda.is_available():
         raise RuntimeError("s2st_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     if device is None or torch.device(device).type != "cuda":

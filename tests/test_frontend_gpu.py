@@ -408,3 +408,33 @@ def test_composite_chain_on_a_ragged_device_batch(pkg, built_lib, tmp_path):
     np.random.seed(9)
     yb = chain.apply_cuda(torch.from_numpy(np.concatenate(xs)).cuda(), [x.shape[0] for x in xs]).cpu().numpy()
     assert np.array_equal(yb, np.concatenate(singles))
+    # the post-collate entry for DataLoader pipelines (numpy list in, device tensors out)
+    np.random.seed(9)
+    outs = chain.apply_cuda_from_host(xs)
+    assert all(o.is_cuda and np.array_equal(o.cpu().numpy(), s) for o, s in zip(outs, singles))
+
+
+def _forked_child(q):
+    import importlib
+    try:
+        pkg = importlib.import_module("speech-to-speech-translation_b200")
+        pkg.GlobalCMVN  # noqa: B018
+        from numpy import zeros
+        importlib.import_module("speech-to-speech-translation_b200.plans").require_cuda()
+        q.put("no error")
+    except RuntimeError as e:
+        q.put(str(e))
+
+
+def test_forked_worker_fails_with_guidance(pkg, built_lib):
+    """The reference's threading model is forked DataLoader workers calling the numpy transforms.  A forked child cannot
+    share the parent's CUDA context: the product says what to do instead of crashing inside CUDA."""
+    import multiprocessing as mp
+    torch.zeros(1).cuda()  # CUDA is initialised in this (parent) process
+    ctx = mp.get_context("fork")
+    q = ctx.SimpleQueue()
+    p = ctx.Process(target=_forked_child, args=(q,))
+    p.start()
+    p.join(60)
+    msg = q.get()
+    assert "apply_cuda_from_host" in msg and "spawn" in msg, msg
