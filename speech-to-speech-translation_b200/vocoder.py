@@ -76,6 +76,17 @@ class PseudoInverseMelScale(torch.nn.Module):
 
 
 class GriffinLim(torch.nn.Module):
+    """Same constructor / ``forward`` / ``inverse`` / ``get_window_sum_square`` as the reference (vocoder.py:49-110).
+
+    One deliberate deviation, visible only with a ``window_fn`` other than ``torch.hann_window`` (the recipe and every
+    config of the reference use hann): the reference builds its ANALYSIS transform and its window-sum-square with the
+    default hann window whatever ``window_fn`` is (vocoder.py:54, :90) and applies ``window_fn`` only to the synthesis
+    basis (:62) -- an inconsistency of that code, not a design.  Here ``window_fn`` is used for analysis, synthesis and
+    the normalisation alike, so a non-hann window gives a consistent (perfect-reconstruction) STFT pair but not the
+    reference's numbers.  The module's constant is registered as ``window`` ([win_length]); the reference's dense
+    ``basis`` buffer ([2050, 1, 2048]) does not exist because the transforms are FFTs (state dicts carry no learned
+    parameters either way)."""
+
     def __init__(self, n_fft: int, win_length: int, hop_length: int, n_iter: int, window_fn=torch.hann_window):
         super().__init__()
         _check_synthesis_geometry(n_fft)
