@@ -99,12 +99,13 @@ __device__ __noinline__ void emit_generic(float* __restrict__ ring, const float*
     }
 }
 
+constexpr int kStdHop = 300, kStdWs = 1200, kStdRot = 424;  // the vocoder's standard geometry (see k_gl_pass STD)
+
 // One Griffin-Lim pass.  FIRST: spectra come from (mag, initial phase) -> inverse only.
 // PRUNED: every live bin is below 704 (kb <= 704): magnitudes are prefetched into registers and the
 // pair exchanges move 22 rows instead of 32.
 // STD: the vocoder's standard geometry (hop 300, window support 1200 starting at sample 424 of the 2048-point
 // frame, magnitude rows at least 704 wide) as compile-time constants: no geometry tests in the frame loop.
-constexpr int kStdHop = 300, kStdWs = 1200, kStdRot = 424;
 // S2ST_GL_SHARED_FFT=1 builds the compact variant: analysis and synthesis share one copy of the 1024-point routine
 // and that routine runs one copy of the in-lane FFT twice (23 KB hot loop instead of 40 KB).  Measured on B200 the
 // straight-line variant is 4.5 % faster: its loop-carried register shuffles cost more than its I-cache misses.
@@ -367,6 +368,11 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                 if (geom4) {
                     // samples past the window support have zero weight: they wrap onto a live slot and add
                     // +0, so every row can accumulate without a bounds test (slots stay even -> 8-byte RMW)
+                    // (Measured and rejected, round 2: issuing the ring / window loads of a batch of rows ahead of the
+                    // stores -- the compiler serialises them as written, possible alias -- costs registers the loop does
+                    // not have: 20-32 bytes of spills, 0.2425 ms per pass instead of 0.2369; specialising the section on
+                    // the four ring positions, immediate offsets and no wrap arithmetic, quadruples it and pushes the hot
+                    // loop past the instruction cache: 0.2450 ms.)
                     const int first = slot0 + 2 * lane;
                     const int until_wrap = ws - first;  // rows with 64 r >= until_wrap wrap around once
 #pragma unroll
