@@ -983,8 +983,9 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
         // small calls (every strip gets a team of kTeam warps): the team kernels -- same arithmetic, same order
         const bool team = std_geom && plan->opt_team != 0 && strips_ub <= (long long)plan->num_sms * (kGlWarps / kTeam);
         const int rc = team ? (it > 0 ? launch_pass_t<19, false, true, true, kTeam>(p, grid, smem, stream)
-                                      : launch_pass_t<19, true, true, false, kTeam>(p, grid, smem, stream))
+                                      : launch_pass_t<19, true, true, true, kTeam>(p, grid, smem, stream))
                        : (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
+                       : std_geom             ? launch_pass_t<19, true, true, true>(p, grid, smem, stream)
                        : (plan->nz == 19)     ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
                                               : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);
         if (rc != S2ST_OK) return rc;
