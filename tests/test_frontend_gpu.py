@@ -187,6 +187,43 @@ def test_default_arguments_and_other_fft_sizes(pkg, built_lib):
         pkg.extract_logmel_spectrogram(torch.zeros(1, 4000), 22050, n_fft=1200, win_length=1200, hop_length=300)
 
 
+def test_config3_shape_properties(pkg, built_lib):
+    """BASELINE config 3 shape (fbank80 + global CMVN over many 8-20 s utterances at 16 kHz; 600 of them here, 8.4 M
+    frames' worth of code paths) through size-independent properties: an utterance's features do not depend on the
+    batch (bitwise), the fused CMVN equals features-then-CMVN to rounding, the fused statistics equal the sums of the
+    returned features, runs are deterministic, and sampled utterances match the oracle."""
+    import importlib
+    rng = np.random.RandomState(0)
+    n_utts, sr = 600, 16000
+    lens = (rng.uniform(8, 20, n_utts) * sr).astype(np.int64)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    flat = (torch.randn(int(lens.sum()), device="cuda", generator=g) * 0.1).clamp_(-1, 1) * 2 ** 15
+    waves = list(torch.split(flat, lens.tolist()))
+    mean = torch.from_numpy((rng.randn(80) - 4).astype(np.float32))
+    std = torch.from_numpy(rng.uniform(0.5, 2, 80).astype(np.float32))
+    stats = torch.zeros(2, 80, dtype=torch.float64, device="cuda")
+    plain = pkg.fbank_batch(waves, sr, stats=stats)
+    again = pkg.fbank_batch(waves, sr)
+    fused = pkg.fbank_batch(waves, sr, cmvn_mean=mean, cmvn_std=std)
+    assert [p.shape[0] for p in plain] == [1 + (int(n) - 400) // 160 for n in lens]
+    assert all(torch.equal(a, b) for a, b in zip(plain, again))  # deterministic
+    allf = torch.cat(plain)
+    assert torch.isfinite(allf).all()
+    assert torch.allclose(stats[0], allf.double().sum(0), rtol=1e-7, atol=1e-3)
+    assert torch.allclose(stats[1], (allf.double() ** 2).sum(0), rtol=1e-7, atol=1e-2)
+    ref_fused = (allf - mean.cuda()) / std.cuda()
+    assert float((torch.cat(fused) - ref_fused).abs().max()) < 2e-5
+    for i in (0, 17, 311, n_utts - 1):
+        alone = pkg.fbank_batch([waves[i]], sr)[0]
+        assert torch.equal(alone, plain[i])  # batch invariant, bitwise
+        if i in (0, 311):
+            ref = ofe.kaldi_fbank(waves[i].cpu().numpy(), sr)
+            assert ogl.rel_l2(plain[i].cpu().numpy(), ref) < 1e-5
+    cm = importlib.import_module(pkg.__name__ + ".feature_transforms.global_cmvn")
+    sep = cm.cmvn_apply_cuda(allf, mean.cuda(), std.cuda())
+    assert torch.equal(sep, ref_fused)  # the stand-alone kernel is the IEEE subtract / divide
+
+
 def test_get_global_cmvn_drop_in_matches_reference_fixture(pkg, built_lib, tmp_path):
     """get_global_cmvn(feature_root, output_path=None) -- the reference's signature -- against the fixture generated by
     the reference's own function: bit-exact when the files are visited in the order the reference saw them (per-file
