@@ -8,14 +8,15 @@
 // and three MMAs are accumulated in fp32 in TMEM:  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (the dropped tail*tail
 // term is ~2^-22 relative).
 //
-// One CTA = 128 frames (UMMA M = 128, cta_group::1), 128 threads:
-//   - all threads: exp + hi/lo split of the A tile into shared memory in the canonical K-major, no-swizzle
-//     UMMA layout (8-row x 16-byte core matrices; SBO = 128 B between 8-row groups, LBO between 4-element
-//     K chunks);
-//   - per N chunk of 176 bins: copy the pre-split, pre-laid-out B chunk from global (L2 resident, built once
-//     by the plan), one elected thread issues 3 x (K / 8) tcgen05.mma kind::tf32 into a 176-column fp32
-//     accumulator in TMEM and commits to an mbarrier; then every thread reads its own row (TMEM lane) back
-//     with tcgen05.ld, clamps at zero and stores it.
+// One CTA = 128 frames (UMMA M = 128, cta_group::1), 128 threads, software-pipelined over 8 chunks of 96 bins:
+//   - the pre-split, pre-laid-out B chunks (built once by the plan, L2 resident) arrive by BULK ASYNC COPY
+//     (cp.async.bulk -> mbarrier complete_tx; SASS UBLKCP) into two alternating shared-memory buffers; the first two
+//     are in flight while all threads do exp + hi/lo split of the A tile into the canonical K-major, no-swizzle UMMA
+//     layout (8-row x 16-byte core matrices; SBO = 128 B between 8-row groups, LBO between 4-element K chunks);
+//   - one elected thread issues the 3 x (K / 8) tcgen05.mma kind::tf32 of chunk c + 1 into the OTHER of two 96-column
+//     fp32 accumulators in TMEM before the CTA reads chunk c back, so the tensor pipe works under the epilogue;
+//   - epilogue: every thread reads its own row (TMEM lane) with tcgen05.ld, clamps at zero and stores 16 bytes at a
+//     time; when the chunk's MMAs have retired its B buffer is refilled with chunk c + 2.
 #include <stdint.h>
 
 #include <cstring>
@@ -28,9 +29,9 @@ namespace s2st {
 namespace {
 
 constexpr int kTcM = 128;        // frames per CTA (UMMA M)
-constexpr int kTcNChunk = 176;   // bins per MMA (UMMA N, multiple of 16)
-constexpr int kTcChunks = 4;     // 4 * 176 = 704 >= live bins
-constexpr int kTcTmemCols = 256; // power of two >= kTcNChunk
+constexpr int kTcNChunk = 96;    // bins per MMA (UMMA N, multiple of 16)
+constexpr int kTcChunks = 8;     // 8 * 96 = 768 >= 704 live bins (rows beyond the basis are zero)
+constexpr int kTcTmemCols = 256; // power of two >= 2 accumulators of kTcNChunk columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -79,24 +80,36 @@ struct TcParams {
     int K, is_log, out_stride, n_out;
 };
 
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int K = p.K, kc = K >> 2;                      // K chunks of 4 elements (16 bytes)
     const int a_floats = kTcM * K, b_floats = kTcNChunk * K;
     float* sA_hi = reinterpret_cast<float*>(smem_raw);
     float* sA_lo = sA_hi + a_floats;
-    float* sB_hi = sA_lo + a_floats;
-    float* sB_lo = sB_hi + b_floats;
-    __shared__ __align__(8) uint64_t s_bar;
+    float* sB[2] = {sA_lo + a_floats, sA_lo + a_floats + 2 * b_floats};  // each: head then tail of one chunk
+    __shared__ __align__(8) uint64_t s_full[2], s_done[2];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t0 = (long long)blockIdx.x * kTcM;
     const int rows = (int)min((long long)kTcM, p.n_frames - t0);
+    const uint32_t chunk_bytes = 2u * (uint32_t)b_floats * 4u;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_done[i])));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first two B chunks fly while the CTA prepares A
+        for (int i = 0; i < 2; ++i) bulk_load(sB[i], p.b_tc + (size_t)i * 2 * b_floats, chunk_bytes, smem_u32(&s_full[i]));
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTcTmemCols));
@@ -117,6 +130,7 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
         *reinterpret_cast<float4*>(sA_hi + off) = hi;
         *reinterpret_cast<float4*>(sA_lo + off) = lo;
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A -> visible to the MMA
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -125,36 +139,38 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNChunk >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
     const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (kTcNChunk / 8) * 128, sbo = 128;
-    uint32_t phase = 0;
-    const bool vec_store = (p.out_stride & 3) == 0 && p.n_out >= kTcChunks * kTcNChunk && (reinterpret_cast<uintptr_t>(p.mag) & 15) == 0;
+    const bool vec_store = (p.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mag) & 15) == 0;
 
-    for (int chunk = 0; chunk < kTcChunks; ++chunk) {
-        // B chunk (head and tail are adjacent in global): straight 16-byte copies
-        const float4* bsrc = reinterpret_cast<const float4*>(p.b_tc + (size_t)chunk * 2 * b_floats);
-        float4* bdst = reinterpret_cast<float4*>(sB_hi);
-        for (int i = tid; i < 2 * b_floats / 4; i += 128) bdst[i] = __ldg(bsrc + i);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t acc = 0;
-#pragma unroll 1
-            for (int term = 0; term < 3; ++term) {
-                const uint32_t a_base = smem_u32(term == 2 ? sA_lo : sA_hi);
-                const uint32_t b_base = smem_u32(term == 1 ? sB_lo : sB_hi);
-                for (int ks = 0; ks < K / 8; ++ks) {
-                    mma_tf32(tmem, make_desc(a_base + ks * 2 * lbo_a, lbo_a, sbo),
-                             make_desc(b_base + ks * 2 * lbo_b, lbo_b, sbo), idesc, acc);
-                    acc = 1;
-                }
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
-        }
-        mbar_wait(smem_u32(&s_bar), phase);
-        phase ^= 1;
+    // chunk c: B buffer c & 1, accumulator columns (c & 1) * kTcNChunk; mbarrier phase (c >> 1) & 1
+    auto issue_mma = [&](int c) {  // thread 0 only
+        const int buf = c & 1;
+        mbar_wait(smem_u32(&s_full[buf]), (uint32_t)(c >> 1) & 1);  // the chunk's B has landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem + (uint32_t)(buf * kTcNChunk);
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int term = 0; term < 3; ++term) {
+            const uint32_t a_base = smem_u32(term == 2 ? sA_lo : sA_hi);
+            const uint32_t b_base = smem_u32(term == 1 ? sB[buf] + b_floats : sB[buf]);
+            for (int ks = 0; ks < K / 8; ++ks) {
+                mma_tf32(d, make_desc(a_base + ks * 2 * lbo_a, lbo_a, sbo), make_desc(b_base + ks * 2 * lbo_b, lbo_b, sbo), idesc, acc);
+                acc = 1;
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_done[buf])) : "memory");
+    };
+    if (tid == 0) issue_mma(0);
+    for (int chunk = 0; chunk < kTcChunks; ++chunk) {
+        const int buf = chunk & 1;
+        // the next chunk's MMAs go to the other accumulator and run under this chunk's epilogue
+        if (tid == 0 && chunk + 1 < kTcChunks) issue_mma(chunk + 1);
+        mbar_wait(smem_u32(&s_done[buf]), (uint32_t)(chunk >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // this chunk's MMAs have retired: its B buffer is free for chunk + 2
+        if (tid == 0 && chunk + 2 < kTcChunks)
+            bulk_load(sB[buf], p.b_tc + (size_t)(chunk + 2) * 2 * b_floats, chunk_bytes, smem_u32(&s_full[buf]));
         // epilogue: thread tid owns row tid (TMEM lane tid); 16 columns per tcgen05.ld
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kTcNChunk);
         float* orow = p.mag + (t0 + tid) * (long long)p.out_stride + chunk * kTcNChunk;
         for (int c0 = 0; c0 < kTcNChunk; c0 += 16) {
             uint32_t r[16];
@@ -164,11 +180,11 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                 : "r"(lane_addr + c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (tid < rows) {
-                if (vec_store) {
-                    // the thread's 16 consecutive bins as four 16-byte stores (rows are 16-byte aligned and at least
-                    // 704 wide): scalar stores from 32 different rows per instruction made this epilogue the
-                    // kernel's bottleneck
+            const int col0 = chunk * kTcNChunk + c0;
+            if (tid < rows && col0 < p.n_out) {
+                if (vec_store && col0 + 16 <= p.n_out) {
+                    // the thread's 16 consecutive bins as four 16-byte stores: scalar stores from 32 different rows per
+                    // instruction made this epilogue the kernel's bottleneck
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
@@ -176,17 +192,16 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
                                         fmaxf(__uint_as_float(r[4 * q + 2]), 0.0f), fmaxf(__uint_as_float(r[4 * q + 3]), 0.0f));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int col = chunk * kTcNChunk + c0 + j;
-                        if (col < p.n_out) orow[c0 + j] = fmaxf(__uint_as_float(r[j]), 0.0f);
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        if (col0 + j < p.n_out) orow[c0 + j] = fmaxf(__uint_as_float(r[j]), 0.0f);
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // TMEM and the B buffers may be overwritten by the next chunk
+        __syncthreads();  // every thread has read this accumulator: chunk + 2 may overwrite it
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    // columns beyond the live bins are exactly zero
+    // columns beyond the chunks are exactly zero
     if (tid < rows)
         for (int col = kTcChunks * kTcNChunk; col < p.n_out; ++col) p.mag[(t0 + tid) * (long long)p.out_stride + col] = 0.0f;
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
@@ -395,7 +410,7 @@ int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float
     p.is_log = is_log ? 1 : 0;
     p.out_stride = out_stride;
     p.n_out = n_out;
-    const size_t smem = sizeof(float) * (size_t)(2 * kTcM * p.K + 2 * kTcNChunk * p.K) + 1024;
+    const size_t smem = sizeof(float) * (size_t)(2 * kTcM * p.K + 4 * kTcNChunk * p.K) + 1024;  // A head + tail, two B chunk buffers
     S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_inverse_mel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = (n_frames + kTcM - 1) / kTcM;
     k_inverse_mel_tc<<<(unsigned)blocks, 128, smem, stream>>>(p);
