@@ -257,30 +257,48 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                 for (int pass = FIRST ? 1 : 0; pass < 2; ++pass) {
                     if (pass == 1) {
                         if constexpr (FIRST) {
-#pragma unroll
-                            for (int r = 0; r < (PRUNED ? kPrunedRows : 32); ++r) {
-                                const int k = 32 * r + lane;
-                                if (k < kb) {
-                                    const float m = __ldg(magrow + k);
-                                    // the caller's phase refers to the un-rotated frame; frames are processed
-                                    // rotated by p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048).  The
-                                    // rotation angle (an exact multiple of pi / 1024, reduced to [-pi, pi)) is added
-                                    // to the phase before the one sincos -- half the transcendental work of
-                                    // rotating the phasor afterwards
-                                    const float rot_pi = (float)(((k * p.rot + 1024) & 2047) - 1024) * (1.0f / 1024.0f);
-                                    float sn, cs;
-                                    if (p.phase) {
-                                        // in units of pi: sincospi reduces its argument exactly (no slow path), the
-                                        // product phase / pi rounds to within 1e-7 rad
-                                        sincospif(fmaf(__ldg(phrow + k), 0.31830988618379067154f, rot_pi), &sn, &cs);
-                                    } else {  // phi = 2 pi u - pi, u ~ U[0, 1): same law as vocoder.py:103
-                                        const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + k;
-                                        sincospif(2.0f * uniform01(p.phase_seed, e) - 1.0f + rot_pi, &sn, &cs);
-                                    }
-                                    a[r] = make_float2(m * cs, m * sn);
-                                } else {
-                                    a[r] = make_float2(0.0f, 0.0f);
+                            // spectrum from (magnitude, initial phase).  All loads of the frame are issued first (22-32
+                            // magnitudes + phases per lane): with the loads inside the per-row code the pass was bound
+                            // by global-load latency, 0.46 ms against 0.24 ms for a full iteration.  The phasor is two
+                            // MUFU operations on an argument reduced to [-pi, pi] (absolute error ~5e-7: the initial
+                            // phase is a uniform random draw and the waveform tolerance 1e-3) instead of the ~50
+                            // instructions of sincospif per bin.
+                            constexpr int kRows = PRUNED ? kPrunedRows : 32;
+                            float mgv[kRows], phv[kRows];
+                            if (f + TEAM < td.nf) {
+                                // the next frame's magnitude and phase rows (4.1 + 2.8 KB) are read exactly once, from
+                                // DRAM: ask L2 for them now, one transform ahead of their use (without this the pass
+                                // waits a full DRAM round trip per frame: 63 % of its stall samples)
+                                const char* nm = reinterpret_cast<const char*>(magrow + TEAM * p.mag_stride);
+                                for (int o = 128 * lane; o < 4 * kb; o += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + o));
+                                if (p.phase) {
+                                    const char* np = reinterpret_cast<const char*>(phrow + TEAM * p.phase_stride);
+                                    for (int o = 128 * lane; o < 4 * kb; o += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + o));
                                 }
+                            }
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r) {
+                                const int k = 32 * r + lane;
+                                mgv[r] = k < kb ? __ldg(magrow + k) : 0.0f;
+                                if (p.phase) {
+                                    phv[r] = k < kb ? __ldg(phrow + k) * 0.31830988618379067154f : 0.0f;  // in units of pi
+                                } else {  // phi = 2 pi u - pi, u ~ U[0, 1): same law as vocoder.py:103
+                                    const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + k;
+                                    phv[r] = 2.0f * uniform01(p.phase_seed, e) - 1.0f;
+                                }
+                            }
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r) {
+                                const int k = 32 * r + lane;
+                                // the caller's phase refers to the un-rotated frame; frames are processed rotated by
+                                // p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048).  The rotation angle (an exact
+                                // multiple of pi / 1024, reduced to [-pi, pi)) is added to the phase before the one sincos
+                                const float rot_pi = (float)(((k * p.rot + 1024) & 2047) - 1024) * (1.0f / 1024.0f);
+                                float v = phv[r] + rot_pi;                  // in [-2, 2] (units of pi)
+                                v -= 2.0f * rintf(0.5f * v);                // -> [-1, 1]
+                                float sn, cs;
+                                __sincosf(v * 3.14159265358979323846f, &sn, &cs);
+                                a[r] = make_float2(mgv[r] * cs, mgv[r] * sn);
                             }
                             if (kb > 1024) {
                                 const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + 1024;
