@@ -998,8 +998,11 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
         // the iteration kernel specialised for the vocoder's standard geometry, else the generic one
         const bool std_geom = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                               plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
-        // small calls (every strip gets a team of kTeam warps): the team kernels -- same arithmetic, same order
-        const bool team = std_geom && plan->opt_team != 0 && strips_ub <= (long long)plan->num_sms * (kGlWarps / kTeam);
+        // small calls: the team kernels (kTeam warps per strip) -- same arithmetic, same order.  Only while every team
+        // can have an SM to itself: measured (tools/time_small.py), one 100- or 500-frame utterance gains 22 %, but with
+        // 464 strips (3-4 teams per SM, i.e. all 16 warps busy) the frames no longer run faster in parallel than in
+        // sequence and the ordered sections cost 12 %
+        const bool team = std_geom && plan->opt_team != 0 && strips_ub <= (long long)plan->num_sms;
         const int rc = team ? (it > 0 ? launch_pass_t<19, false, true, true, kTeam>(p, grid, smem, stream)
                                       : launch_pass_t<19, true, true, true, kTeam>(p, grid, smem, stream))
                        : (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
