@@ -259,10 +259,10 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                         if constexpr (FIRST) {
                             // spectrum from (magnitude, initial phase).  All loads of the frame are issued first (22-32
                             // magnitudes + phases per lane): with the loads inside the per-row code the pass was bound
-                            // by global-load latency, 0.46 ms against 0.24 ms for a full iteration.  The phasor is two
-                            // MUFU operations on an argument reduced to [-pi, pi] (absolute error ~5e-7: the initial
-                            // phase is a uniform random draw and the waveform tolerance 1e-3) instead of the ~50
-                            // instructions of sincospif per bin.
+                            // by global-load latency, 0.46 ms against 0.24 ms for a full iteration.  The phasor stays
+                            // the accurate sincospif: a MUFU sin / cos pair (absolute error ~5e-7) is 0.03 ms faster, but
+                            // the iterations amplify a perturbed start -- on the 4800-frame utterance the distance to the
+                            // oracle after 64 iterations went from ~1e-4 to 6.7e-4 of the 1e-3 budget (measured).
                             constexpr int kRows = PRUNED ? kPrunedRows : 32;
                             float mgv[kRows], phv[kRows];
                             if (f + TEAM < td.nf) {
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                                 const int k = 32 * r + lane;
                                 mgv[r] = k < kb ? __ldg(magrow + k) : 0.0f;
                                 if (p.phase) {
-                                    phv[r] = k < kb ? __ldg(phrow + k) * 0.31830988618379067154f : 0.0f;  // in units of pi
-                                } else {  // phi = 2 pi u - pi, u ~ U[0, 1): same law as vocoder.py:103
+                                    phv[r] = k < kb ? __ldg(phrow + k) : 0.0f;  // radians
+                                } else {  // phi = 2 pi u - pi, u ~ U[0, 1): same law as vocoder.py:103 (kept in units of pi)
                                     const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + k;
                                     phv[r] = 2.0f * uniform01(p.phase_seed, e) - 1.0f;
                                 }
@@ -294,10 +294,11 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                                 // p.rot samples:  Y'[k] = Y[k] * exp(+2 pi i k rot / 2048).  The rotation angle (an exact
                                 // multiple of pi / 1024, reduced to [-pi, pi)) is added to the phase before the one sincos
                                 const float rot_pi = (float)(((k * p.rot + 1024) & 2047) - 1024) * (1.0f / 1024.0f);
-                                float v = phv[r] + rot_pi;                  // in [-2, 2] (units of pi)
-                                v -= 2.0f * rintf(0.5f * v);                // -> [-1, 1]
+                                // in units of pi: sincospi reduces its argument exactly (no slow path); the product
+                                // phase / pi rounds to within 1e-7 rad
+                                const float v = p.phase ? fmaf(phv[r], 0.31830988618379067154f, rot_pi) : phv[r] + rot_pi;
                                 float sn, cs;
-                                __sincosf(v * 3.14159265358979323846f, &sn, &cs);
+                                sincospif(v, &sn, &cs);
                                 a[r] = make_float2(mgv[r] * cs, mgv[r] * sn);
                             }
                             if (kb > 1024) {
