@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                             // by global-load latency, 0.46 ms against 0.24 ms for a full iteration.  The phasor stays
                             // the accurate sincospif: a MUFU sin / cos pair (absolute error ~5e-7) is 0.03 ms faster, but
                             // the iterations amplify a perturbed start -- on the 4800-frame utterance the distance to the
-                            // oracle after 64 iterations went from ~1e-4 to 6.7e-4 of the 1e-3 budget (measured).
+                            // CPU restatement after 64 iterations went from ~1e-4 to 6.7e-4 of the 1e-3 budget (measured).
                             constexpr int kRows = PRUNED ? kPrunedRows : 32;
                             float mgv[kRows], phv[kRows];
                             if (f + TEAM < td.nf) {
