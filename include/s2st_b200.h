@@ -252,6 +252,15 @@ int s2st_dtw(int bsz, int m, int n, const float* distance_dev, const int64_t* sh
  * x2_dev [n, d]. */
 int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev, float* out_dev, void* stream);
 
+/* The time warping of SpecAugmentTransform.__call__ (specaugment.py:96-110) for a ragged batch: warp_dev int32 [n_utts, 2] =
+ * (w0, w) per utterance as the reference draws them (w0 < 0: the utterance is copied); rows [0, w0) are resized to w0 + w
+ * rows and rows [w0, T) to T - w0 - w rows like cv2.resize(..., INTER_LINEAR) on float32.  arithmetic = 1: the x86-64
+ * opencv-python wheels (IPP: source position in double, dst = fma(S1 - S0, w, S0)); arithmetic = 0: OpenCV's own code
+ * (position rounded to float, dst = S0 * (1 - w) + S1 * w, both products rounded).  Both are bit-exact against fixtures made
+ * with the reference class.  out_dev must not alias x_dev. */
+int s2st_time_warp(int n_utts, int64_t total_rows, const int32_t* frame_offsets_dev, int n_cols, const int32_t* warp_dev,
+                   int arithmetic, const float* x_dev, float* out_dev, void* stream);
+
 /* Waveform post-processing for file output (examples/s2s_trans/generate_waveform.py:115-124: sf.write of the float
  * waveform, which soundfile stores as 16-bit PCM): pcm[i] = saturate_int16(lrint(wave[i] * 32767)), NaN -> 0.  Runs on
  * the concatenated batch so the device-to-host copy carries 2 bytes per sample. */

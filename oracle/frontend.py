@@ -124,10 +124,44 @@ def utterance_cmvn(x, norm_means=True, norm_vars=True):
     return x
 
 
+def resize_rows_linear(src, dst_h, ipp=True):
+    """cv2.resize(src, dsize=(src.shape[1], dst_h), interpolation=cv2.INTER_LINEAR) for float32 input (third-party:
+    OpenCV 4.x, what specaugment.py:104-107 calls).  The width is unchanged, so the horizontal pass is the identity and
+    every output row blends two source rows.  Two arithmetics exist in the field and both are pinned by fixtures
+    (tests/golden/specaug_warp.npz, made with cv2 4.13):
+      ipp=False  OpenCV's own code (imgproc/resize.cpp, cv2.ipp.setUseIPP(False) or a build without IPP):
+                 fy = (float)((dy + 0.5) * scale - 0.5) with scale = 1 / (dst_h / src_h) in double, sy = floor(fy), float
+                 weights (1 - fy, fy), dst = S0 * b0 + S1 * b1 with both products rounded (baseline SSE, no FMA);
+      ipp=True   the x86-64 opencv-python wheels (IPP on by default -- what the reference gets from pip): source
+                 position in double, weight rounded to float, dst = fma(S1 - S0, w, S0).  IPP is closed source; this
+                 form was found by search and is bit-exact on every fixture.
+    Source rows are clamped to the image in both."""
+    src = np.asarray(src, np.float32)
+    src_h = src.shape[0]
+    out = np.empty((dst_h, src.shape[1]), np.float32)
+    scale = 1.0 / (float(dst_h) / float(src_h))
+    for dy in range(dst_h):
+        if ipp:
+            pos = (dy + 0.5) * (float(src_h) / float(dst_h)) - 0.5
+            sy = int(np.floor(pos))
+            w = np.float32(pos - sy)
+        else:
+            fy = np.float32((dy + 0.5) * scale - 0.5)
+            sy = int(np.floor(fy))
+            w = np.float32(fy - np.float32(sy))
+        s0, s1 = min(max(sy, 0), src_h - 1), min(max(sy + 1, 0), src_h - 1)
+        if ipp:
+            d = src[s1] - src[s0]
+            out[dy] = (d.astype(np.float64) * np.float64(w) + src[s0].astype(np.float64)).astype(np.float32)
+        else:
+            out[dy] = src[s0] * (np.float32(1.0) - w) + src[s1] * w
+    return out
+
+
 def specaugment(spectrogram, freq_mask_n=0, freq_mask_f=0, time_mask_n=0, time_mask_t=0, time_mask_p=0.0,
-                mask_value=0.0):
-    """feature_transforms/specaugment.py:79-131 without time warping (time_warp_W = 0): same RNG call sequence on
-    numpy's global generator."""
+                mask_value=0.0, time_warp_w=0, ipp=True):
+    """feature_transforms/specaugment.py:79-131: same RNG call sequence on numpy's global generator; the time warp
+    (:96-110) uses the restatement of OpenCV's linear resize above."""
     import math
     distorted = spectrogram.copy()
     num_frames, num_freqs = spectrogram.shape
@@ -135,6 +169,11 @@ def specaugment(spectrogram, freq_mask_n=0, freq_mask_f=0, time_mask_n=0, time_m
         mask_value = spectrogram.mean()
     if num_frames == 0 or num_freqs < freq_mask_f:
         return spectrogram
+    if time_warp_w > 0 and 2 * time_warp_w < num_frames:
+        w0 = np.random.randint(time_warp_w, num_frames - time_warp_w)
+        w = np.random.randint(-time_warp_w + 1, time_warp_w)
+        distorted = np.concatenate((resize_rows_linear(distorted[:w0], w0 + w, ipp),
+                                    resize_rows_linear(distorted[w0:], num_frames - w0 - w, ipp)), axis=0)
     for _ in range(freq_mask_n):
         f = np.random.randint(0, freq_mask_f)
         f0 = np.random.randint(0, num_freqs - f)

@@ -950,6 +950,16 @@ int s2st_rms_dist(int m, int n, int d, const float* x1_dev, const float* x2_dev,
     return launch_rms_dist(m, n, d, x1_dev, x2_dev, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int s2st_time_warp(int n_utts, int64_t total_rows, const int32_t* frame_offsets_dev, int n_cols, const int32_t* warp_dev,
+                   int arithmetic, const float* x_dev, float* out_dev, void* stream) {
+    if (n_utts < 0 || total_rows < 0 || n_cols <= 0 || x_dev == out_dev || (arithmetic != 0 && arithmetic != 1) ||
+        (n_utts > 0 && (!frame_offsets_dev || !warp_dev || !x_dev || !out_dev))) {
+        set_error("bad argument to s2st_time_warp (in place is not supported)");
+        return S2ST_EINVAL;
+    }
+    return launch_time_warp(n_utts, total_rows, frame_offsets_dev, n_cols, warp_dev, arithmetic, x_dev, out_dev, static_cast<cudaStream_t>(stream));
+}
+
 int s2st_wave_to_pcm16(int64_t n_samples, const float* wave_dev, int16_t* pcm_out_dev, void* stream) {
     if (n_samples < 0 || (n_samples > 0 && (!wave_dev || !pcm_out_dev))) {
         set_error("bad argument to s2st_wave_to_pcm16");

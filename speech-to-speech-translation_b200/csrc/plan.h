@@ -130,6 +130,8 @@ int launch_utterance_sums(int n_utts, const int32_t* fo, int n_cols, const float
 int launch_utterance_sum(int n_utts, const int32_t* fo, int n_cols, const float* x, double* sums, cudaStream_t stream);
 int launch_fill_rects(int n_rects, const int32_t* rects, const float* values, int n_cols, float* x, cudaStream_t stream);
 
+int launch_time_warp(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const int32_t* warp, int arithmetic,
+                     const float* x, float* out, cudaStream_t stream);
 int launch_wave_to_pcm16(long long n, const float* x, short* out, cudaStream_t stream);
 
 // dtw_kernels.cu

@@ -145,6 +145,64 @@ __global__ void __launch_bounds__(256) k_fill_rects(const int4* __restrict__ rec
     }
 }
 
+// SpecAugment time warping (feature_transforms/specaugment.py:96-110): the rows [0, w0) of an utterance are resized to
+// w0 + w rows and the rows [w0, T) to T - w0 - w rows with cv2.resize(..., INTER_LINEAR) -- the width stays, so the
+// horizontal pass is the identity and every output row is a blend of two source rows (clamped to the part).
+//   IPP = false  OpenCV's own float32 resize: position fy = (float)((dy + 0.5) * scale - 0.5) with scale = 1 / (dst_h /
+//                src_h) in double, sy = floor(fy), weights (1 - fy, fy) in float, dst = S0 * b0 + S1 * b1 (two rounded
+//                products: the baseline-SSE build has no FMA);
+//   IPP = true   the x86-64 opencv-python wheels (IPP on): position in double, weight rounded to float,
+//                dst = fma(S1 - S0, w, S0).
+// warp[u] = (w0, w); w0 < 0: the utterance is copied.  One thread per (row, column); HBM-bound (4 B in + 4 B out, the
+// second source row comes from L1/L2).
+template <bool IPP>
+__global__ void __launch_bounds__(256) k_time_warp(const int32_t* __restrict__ fo, int n_utts, long long n_rows, int n_cols,
+                                                    const int2* __restrict__ warp, const float* __restrict__ x,
+                                                    float* __restrict__ out) {
+    const long long total = n_rows * n_cols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long row = idx / n_cols;
+        const int c = (int)(idx - row * n_cols);
+        int lo = 0, hi = n_utts - 1;  // last u with fo[u] <= row
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (fo[mid] <= row) lo = mid; else hi = mid - 1;
+        }
+        const int r0 = fo[lo], T = fo[lo + 1] - r0;
+        const int2 wp = warp[lo];
+        const int i = (int)(row - r0);
+        float v;
+        if (wp.x < 0) {
+            v = x[idx];
+        } else {
+            const int w0 = wp.x, w = wp.y;
+            int src0, src_h, dst_h, dy;
+            if (i < w0 + w) {
+                src0 = 0, src_h = w0, dst_h = w0 + w, dy = i;
+            } else {
+                src0 = w0, src_h = T - w0, dst_h = T - w0 - w, dy = i - (w0 + w);
+            }
+            int sy;
+            float fy;
+            if (IPP) {
+                const double pos = __dsub_rn(__dmul_rn(dy + 0.5, (double)src_h / (double)dst_h), 0.5);
+                const double fl = floor(pos);
+                sy = (int)fl;
+                fy = (float)(pos - fl);
+            } else {
+                const double scale = 1.0 / ((double)dst_h / (double)src_h);  // OpenCV: scale_y = 1. / inv_scale_y
+                fy = (float)__dsub_rn(__dmul_rn(dy + 0.5, scale), 0.5);
+                sy = (int)floorf(fy);
+                fy -= (float)sy;
+            }
+            const int s0 = min(max(sy, 0), src_h - 1), s1 = min(max(sy + 1, 0), src_h - 1);
+            const float a = x[(size_t)(r0 + src0 + s0) * n_cols + c], b = x[(size_t)(r0 + src0 + s1) * n_cols + c];
+            v = IPP ? fmaf(__fsub_rn(b, a), fy, a) : __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, fy)), __fmul_rn(b, fy));
+        }
+        out[idx] = v;
+    }
+}
+
 // Waveform post-processing of generate_waveform.py:115-124 (soundfile writes float data to a WAV / FLAC file as 16-bit
 // PCM): sample = lrint(x * 32767) like libsndfile's float -> short conversion, saturated to the int16 range.  Done on
 // the device for the whole batch so the download is 2 bytes per sample instead of 4.  HBM-bound: 4 B in + 2 B out.
@@ -172,6 +230,19 @@ __global__ void __launch_bounds__(256) k_wave_to_pcm16(long long n, const float*
 }
 
 }  // namespace
+
+int launch_time_warp(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const int32_t* warp, int arithmetic,
+                     const float* x, float* out, cudaStream_t stream) {
+    if (n_utts <= 0 || n_rows <= 0) return S2ST_OK;
+    const long long total = n_rows * n_cols;
+    const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+    if (arithmetic)
+        k_time_warp<true><<<grid, 256, 0, stream>>>(fo, n_utts, n_rows, n_cols, reinterpret_cast<const int2*>(warp), x, out);
+    else
+        k_time_warp<false><<<grid, 256, 0, stream>>>(fo, n_utts, n_rows, n_cols, reinterpret_cast<const int2*>(warp), x, out);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
 
 int launch_wave_to_pcm16(long long n, const float* x, short* out, cudaStream_t stream) {
     if (n <= 0) return S2ST_OK;

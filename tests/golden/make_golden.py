@@ -24,6 +24,7 @@ Outputs (float32 unless noted), all produced by reference code:
   cmvn.npz         features, stats, GlobalCMVN output, gcmvn_denormalize output
   wss.npz          GriffinLim.get_window_sum_square for a few frame counts
   logmel_default.npz  log-mel with the reference's default geometry (n_fft 1024) and an n_fft 512 STFT with phase
+  specaug_warp.npz  SpecAugmentTransform with time_warp_W > 0 (OpenCV) on seeded inputs
   gcmvn_stats.npz  get_global_cmvn (examples/speech_synthesis/data_utils.py:190-220) run on a directory of .npy
                    feature files: the files' seeds / shapes, the order Path.glob returned them in, mean and std
 
@@ -171,9 +172,37 @@ def make_logmel_default():
     np.savez_compressed(os.path.join(HERE, "logmel_default.npz"), **out)
 
 
+def make_specaug_warp():
+    """SpecAugmentTransform with time warping (specaugment.py:96-110; needs OpenCV, present in the build container):
+    the reference class on seeded inputs, several (T, W) incl. a spectrogram too short to be warped."""
+    import cv2
+    _, _, ft = load_reference()
+    reg = ft.AUDIO_FEATURE_TRANSFORM_REGISTRY
+    out = {}
+    rng = np.random.RandomState(21)
+    cases = {"w5": ({"time_warp_W": 5, "freq_mask_N": 1, "freq_mask_F": 10, "time_mask_N": 1, "time_mask_T": 20, "time_mask_p": 0.3}, (40, 333)),
+             "w40": ({"time_warp_W": 40, "freq_mask_N": 2, "freq_mask_F": 27, "time_mask_N": 2, "time_mask_T": 100, "time_mask_p": 1.0,
+                      "mask_value": 0.0}, (81, 250, 1203, 60)),
+             "wonly": ({"time_warp_W": 8}, (17, 100))}
+    for cname, (cfg, lengths) in cases.items():
+        t = reg["specaugment"].from_config_dict(cfg)
+        for T in lengths:
+            x = (rng.randn(T, 80) * 2 - 4).astype(np.float32)
+            out[f"{cname}_{T}_x"] = x
+            for tag, use_ipp in (("y", True), ("y_noipp", False)):  # the pip wheel's default (IPP) / OpenCV's own code
+                cv2.ipp.setUseIPP(use_ipp)
+                np.random.seed(2000 + T)
+                out[f"{cname}_{T}_{tag}"] = t(x)
+    cv2.ipp.setUseIPP(True)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(HERE, "specaug_warp.npz"), **out)
+    print("specaug warp ok", len(out))
+
+
 def main():
     if "--only" in sys.argv:
-        {"gcmvn": make_gcmvn, "logmel_default": make_logmel_default}[sys.argv[sys.argv.index("--only") + 1]]()
+        {"gcmvn": make_gcmvn, "logmel_default": make_logmel_default,
+         "specaug_warp": make_specaug_warp}[sys.argv[sys.argv.index("--only") + 1]]()
         return
     torch.set_num_threads(os.cpu_count())
     au, voc_mod, ft = load_reference()
@@ -336,6 +365,7 @@ def main():
     dt.update(mcd_ya0=ya[0].numpy(), mcd_ya1=ya[1].numpy(), mcd_yb0=yb[0].numpy(), mcd_yb1=yb[1].numpy())
     make_gcmvn()
     make_logmel_default()
+    make_specaug_warp()
     np.savez_compressed(os.path.join(HERE, "dtw.npz"), **dt)
     print("dtw ok", {k: v.shape for k, v in dt.items() if k.startswith("mcd_") and v.ndim == 1 and v.size == 2})
 

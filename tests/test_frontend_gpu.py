@@ -371,8 +371,35 @@ def test_specaugment_matches_reference(pkg, built_lib):
     tr = ft.get_audio_feature_transform("specaugment").from_config_dict({"freq_mask_N": 1, "freq_mask_F": 100})
     x = np.ones((5, 80), np.float32)
     assert tr(x) is x
-    with pytest.raises(NotImplementedError):
-        ft.get_audio_feature_transform("specaugment").from_config_dict({"time_warp_W": 5})(np.ones((50, 80), np.float32))
+
+
+def test_specaugment_time_warp_bit_exact(pkg, built_lib):
+    """SpecAugment with time_warp_W > 0 (specaugment.py:96-110, cv2.resize INTER_LINEAR) against fixtures produced by
+    the reference class with OpenCV 4.13: bit-exact for both arithmetics in the field (IPP on = the pip wheel's
+    default, IPP off = OpenCV's own code), including a spectrogram too short to warp, then a ragged batch."""
+    from test_oracle_golden import WARP_CASES as _WARP_CASES
+    ft = pkg.feature_transforms
+    g = load_golden("specaug_warp.npz")
+    for cname, (cfg, lengths) in _WARP_CASES.items():
+        for arith, tag in (("ipp", "y"), ("opencv", "y_noipp")):
+            tr = ft.get_audio_feature_transform("specaugment").from_config_dict(cfg)
+            tr.resize_arithmetic = arith
+            for T in lengths:
+                np.random.seed(2000 + T)
+                y = tr(g[f"{cname}_{T}_x"])
+                ref = g[f"{cname}_{T}_{tag}"]
+                if cfg.get("mask_value", None) is None and "freq_mask_N" in cfg:   # local-mean mask value: 1e-6 relative
+                    assert np.allclose(y, ref, rtol=2e-6, atol=0), (cname, T, arith)
+                else:
+                    assert np.array_equal(y, ref), (cname, T, arith, np.abs(y - ref).max())
+    cfg, lengths = _WARP_CASES["w40"]
+    tr = ft.get_audio_feature_transform("specaugment").from_config_dict(cfg)
+    xs = [g[f"w40_{T}_x"] for T in lengths]
+    np.random.seed(5)
+    singles = [tr(x) for x in xs]
+    np.random.seed(5)
+    yb = tr.apply_cuda(torch.from_numpy(np.concatenate(xs)).cuda(), list(lengths)).cpu().numpy()
+    assert np.array_equal(yb, np.concatenate(singles))
 
 
 def test_dtw_bit_exact_and_mcd_metric(pkg, built_lib):

@@ -180,6 +180,30 @@ def test_specaugment_matches_reference_bit_exact():
             assert (y != x).any() or cname == "zero" or T < 20
 
 
+WARP_CASES = {"w5": ({"time_warp_W": 5, "freq_mask_N": 1, "freq_mask_F": 10, "time_mask_N": 1, "time_mask_T": 20, "time_mask_p": 0.3},
+                      (40, 333)),
+               "w40": ({"time_warp_W": 40, "freq_mask_N": 2, "freq_mask_F": 27, "time_mask_N": 2, "time_mask_T": 100,
+                        "time_mask_p": 1.0, "mask_value": 0.0}, (81, 250, 1203, 60)),
+               "wonly": ({"time_warp_W": 8}, (17, 100))}
+
+
+def test_specaugment_time_warp_oracle_bit_exact():
+    """The restated cv2.resize (oracle/frontend.py:resize_rows_linear) inside SpecAugment's time warp
+    (specaugment.py:96-110) against the reference class's outputs, for both arithmetics (IPP on / off)."""
+    g = load_golden("specaug_warp.npz")
+    keys = {"time_warp_W": "time_warp_w", "freq_mask_N": "freq_mask_n", "freq_mask_F": "freq_mask_f", "time_mask_N": "time_mask_n",
+            "time_mask_T": "time_mask_t", "time_mask_p": "time_mask_p", "mask_value": "mask_value"}
+    for cname, (cfg, lengths) in WARP_CASES.items():
+        kw = {keys[k]: v for k, v in cfg.items()}
+        kw.setdefault("mask_value", None)
+        for T in lengths:
+            for tag, ipp in (("y", True), ("y_noipp", False)):
+                np.random.seed(2000 + T)
+                y = fe.specaugment(g[f"{cname}_{T}_x"], ipp=ipp, **kw)
+                assert np.array_equal(y, g[f"{cname}_{T}_{tag}"]), (cname, T, tag)
+    assert np.abs(g["w40_1203_y"] - g["w40_1203_y_noipp"]).max() > 1e-5   # the two arithmetics really differ
+
+
 def test_conv_formulation_reproduces_reference_bit_for_bit(golden_basis):
     """oracle/conv_formulation.py is the reference's own dense-convolution formulation: same torch ops in the same
     order, so the golden waveforms come back exactly; and it pins the FFT oracle from a second, independent side."""
