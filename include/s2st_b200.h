@@ -75,6 +75,10 @@ int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
                                        of up to ~590 frames) spreads the frames of a strip over a team of four warps that
                                        overlap-add in frame order: bitwise identical results, 22 % less latency.
                                        0: always one warp per strip */
+#define S2ST_OPT_GL_FRAMES 7        /* [S2ST_GL_FRAMES=0 | N] 1 (default): synthesis calls of a few thousand frames (one utterance, a small
+                                       batch) run ALL iterations in one launch with a warp per frame, overlap-add gathered from
+                                       the neighbours' frames; bitwise equal to one strip per utterance, independent of the batch.
+                                       0: always the strip kernels; N > 1: the frame-parallel kernel for calls of up to N frames */
 #define S2ST_OPT_INVERSE_MEL 4      /* [S2ST_INVERSE_MEL=simt] 0 (default): tcgen05 tensor-core inverse-mel; 1: FP32 SIMT kernel */
 #define S2ST_OPT_FRONTEND_GENERIC 5 /* [S2ST_LOGMEL_GENERIC / S2ST_FBANK_GENERIC] 0 (default): register-resident log-mel / fbank
                                        kernels where they apply; 1: always the generic kernels */

@@ -154,6 +154,9 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
         p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == 'a') ? -1 : 0;
         e = getenv("S2ST_GL_PDL");
         p->opt_pdl = !(e && e[0] == '0');
+        e = getenv("S2ST_GL_FRAMES");  // 0 = never the frame-parallel kernel, N > 1 = up to N frames
+        p->opt_frames = !(e && e[0] == '0');
+        p->opt_frames_max = (e && atoi(e) > 1) ? atoi(e) : 16 * 148 * 4;
         e = getenv("S2ST_GL_TEAM");
         p->opt_team = !(e && e[0] == '0');
         e = getenv("S2ST_INVERSE_MEL");
@@ -410,6 +413,11 @@ int s2st_plan_set_option(s2st_plan* plan, int option, int value) {
             return S2ST_OK;
         case S2ST_OPT_GL_PDL:
             plan->opt_pdl = value != 0;
+            return S2ST_OK;
+        case S2ST_OPT_GL_FRAMES:
+            if (value < 0) break;
+            plan->opt_frames = value != 0;
+            if (value > 1) plan->opt_frames_max = value;
             return S2ST_OK;
         case S2ST_OPT_GL_TEAM:
             plan->opt_team = value != 0;

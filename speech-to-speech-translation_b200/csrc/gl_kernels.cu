@@ -20,6 +20,9 @@
 // bitwise deterministic.  Three waveform buffers rotate: pass i reads buf[(i-1)%3], writes buf[i%3]
 // and zeroes the seams of buf[(i+1)%3] for the next pass.
 #include <math_constants.h>
+#ifdef S2ST_FRAMES_PROF
+#include <cstdio>
+#endif
 
 #include "../../include/s2st_b200.h"
 #include "frame_fft.cuh"
@@ -709,9 +712,18 @@ __global__ void __launch_bounds__(256) k_phase_from_uniform(const double* __rest
     }
 }
 
+#include "gl_frames.cuh"
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// The frame-parallel path keeps two raw synthesis frames per frame in the workspace (9.7 KB): only calls of up to this
+// many frames carry that space (and can take the path).
+constexpr long long kFramesPathMax = 16 * 148 * 4;
+
 struct GlWorkspace {
+    int4* frames;    // frame-parallel path: (T, f, utterance) per frame, or NULL
+    float* y[2];     //                      raw synthesis frames, with guard rows
+    int* fdone;      //                      last published iteration + 1 per frame
     UttDesc* utts;
     TileDesc* tiles;
     TileDesc* tiles_tmp;
@@ -747,6 +759,15 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
     w.mag = reinterpret_cast<float*>(take(sizeof(float) * (size_t)total_frames * w.mag_stride));
     for (int i = 0; i < 2; ++i)
         w.buf[i] = reinterpret_cast<float*>(take(sizeof(float) * (size_t)(w.wave_samples > 0 ? w.wave_samples : 1)));
+    w.frames = nullptr;
+    w.y[0] = w.y[1] = nullptr;
+    w.fdone = nullptr;
+    if (total_frames <= kFramesPathMax) {
+        const size_t rows = (size_t)total_frames + 2 * kFrGuard * (size_t)n_utts + 2;
+        w.frames = reinterpret_cast<int4*>(take(sizeof(int4) * (size_t)total_frames));
+        w.fdone = reinterpret_cast<int*>(take(sizeof(int) * (size_t)total_frames));
+        for (int i = 0; i < 2; ++i) w.y[i] = reinterpret_cast<float*>(take(sizeof(float) * rows * kFrPitch));
+    }
     w.total = off;
     return w;
 }
@@ -803,6 +824,27 @@ int allow_dynamic_smem(size_t smem, int device) {
         S2ST_CUDA_CHECK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (device >= 0 && device < 64) granted[device] = smem;
     }
+    return S2ST_OK;
+}
+
+// Frame-parallel path: one cooperative launch for the whole call (gl_frames.cuh).  Returns S2ST_OK with *launched = false
+// when the launch is refused (not co-resident): the caller then runs the strip kernels.
+template <int WARPS>
+int launch_frames_t(const FrameGlParams& fp, int device, int grid, cudaStream_t stream, bool* launched) {
+    const size_t smem = sizeof(float2) * 2048 + sizeof(float) * (64 * 19 + kStdWs + kStdHop + 2 * (kStdWs - kStdHop) + WARPS * kScratchFloats);
+    if (int rc = allow_dynamic_smem<k_gl_frames<WARPS>>(smem, device)) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(32 * WARPS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // every warp must be resident: frames wait for their neighbours
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    *launched = cudaLaunchKernelEx(&cfg, k_gl_frames<WARPS>, fp) == cudaSuccess;
+    if (!*launched) (void)cudaGetLastError();
     return S2ST_OK;
 }
 
@@ -897,8 +939,6 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
     const int s_floor = plan->nphase > kMinStrip ? plan->nphase : kMinStrip;
     const int S = plan->strip_frames > 0 ? (plan->strip_frames < s_floor ? s_floor : plan->strip_frames)
                                          : choose_strip(plan, n_utts, total_frames, frame_offsets_host);
-    k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, S, w.utts, w.tiles_tmp, w.tiles, w.tile_pos, w.n_tiles);
-    S2ST_CUDA_CHECK(cudaGetLastError());
 
     GlParams p;
     p.device = plan->device;
@@ -941,12 +981,65 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
     ring[n_iter % 3] = wave_out;
     ring[(n_iter + 1) % 3] = w.buf[0];
     ring[(n_iter + 2) % 3] = w.buf[1];
-    // pass 0 accumulates its seams into ring[0]: clear it (later passes get theirs cleared by the pass before)
-    S2ST_CUDA_CHECK(cudaMemsetAsync(ring[0], 0, sizeof(float) * (size_t)w.wave_samples, stream));
     // Persistent mode (see k_gl_pass PERSIST): all iterations in one cooperative launch when every strip gets a
     // resident warp of its own.  Needs the exact strip count, i.e. the host copy of the frame offsets.
     const bool std_geom0 = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                            plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
+    // Calls that fit (a few frames per resident warp): the frame-parallel kernel, all iterations in one launch.
+    // A pinned strip length (s2st_plan_set_strip_frames) asks for the strip decomposition and keeps it.
+    if (std_geom0 && plan->opt_frames != 0 && plan->strip_frames == 0 && w.frames && n_iter >= 0 &&
+        total_frames <= (long long)plan->opt_frames_max) {
+        const int blocks = (int)min((long long)148 * 4, (total_frames + 255) / 256);
+        k_build_frames<<<blocks, 256, 0, stream>>>(frame_offsets, n_utts, (int)total_frames, w.frames, w.y[0], w.y[1], w.fdone);
+        S2ST_CUDA_CHECK(cudaGetLastError());
+        FrameGlParams fp;
+        fp.win_a = plan->win_a;
+        fp.w2 = plan->w2;
+        fp.inv_wss = plan->inv_wss;
+        fp.inv_nfft = p.inv_nfft;
+        fp.tw = plan->tw;
+        fp.vtab = plan->vtab;
+        fp.rot = plan->rot;
+        fp.frames = w.frames;
+        fp.n_frames = (int)total_frames;
+        fp.n_iter = n_iter;
+        fp.mag = p.mag;
+        fp.mag_stride = p.mag_stride;
+        fp.kb = p.kb;
+        fp.phase = phase;
+        fp.phase_stride = kBins;
+        fp.phase_seed = phase_seed;
+        fp.Y[0] = w.y[0];
+        fp.Y[1] = w.y[1];
+        fp.done = w.fdone;
+        fp.out = wave_out;
+        const int fgrid = (int)min((long long)plan->num_sms, total_frames);
+        const long long per_cta = (total_frames + fgrid - 1) / fgrid;
+        bool launched = false;
+        if (timed) {
+            if (!plan->timing_events[0]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[0]));
+            S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[0], stream));
+        }
+        int rc = per_cta <= 1 ? launch_frames_t<1>(fp, plan->device, fgrid, stream, &launched)
+               : per_cta <= 2 ? launch_frames_t<2>(fp, plan->device, fgrid, stream, &launched)
+               : per_cta <= 4 ? launch_frames_t<4>(fp, plan->device, fgrid, stream, &launched)
+               : per_cta <= 8 ? launch_frames_t<8>(fp, plan->device, fgrid, stream, &launched)
+                              : launch_frames_t<16>(fp, plan->device, fgrid, stream, &launched);
+        if (rc != S2ST_OK) return rc;
+        if (launched) {
+            plan->last_launches = (logmel ? 1 : 0) + 2;  // [inverse_mel], build_frames, the frame kernel
+            if (timed) {
+                if (!plan->timing_events[1]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[1]));
+                S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[1], stream));
+                plan->timing_recorded = 2;
+            }
+            return S2ST_OK;
+        }
+    }
+    k_build_tiles<<<1, 1024, 0, stream>>>(frame_offsets, n_utts, plan->hop, S, w.utts, w.tiles_tmp, w.tiles, w.tile_pos, w.n_tiles);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    // pass 0 accumulates its seams into ring[0]: clear it (later passes get theirs cleared by the pass before)
+    S2ST_CUDA_CHECK(cudaMemsetAsync(ring[0], 0, sizeof(float) * (size_t)w.wave_samples, stream));
     const int pmode = plan->opt_persistent;
     bool persist = std_geom0 && n_iter >= 1 && frame_offsets_host && pmode != 0;
     plan->last_launches = 1 + (logmel ? 1 : 0) + (n_iter + 1);  // build_tiles, [inverse_mel], the passes

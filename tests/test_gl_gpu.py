@@ -207,6 +207,7 @@ def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
     for strip in (0, 7):
         plan.set_strip_frames(strip)
         try:
+            plan.set_option(pkg._lib.OPT_GL_FRAMES, 0)  # this test is about the strip kernels
             plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 0)
             base = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
             assert plan.gl_launch_count(12) == 2 + 13  # build_tiles, inverse_mel, 13 passes
@@ -216,6 +217,7 @@ def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
         finally:
             plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 0)
             plan.set_strip_frames(0)
+            plan.set_option(pkg._lib.OPT_GL_FRAMES, 1)
         for a, b in zip(base, pers):
             assert torch.equal(a, b)
 
@@ -226,6 +228,7 @@ def test_team_mode_is_bitwise_identical(pkg, voc, basis):
     single utterances of every tail shape, ragged small batches, the initial inverse alone, and pinned strip lengths."""
     plan = voc._plan(torch.device("cuda", 0))
     cases = [[5], [6], [7], [8], [9], [37], [500], [5, 9, 31, 64, 65, 100, 257, 400], [56] * 30]
+    plan.set_option(pkg._lib.OPT_GL_FRAMES, 0)  # this test is about the strip kernels
     try:
         for strip in (0, 7):
             plan.set_strip_frames(strip)
@@ -247,8 +250,62 @@ def test_team_mode_is_bitwise_identical(pkg, voc, basis):
         assert torch.equal(a, voc.synthesize_flat(x, [300], None, n_iter=3, seed=11))
     finally:
         plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
+        plan.set_option(pkg._lib.OPT_GL_FRAMES, 1)
         plan.set_strip_frames(0)
     ref = ogl.vocoder_forward(synth_logmel(37, 905, "smooth").numpy(), seeded_phase(955, 37), 5, basis=basis)
+
+
+def test_frame_parallel_path_equals_one_strip_per_utterance(pkg, voc, basis):
+    """Calls that fit the resident warps run k_gl_frames (gl_frames.cuh): all iterations in one cooperative launch, a warp
+    per frame, the overlap-add gathered from the neighbours' raw frames in frame order -- the same additions in the same
+    order as the strip kernel's ring when ONE strip covers the utterance.  The two kernels are compiled separately, and
+    ptxas (12.9) fuses mul.rn.f32x2 + add.rn.f32x2 pairs into FFMA2 as it sees fit (even with --fmad=false), so the
+    transforms round differently in the last bit: equal to rounding noise (measured up to 5e-6 after 6 iterations, which amplify it),
+    not bitwise.  Covered: every edge shape (T = 5 ... 12: both reflect paddings and clipped window sums interact), ragged
+    batches, several frames per warp (> 2368 frames), the initial inverse alone, the device-drawn phase; the path is
+    deterministic and independent of the batch (bitwise); and it is within tolerance of the oracle."""
+    plan = voc._plan(torch.device("cuda", 0))
+    cases = [[T] for T in (5, 6, 7, 8, 9, 10, 11, 12, 37, 500)] + [[5, 9, 31, 64, 65, 100, 257, 400], [56] * 30, [230] * 12, [1500, 1300]]
+    worst = 0.0
+    try:
+        for ci, frames in enumerate(cases):
+            feats = [synth_logmel(T, 1900 + i, "smooth" if i % 2 else "iid").cuda() for i, T in enumerate(frames)]
+            phases = [seeded_phase(1950 + i, T) for i, T in enumerate(frames)]
+            for n_iter in (0, 1, 6):
+                plan.set_strip_frames(max(frames))
+                base = voc.synthesize_batch(feats, init_phase=phases, n_iter=n_iter)
+                assert plan.gl_launch_count(n_iter) == 2 + n_iter + 1
+                plan.set_strip_frames(0)
+                fr = voc.synthesize_batch(feats, init_phase=phases, n_iter=n_iter)
+                assert plan.gl_launch_count(n_iter) == 3  # inverse_mel, build_frames, the frame kernel
+                for a, b in zip(base, fr):
+                    err = ogl.rel_l2(b.cpu().numpy(), a.cpu().numpy())
+                    worst = max(worst, err)
+                    assert err < (1e-6 if n_iter <= 1 else 2e-5), (frames, n_iter, err)
+                again = voc.synthesize_batch(feats, init_phase=phases, n_iter=n_iter)
+                assert all(torch.equal(a, b) for a, b in zip(fr, again))  # deterministic
+            if ci == 10:  # batch independence: an utterance alone equals the same utterance inside the batch, bitwise
+                alone = voc.synthesize_batch([feats[7]], init_phase=[phases[7]], n_iter=6)[0]
+                assert torch.equal(alone, fr[7])
+        x = synth_logmel(300, 1).cuda()
+        plan.set_strip_frames(300)
+        a = voc.synthesize_flat(x, [300], None, n_iter=3, seed=11)
+        plan.set_strip_frames(0)
+        assert ogl.rel_l2(voc.synthesize_flat(x, [300], None, n_iter=3, seed=11).cpu().numpy(), a.cpu().numpy()) < 5e-6
+        # the option switches the path off / bounds it
+        plan.set_option(pkg._lib.OPT_GL_FRAMES, 0)
+        voc.synthesize_flat(x, [300], None, n_iter=3, seed=11)
+        assert plan.gl_launch_count(3) == 2 + 4
+        plan.set_option(pkg._lib.OPT_GL_FRAMES, 299)
+        voc.synthesize_flat(x, [300], None, n_iter=3, seed=11)
+        assert plan.gl_launch_count(3) == 2 + 4
+    finally:
+        plan.set_strip_frames(0)
+        plan.set_option(pkg._lib.OPT_GL_FRAMES, 16 * 148 * 4)
+    print("frame-parallel vs one strip per utterance: worst rel-L2", worst)
+    xs, ph = synth_logmel(37, 905, "smooth"), seeded_phase(955, 37)
+    y = voc.synthesize_batch([xs.cuda()], init_phase=[ph], n_iter=16)[0].cpu().numpy()
+    assert ogl.rel_l2(y, ogl.vocoder_forward(xs.numpy(), ph, 16, basis=basis)) < 1e-3
 
 
 def test_config1_500_frames_64_iters(pkg, voc, basis):
