@@ -135,6 +135,15 @@ int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int
 int s2st_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double* uniform_dev, float* phase_out_dev,
                             void* stream);
 
+/* The same initial phase with numpy's generator CONTINUED ON THE DEVICE: the host shim passes numpy's legacy global state
+ * (np.random.get_state(): MT19937 key[624] + position), this entry produces the next 2 * n_batch * n_bins * n_frames
+ * 32-bit outputs (what np.random.rand(*shape) consumes, randomkit's rk_double), the phase they give, and the key numpy
+ * would hold afterwards (new position = pos + 2 n - 624 * max((pos + 2 n - 1) / 624, 0)); the shim puts it back with
+ * np.random.set_state.  Bit-for-bit numpy's stream, without the host draw and the 8 B / element upload.
+ *   key_dev [624] uint32; words_ws_dev scratch [2 * n] uint32 (8-byte aligned); key_out_dev [624] uint32 */
+int s2st_phase_from_mt19937(int n_batch, int n_bins, int n_frames, const uint32_t* key_dev, int pos, uint32_t* words_ws_dev,
+                            float* phase_out_dev, uint32_t* key_out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* building blocks (test surface + the reference's public sub-modules)                         */
 

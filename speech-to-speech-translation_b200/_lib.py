@@ -41,6 +41,8 @@ SIGNATURES = {
     "s2st_fbank_plan_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "s2st_phase_from_uniform": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p]),
+    "s2st_phase_from_mt19937": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "s2st_plan_set_pass_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "s2st_plan_get_pass_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_int)]),

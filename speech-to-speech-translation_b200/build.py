@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libs2st_b200.so")
-SOURCES = ["api.cu", "gl_kernels.cu", "frontend_kernels.cu", "mel_tc.cu", "transform_kernels.cu", "dtw_kernels.cu"]
+SOURCES = ["api.cu", "gl_kernels.cu", "frontend_kernels.cu", "mel_tc.cu", "transform_kernels.cu", "dtw_kernels.cu", "rng_kernels.cu"]
 HEADERS = ["common.cuh", "plan.h", "fft32.cuh", "frame_fft.cuh", "gl_frames.cuh", os.path.join("..", "..", "include", "s2st_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--shared", "-Xcompiler", "-fPIC"]

@@ -498,6 +498,18 @@ int s2st_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double*
     return launch_phase_from_uniform(n_batch, n_bins, n_frames, uniform_dev, phase_out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int s2st_phase_from_mt19937(int n_batch, int n_bins, int n_frames, const uint32_t* key_dev, int pos, uint32_t* words_ws_dev,
+                            float* phase_out_dev, uint32_t* key_out_dev, void* stream) {
+    const long long n = (long long)n_batch * n_bins * n_frames;
+    if (n_batch < 0 || n_bins < 0 || n_frames < 0 || pos < 0 || pos > 624 || !key_dev || !key_out_dev ||
+        (n > 0 && (!words_ws_dev || !phase_out_dev)) || (reinterpret_cast<uintptr_t>(words_ws_dev) & 7)) {
+        set_error("bad argument to s2st_phase_from_mt19937");
+        return S2ST_EINVAL;
+    }
+    return launch_phase_from_mt19937(n_batch, n_bins, n_frames, key_dev, pos, words_ws_dev, phase_out_dev, key_out_dev,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 int s2st_gl_synthesize(s2st_plan* plan, int n_utts, int64_t total_frames,
                        const int32_t* frame_offsets_dev, const int32_t* frame_offsets_host, const float* logmel_dev,
                        const float* mag_dev, const float* init_phase_dev, uint64_t phase_seed, int n_iter,

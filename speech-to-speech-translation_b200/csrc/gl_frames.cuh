@@ -263,36 +263,38 @@ __global__ void __launch_bounds__(32 * WARPS, 1) k_gl_frames(const __grid_consta
                             acc = fma2(swap2(y), w, acc);
                         }
                         const int i = f * HOP + m, e = i - T * HOP;
-                        const float2 x = mul2(acc, *reinterpret_cast<const float2*>(s_inv_head + (i < WS - HOP ? i : e >= 0 ? e + WS : o + (WS - HOP))));
-                        a[brev5(r)] = mul2(x, *reinterpret_cast<const float2*>(s_win + m));
+                        a[brev5(r)] = mul2(acc, *reinterpret_cast<const float2*>(s_inv_head + (i < WS - HOP ? i : e >= 0 ? e + WS : o + (WS - HOP))));
                     }
                     // Reflect padding (audio_utils.py:262-263): the first two and the last two frames of an utterance read
                     // mirrored samples in their first / last rows (frame 0: rows 0-9, frame 1: 0-4, frame T-1: 9-18,
-                    // frame T-2: 14-18).  Those rows are redone sample by sample; the row index is a run-time value so
-                    // that the (branch-free) loads of all ten rows are in flight together, and the rows go through the warp
-                    // scratch (registers cannot be indexed at run time).
-                    const int fix_base = f <= 1 ? 0 : f == T - 1 ? 9 : 14;
-                    const int fix_n = (f == 0 || f == T - 1) ? 10 : (f == 1 || f == T - 2) ? 5 : 0;
-                    if (fix_n > 0) {
-                        float2* stg = reinterpret_cast<float2*>(scratch);  // [row][lane]; every lane reads back its own values
+                    // frame T-2: 14-18).  The mirror image of such a sample is one of the frame's OWN samples -- sample m
+                    // of the frame takes the value of sample c - m with c = 1200, 600, 1198, 1798 -- so the rows are
+                    // exchanged through the warp scratch, no further loads.
+                    const int fix_lo = f <= 1 ? 0 : f == T - 1 ? 9 : 14;
+                    const int fix_hi = f == 0 ? 10 : f == 1 ? 5 : (f >= T - 2 ? NZ : 0);  // rows [fix_lo, fix_hi)
+                    if (fix_hi > fix_lo) {
+                        const int c = f == 0 ? 4 * HOP : f == 1 ? 2 * HOP : f == T - 1 ? 4 * HOP - 2 : 6 * HOP - 2;
+                        float* xs = scratch;  // the frame's samples, linear
 #pragma unroll
-                        for (int k = 0; k < 10; ++k) {
-                            const int r = min(fix_base + k, NZ - 1);
-                            const int j = f * HOP - WS / 2 + 64 * r + 2 * lane;
-                            int j0 = j < 0 ? -j : j, j1 = j + 1 < 0 ? -(j + 1) : j + 1;
-                            j0 = j0 >= L ? 2 * (L - 1) - j0 : j0;
-                            j1 = j1 >= L ? 2 * (L - 1) - j1 : j1;
-                            j0 = min(max(j0, 0), L - 1);  // only reachable where the window is zero
-                            j1 = min(max(j1, 0), L - 1);
-                            stg[32 * r + lane] = mul2(make_float2(sample_at(j0), sample_at(j1)),
-                                                      *reinterpret_cast<const float2*>(s_win + 64 * r + 2 * lane));
+                        for (int r = 0; r < NZ; ++r) *reinterpret_cast<float2*>(xs + 64 * r + 2 * lane) = a[brev5(r)];
+                        __syncwarp();
+#pragma unroll
+                        for (int r = 0; r < NZ; ++r) {
+                            const int m = 64 * r + 2 * lane;
+                            // which samples of the row are mirrored: left edge j < 0 <=> m < 600 - f hop; right edge j >= L
+                            const int j = f * HOP - WS / 2 + m;
+                            if (r >= fix_lo && r < fix_hi) {
+                                const int s0 = min(max(c - m, 0), 64 * NZ - 1), s1 = min(max(c - m - 1, 0), 64 * NZ - 1);
+                                const float x0 = (j < 0 || j >= L) ? xs[s0] : a[brev5(r)].x;
+                                const float x1 = (j + 1 < 0 || j + 1 >= L) ? xs[s1] : a[brev5(r)].y;
+                                a[brev5(r)] = make_float2(x0, x1);
+                            }
                         }
                         __syncwarp();
-#pragma unroll
-                        for (int r = 0; r < NZ; ++r)
-                            if (r >= fix_base && r < fix_base + fix_n) a[brev5(r)] = stg[32 * r + lane];
-                        __syncwarp();
                     }
+#pragma unroll
+                    for (int r = 0; r < NZ; ++r)
+                        a[brev5(r)] = mul2(a[brev5(r)], *reinterpret_cast<const float2*>(s_win + 64 * r + 2 * lane));
                 }
                 float mg[kPrunedRows];
 #pragma unroll
@@ -341,7 +343,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) k_gl_frames(const __grid_consta
 #pragma unroll
             for (int r = 0; r < NZ; ++r) dst[32 * r] = a[r];
             FR_STAMP(5);
-            __threadfence();
+            // publish: the warp barrier orders every lane's stores before lane 0's release (cumulative at gpu scope) -- the
+            // pattern of a cooperative-groups grid barrier (block barrier, then one thread fences and signals)
             __syncwarp();
             if (lane == 0) st_release(p.done + g, it + 1);
             FR_STAMP(6);

@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
     const long long t0 = (long long)blockIdx.x * kTcM;
     const int rows = (int)min((long long)kTcM, p.n_frames - t0);
     const uint32_t chunk_bytes = 2u * (uint32_t)b_floats * 4u;
+    // gridDim.y > 1 (small calls): the CTAs of one frame tile share its bin chunks, [cb, ce) each -- a call of a few
+    // hundred frames is bound by the latency of one CTA walking all eight chunks (41 us), not by throughput
+    const int per = (kTcChunks + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int cb = (int)blockIdx.y * per, ce = min(kTcChunks, cb + per);
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -109,7 +113,8 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the first two B chunks fly while the CTA prepares A
-        for (int i = 0; i < 2; ++i) bulk_load(sB[i], p.b_tc + (size_t)i * 2 * b_floats, chunk_bytes, smem_u32(&s_full[i]));
+        for (int i = 0; i < 2; ++i)
+            if (cb + i < ce) bulk_load(sB[i], p.b_tc + (size_t)(cb + i) * 2 * b_floats, chunk_bytes, smem_u32(&s_full[i]));
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTcTmemCols));
@@ -141,10 +146,10 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
     const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (kTcNChunk / 8) * 128, sbo = 128;
     const bool vec_store = (p.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mag) & 15) == 0;
 
-    // chunk c: B buffer c & 1, accumulator columns (c & 1) * kTcNChunk; mbarrier phase (c >> 1) & 1
+    // the CTA's chunk number lc = c - cb: B buffer lc & 1, accumulator columns (lc & 1) * kTcNChunk; mbarrier phase (lc >> 1) & 1
     auto issue_mma = [&](int c) {  // thread 0 only
-        const int buf = c & 1;
-        mbar_wait(smem_u32(&s_full[buf]), (uint32_t)(c >> 1) & 1);  // the chunk's B has landed
+        const int buf = (c - cb) & 1;
+        mbar_wait(smem_u32(&s_full[buf]), (uint32_t)((c - cb) >> 1) & 1);  // the chunk's B has landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem + (uint32_t)(buf * kTcNChunk);
         uint32_t acc = 0;
@@ -159,15 +164,15 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_done[buf])) : "memory");
     };
-    if (tid == 0) issue_mma(0);
-    for (int chunk = 0; chunk < kTcChunks; ++chunk) {
-        const int buf = chunk & 1;
+    if (tid == 0 && cb < ce) issue_mma(cb);
+    for (int chunk = cb; chunk < ce; ++chunk) {
+        const int buf = (chunk - cb) & 1;
         // the next chunk's MMAs go to the other accumulator and run under this chunk's epilogue
-        if (tid == 0 && chunk + 1 < kTcChunks) issue_mma(chunk + 1);
-        mbar_wait(smem_u32(&s_done[buf]), (uint32_t)(chunk >> 1) & 1);
+        if (tid == 0 && chunk + 1 < ce) issue_mma(chunk + 1);
+        mbar_wait(smem_u32(&s_done[buf]), (uint32_t)((chunk - cb) >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // this chunk's MMAs have retired: its B buffer is free for chunk + 2
-        if (tid == 0 && chunk + 2 < kTcChunks)
+        if (tid == 0 && chunk + 2 < ce)
             bulk_load(sB[buf], p.b_tc + (size_t)(chunk + 2) * 2 * b_floats, chunk_bytes, smem_u32(&s_full[buf]));
         // epilogue: thread tid owns row tid (TMEM lane tid); 16 columns per tcgen05.ld
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kTcNChunk);
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(128, 1) k_inverse_mel_tc(const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     // columns beyond the chunks are exactly zero
-    if (tid < rows)
+    if (tid < rows && blockIdx.y == gridDim.y - 1)
         for (int col = kTcChunks * kTcNChunk; col < p.n_out; ++col) p.mag[(t0 + tid) * (long long)p.out_stride + col] = 0.0f;
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
 }
@@ -413,7 +418,9 @@ int launch_inverse_mel_tc(const s2st_plan* plan, long long n_frames, const float
     const size_t smem = sizeof(float) * (size_t)(2 * kTcM * p.K + 4 * kTcNChunk * p.K) + 1024;  // A head + tail, two B chunk buffers
     S2ST_CUDA_CHECK(cudaFuncSetAttribute(k_inverse_mel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = (n_frames + kTcM - 1) / kTcM;
-    k_inverse_mel_tc<<<(unsigned)blocks, 128, smem, stream>>>(p);
+    // small calls: split the eight bin chunks of a frame tile over up to eight CTAs (as long as the grid fits one wave)
+    const int split = blocks * 8 <= plan->num_sms ? 8 : blocks * 4 <= plan->num_sms ? 4 : blocks * 2 <= plan->num_sms ? 2 : 1;
+    k_inverse_mel_tc<<<dim3((unsigned)blocks, (unsigned)split), 128, smem, stream>>>(p);
     S2ST_CUDA_CHECK(cudaGetLastError());
     return S2ST_OK;
 }

@@ -96,6 +96,10 @@ int launch_rfft2048(const s2st_plan* plan, long long n, const float* in, float* 
                     cudaStream_t stream);
 int launch_phase_from_uniform(int n_batch, int n_bins, int n_frames, const double* u, float* phase, cudaStream_t stream);
 
+// rng_kernels.cu
+int launch_phase_from_mt19937(int n_batch, int n_bins, int n_frames, const uint32_t* key, int pos, uint32_t* words,
+                              float* phase, uint32_t* key_out, cudaStream_t stream);
+
 // mel_tc.cu (tcgen05 tensor-core path of the inverse-mel projection)
 void build_inverse_mel_tc(const float* inv_mel, int kb, int K, float* out);
 size_t inverse_mel_tc_floats(int K);

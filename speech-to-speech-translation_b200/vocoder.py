@@ -10,6 +10,8 @@ one kernel launch per Griffin-Lim iteration for the whole batch.
 import logging
 from typing import List, Optional, Sequence
 
+import ctypes
+
 import numpy as np
 import torch
 from torch import nn
@@ -26,12 +28,11 @@ def draw_initial_phase(shape) -> np.ndarray:
     return np.angle(np.exp(2j * np.pi * np.random.rand(*shape))).astype(np.float32)
 
 
-def draw_initial_phase_device(shape, dev) -> torch.Tensor:
-    """The same draw with only the RNG on the host: ``np.random.rand(*shape)`` consumes numpy's GLOBAL generator
-    exactly like vocoder.py:103 (so ``np.random.seed(s)`` before ``forward`` reproduces the reference), the uniforms are
-    uploaded from pinned memory, and ``angle(exp(2j pi u))`` -- 40 of the 50 host milliseconds for a 500-frame utterance
-    -- becomes the closed form theta / theta - 2 pi in float64 on the device, written frame-major.
-    shape = (B,) F, T  ->  [B * T, F] float32 on ``dev``."""
+def _draw_initial_phase_host_rng(shape, dev) -> torch.Tensor:
+    """The draw with the RNG on the host: ``np.random.rand(*shape)`` consumes numpy's GLOBAL generator exactly like
+    vocoder.py:103, the float64 uniforms are uploaded from pinned memory, and ``angle(exp(2j pi u))`` becomes the closed
+    form theta / theta - 2 pi in float64 on the device, written frame-major.  Used when numpy's global generator is not
+    the legacy MT19937 (it always is unless somebody replaced it)."""
     u = np.random.rand(*shape)
     B = shape[0] if len(shape) == 3 else 1
     F, T = shape[-2], shape[-1]
@@ -43,6 +44,81 @@ def draw_initial_phase_device(shape, dev) -> torch.Tensor:
         rc = _lib.load().s2st_phase_from_uniform(B, F, T, _lib.ptr(u_d), _lib.ptr(phase), _lib.stream_ptr(dev))
     _lib.check(rc, "s2st_phase_from_uniform")
     return phase
+
+
+class _NumpyStreamOnDevice:
+    """Per-device resources of ``draw_initial_phase_device``: a side stream and the small buffers that only that stream
+    touches (key up / down, the raw output words), reused from call to call -- the stream orders their uses, and
+    ``finish()`` of a call has synchronised with its last kernel before the next call writes the pinned buffers."""
+    _by_device = {}
+
+    @classmethod
+    def get(cls, dev):
+        if dev.index not in cls._by_device:
+            cls._by_device[dev.index] = cls(dev)
+        return cls._by_device[dev.index]
+
+    def __init__(self, dev):
+        self.stream = torch.cuda.Stream(device=dev)
+        self.key_stage = torch.empty(624, dtype=torch.int32, pin_memory=True)
+        self.key_host = torch.empty(624, dtype=torch.int32, pin_memory=True)
+        with torch.cuda.stream(self.stream):
+            self.key_d = torch.empty(624, dtype=torch.int32, device=dev)
+            self.key_out = torch.empty(624, dtype=torch.int32, device=dev)
+            self.words = torch.empty(0, dtype=torch.int32, device=dev)
+        self.done = torch.cuda.Event()
+
+    def words_buffer(self, n_words, dev):
+        if self.words.numel() < n_words:
+            with torch.cuda.stream(self.stream):
+                self.words = torch.empty(n_words, dtype=torch.int32, device=dev)
+        return self.words
+
+
+def draw_initial_phase_device(shape, dev):
+    """The reference's initial phase (vocoder.py:103: ``angle(exp(2j pi np.random.rand(*shape)))``) for shape = (B,) F, T,
+    frame-major [B * T, F] float32 on ``dev`` -- with numpy's GLOBAL generator continued on the device.
+
+    ``np.random.seed(s)`` before ``forward`` must reproduce the reference, so the draw has to be numpy's stream; but
+    512 500 doubles for a 500-frame utterance cost ~1.2 ms on the host plus a 4 MB upload -- more than the synthesis.
+    Instead the generator state (MT19937 key + position, 2.5 KB) goes to the device, ``s2st_phase_from_mt19937``
+    produces exactly the outputs ``rand`` would consume and the state it would leave, and that state is put back.
+
+    Returns ``(phase, finish)``: call ``finish()`` once the rest of the work has been enqueued -- it waits for the
+    generator kernel (not for the synthesis) and hands the advanced state to ``np.random.set_state``."""
+    st = np.random.get_state()
+    n = int(np.prod(shape))
+    if st[0] != "MT19937" or n == 0:
+        return _draw_initial_phase_host_rng(shape, dev), (lambda: None)
+    B = shape[0] if len(shape) == 3 else 1
+    F, T = shape[-2], shape[-1]
+    pos = int(st[2])
+    # The generator runs on a side stream: it is one thread block walking a sequential recurrence, so in a loop of
+    # forward() calls it overlaps the previous call's synthesis kernels instead of queueing behind them (and finish()
+    # waits for the generator only).  The phase is allocated on that stream; the caller's stream waits for it.
+    res = _NumpyStreamOnDevice.get(dev)
+    main = torch.cuda.current_stream(dev)
+    side = res.stream
+    words = res.words_buffer(2 * n, dev)
+    res.key_stage.numpy()[...] = np.asarray(st[1], np.uint32).view(np.int32)
+    with torch.cuda.stream(side):
+        res.key_d.copy_(res.key_stage, non_blocking=True)
+        phase = torch.empty(B * T, F, dtype=torch.float32, device=dev)
+        rc = _lib.load().s2st_phase_from_mt19937(B, F, T, _lib.ptr(res.key_d), pos, _lib.ptr(words), _lib.ptr(phase),
+                                                 _lib.ptr(res.key_out), ctypes.c_void_p(side.cuda_stream))
+        _lib.check(rc, "s2st_phase_from_mt19937")
+        res.key_host.copy_(res.key_out, non_blocking=True)
+        res.done.record(side)
+    main.wait_stream(side)
+    phase.record_stream(main)
+    end = pos + 2 * n
+    new_pos = end - 624 * ((end - 1) // 624)
+
+    def finish():
+        res.done.synchronize()
+        np.random.set_state((st[0], res.key_host.numpy().view(np.uint32).copy(), new_pos, st[3], st[4]))
+
+    return phase, finish
 
 
 class PseudoInverseMelScale(torch.nn.Module):
@@ -140,12 +216,15 @@ class GriffinLim(torch.nn.Module):
         """specgram [F, T] or [B, F, T] linear magnitudes -> waveform(s); random initial phase from the
         global numpy RNG exactly like the reference."""
         dev = require_cuda(specgram.device)
-        ph = draw_initial_phase_device(tuple(specgram.shape), dev)  # consumes numpy's global RNG first, like the reference
-        spec = specgram.detach().reshape(-1, specgram.shape[-2], specgram.shape[-1])
-        B, F, T = spec.shape
-        _check_length(T, self.hop_length, self.n_fft, self.n_iter)
-        mag = spec.to(dev, torch.float32).transpose(1, 2).reshape(B * T, F).contiguous()
-        wave = self._run(mag, ph, B, T, self.n_iter, dev)
+        ph, finish_rng = draw_initial_phase_device(tuple(specgram.shape), dev)  # consumes numpy's global RNG first, like the reference
+        try:
+            spec = specgram.detach().reshape(-1, specgram.shape[-2], specgram.shape[-1])
+            B, F, T = spec.shape
+            _check_length(T, self.hop_length, self.n_fft, self.n_iter)
+            mag = spec.to(dev, torch.float32).transpose(1, 2).reshape(B * T, F).contiguous()
+            wave = self._run(mag, ph, B, T, self.n_iter, dev)
+        finally:
+            finish_rng()
         return wave.squeeze(0).to(specgram.device, specgram.dtype)
 
 
@@ -217,10 +296,13 @@ class GriffinLimVocoder(nn.Module):
         # initial phase: one draw of shape (B x) F x T from numpy's global RNG (vocoder.py:103)
         shape = ((B,) if batched else ()) + (g.n_fft // 2 + 1, T)
         dev = self._device(feats)
-        phase_fm = draw_initial_phase_device(shape, dev)
-        _check_length(T, g.hop_length, g.n_fft, g.n_iter)
-        waves = self._synthesize_flat(feats.reshape(B * T, self.n_mels).to(dev, torch.float32).contiguous(),
-                                      [T] * B, phase_fm, g.n_iter, dev)
+        phase_fm, finish_rng = draw_initial_phase_device(shape, dev)
+        try:
+            _check_length(T, g.hop_length, g.n_fft, g.n_iter)
+            waves = self._synthesize_flat(feats.reshape(B * T, self.n_mels).to(dev, torch.float32).contiguous(),
+                                          [T] * B, phase_fm, g.n_iter, dev)
+        finally:
+            finish_rng()  # numpy's generator is where the reference's draw would have left it
         out = waves.view(B, -1)
         out = out.squeeze(0) if (not batched or B == 1) else out
         return out.to(x.device, x.dtype)

@@ -204,6 +204,25 @@ def test_specaugment_time_warp_oracle_bit_exact():
     assert np.abs(g["w40_1203_y"] - g["w40_1203_y_noipp"]).max() > 1e-5   # the two arithmetics really differ
 
 
+def test_mt19937_restatement_is_numpy():
+    """oracle/mt19937.py (numpy's legacy global generator as one untempered sequence, the form the device kernel uses)
+    against numpy itself: uniforms and the state left behind, from fresh seeds, mid-block, odd word positions, draws
+    ending on block boundaries."""
+    from oracle import mt19937 as mt
+    for seed, pre, shape in [(0, 0, (3, 5)), (1, 7, (1025, 50)), (2, 623, (2, 3, 4)), (3, 1247, (1,)), (4, 100, (312,)),
+                             (5, 0, (311,)), (6, 0, (312,)), (7, 5, (1025, 64)), (8, 0, (0,))]:
+        np.random.seed(seed)
+        if pre:
+            np.random.rand(pre)
+            if pre % 2:
+                np.random.randint(0, 2 ** 31)
+        st = np.random.get_state()
+        u, st2 = mt.rand(st, shape)
+        v = np.random.rand(*shape)
+        st3 = np.random.get_state()
+        assert np.array_equal(u, v) and np.array_equal(st2[1], st3[1]) and st2[2] == st3[2], (seed, pre, shape)
+
+
 def test_conv_formulation_reproduces_reference_bit_for_bit(golden_basis):
     """oracle/conv_formulation.py is the reference's own dense-convolution formulation: same torch ops in the same
     order, so the golden waveforms come back exactly; and it pins the FFT oracle from a second, independent side."""

@@ -25,3 +25,15 @@ for T in [int(a) for a in sys.argv[1:]] or [100, 500]:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record(); y = voc.synthesize_flat(x, [T], ph); e1.record(); torch.cuda.synchronize()
     print(f"   single call, events: {e0.elapsed_time(e1):.3f} ms")
+    # the reference's call: forward() on one utterance (numpy's global RNG continued on the device)
+    np.random.seed(0)
+    for _ in range(5): y = voc(x)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20): y = voc(x)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"   forward(): host {1e3 * (t1 - t0) / 20:.3f} ms/call, until done {1e3 * (t2 - t0) / 20:.3f} ms/call -> {(T - 1) * 300 / 24000 / ((t2 - t0) / 20):.0f} audio-s/s", flush=True)
+    t0 = time.perf_counter(); y = voc(x); torch.cuda.synchronize(); t1 = time.perf_counter()
+    print(f"   forward(), one call with sync: {1e3 * (t1 - t0):.3f} ms")
