@@ -602,8 +602,9 @@ def gl_extras(ctx, voc):
     out["config1"] = {"workload": "one 500-frame utterance, 64 iters", "forward_ms": ms_fwd,
                       "forward_audio_s_per_s": audio / (ms_fwd * 1e-3), "device_phase_resident_ms": ms_dev,
                       "device_phase_resident_audio_s_per_s": audio / (ms_dev * 1e-3),
-                      "note": "forward() draws 1025 x T float64 uniforms from numpy's global RNG on the host "
-                              "(vocoder.py:103) -- that draw bounds the per-utterance API"}
+                      "note": "small calls run all iterations in ONE cooperative launch, a warp per frame (k_gl_frames); "
+                              "forward() continues numpy's global MT19937 on the device (vocoder.py:103 draws 1025 x T "
+                              "float64 uniforms from it) instead of drawing on the host; round 1: 3.16 / 1.65 ms"}
     # config 5: one 60 s utterance
     T = 4800
     x5 = torch.from_numpy(synth_logmel_np(T, 78)).to(dev)
