@@ -463,10 +463,8 @@ def run_gl(args, ctx):
     n_sus = max(args.steps, int(np.ceil(2000.0 / ms_step)))
     ms_sus, _ = ctx.timed(step, n_sus)
     last_pass_ms = pass_profile(ctx, plan, step, min(args.steps, 20))
-    # one launch per iteration: [initial inverse, iteration 1, ..., iteration n]; persistent mode (all iterations in
-    # one launch): [initial inverse, the persistent launch]
-    persistent = len(last_pass_ms) == 2 and N_ITER > 1
-    iters_per_launch = N_ITER if persistent else 1
+    # one launch per iteration: [initial inverse, iteration 1, ..., iteration n]
+    iters_per_launch = 1
     iter_ms = float(np.mean(last_pass_ms[1:])) if len(last_pass_ms) > 1 else float("nan")  # per LAUNCH
     launches = plan.gl_launch_count(N_ITER, True) * args.steps
 
@@ -543,9 +541,7 @@ def run_gl(args, ctx):
                 "with_device_drawn_phase": {"value": world * audio_s / (e2e_dev_ms * 1e-3), "ms_per_step": e2e_dev_ms,
                                             "h2d_bytes_per_step": int(logmel_h.numel() * 4)}},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": ("k_gl_pass<19,false,true,true,PERSIST> (all %d iterations in one cooperative launch: " % N_ITER
-                                                 if persistent else "k_gl_pass<19,false,true,true> (") +
-                                                "fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
+        "roofline": {"bound": "hbm", "kernel": "k_gl_pass<19,false,true,true> (fused iSTFT+OLA+normalise+STFT+magnitude re-imposition)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic * iters_per_launch if traffic else None,
                      "traffic_source": ("ncu --set full capture of one iteration on this workload, committed as %s "

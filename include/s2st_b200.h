@@ -66,19 +66,15 @@ int s2st_plan_destroy(s2st_plan* plan);
 int s2st_plan_active_bins(const s2st_plan* plan, int* active_bins_out);
 /* Plan options (all have working defaults; they exist for A/B measurements and tests).  Initial values come from the
  * environment variable named in brackets, read once by s2st_plan_create. */
-#define S2ST_OPT_GL_PERSISTENT 1    /* [S2ST_GL_PERSISTENT=1 | auto] 0 (default): one launch per Griffin-Lim iteration; 1: all
-                                       iterations as ONE persistent cooperative launch whenever every strip is resident; -1:
-                                       persistent for small calls only (<= 1/4 of the resident warps get a strip).  Results are
-                                       bitwise identical in all three modes; measured on B200 the persistent launch never wins. */
+/* (options 1 and 3 -- a persistent launch of the strip kernel and a four-warps-per-strip mode for small calls -- were measured,
+ * superseded by S2ST_OPT_GL_FRAMES and removed; s2st_plan_set_option rejects them) */
 #define S2ST_OPT_GL_PDL 2           /* [S2ST_GL_PDL] 1 (default): programmatic dependent launch of the passes; 0: plain launches */
-#define S2ST_OPT_GL_TEAM 3          /* [S2ST_GL_TEAM=0] 1 (default): a SMALL synthesis call (at most one strip per SM, e.g. one utterance
-                                       of up to ~590 frames) spreads the frames of a strip over a team of four warps that
-                                       overlap-add in frame order: bitwise identical results, 22 % less latency.
-                                       0: always one warp per strip */
-#define S2ST_OPT_GL_FRAMES 7        /* [S2ST_GL_FRAMES=0 | N] 1 (default): synthesis calls of a few thousand frames (one utterance, a small
-                                       batch) run ALL iterations in one launch with a warp per frame, overlap-add gathered from
-                                       the neighbours' frames; bitwise equal to one strip per utterance, independent of the batch.
-                                       0: always the strip kernels; N > 1: the frame-parallel kernel for calls of up to N frames */
+#define S2ST_OPT_GL_FRAMES 7        /* [S2ST_GL_FRAMES=0 | N] 1 (default): synthesis calls of up to 9 472 frames (one utterance, a small
+                                       batch) run ALL iterations in ONE cooperative launch with a warp per frame, the overlap-add
+                                       gathered from the neighbours' frames: the arithmetic of one strip per utterance (equal to
+                                       rounding noise), bitwise independent of the batch, 3-4 x less latency than a launch per
+                                       iteration.  0: always the strip kernels; N > 1: the frame-parallel kernel up to N frames.
+                                       A pinned strip length (s2st_plan_set_strip_frames) keeps the strip kernels. */
 #define S2ST_OPT_INVERSE_MEL 4      /* [S2ST_INVERSE_MEL=simt] 0 (default): tcgen05 tensor-core inverse-mel; 1: FP32 SIMT kernel */
 #define S2ST_OPT_FRONTEND_GENERIC 5 /* [S2ST_LOGMEL_GENERIC / S2ST_FBANK_GENERIC] 0 (default): register-resident log-mel / fbank
                                        kernels where they apply; 1: always the generic kernels */
@@ -117,9 +113,8 @@ int s2st_plan_set_strip_frames(s2st_plan* plan, int frames);
 /* Profiling aid (not part of the reference's interface): when enabled, s2st_gl_synthesize / s2st_istft
  * record a CUDA event on the caller's stream before every Griffin-Lim pass and after the last one;
  * s2st_plan_get_pass_times waits for the last event and returns the device time of each pass of the
- * most recent call in milliseconds (pass 0 = initial inverse, passes 1..n_iter = fused iterations).  When the call ran
- * its iterations as ONE persistent launch (standard geometry, host frame offsets given, every strip resident) two
- * values come back: the initial inverse and the whole persistent launch. */
+ * most recent call in milliseconds (pass 0 = initial inverse, passes 1..n_iter = fused iterations).  A call that ran the
+ * frame-parallel kernel (S2ST_OPT_GL_FRAMES) is ONE launch: one value comes back, the whole synthesis. */
 int s2st_plan_set_pass_timing(s2st_plan* plan, int enabled);
 int s2st_plan_get_pass_times(s2st_plan* plan, float* ms_out_host, int capacity, int* n_passes_out);
 /* number of kernel launches of the plan's most recent s2st_gl_synthesize call (for bench.py's gpu_launches); before

@@ -18,7 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "s2st_b200.h")
 S2ST_OK = 0
 ABI_VERSION = 2
 # s2st_plan_set_option keys (include/s2st_b200.h)
-OPT_GL_PERSISTENT, OPT_GL_PDL, OPT_GL_TEAM, OPT_INVERSE_MEL, OPT_FRONTEND_GENERIC, OPT_MEL_PROJECT, OPT_GL_FRAMES = 1, 2, 3, 4, 5, 6, 7
+OPT_GL_PDL, OPT_INVERSE_MEL, OPT_FRONTEND_GENERIC, OPT_MEL_PROJECT, OPT_GL_FRAMES = 2, 4, 5, 6, 7
 
 c_f32p = ctypes.c_void_p  # device pointers are passed as integers (tensor.data_ptr())
 

@@ -150,15 +150,11 @@ int s2st_plan_create(s2st_plan** plan_out, int device, int n_fft, int win_length
     s2st_plan* p = new s2st_plan();
     std::memset(p, 0, sizeof(*p));
     {   // options: the S2ST_* environment variables are read HERE, once; afterwards only s2st_plan_set_option changes them
-        const char* e = getenv("S2ST_GL_PERSISTENT");
-        p->opt_persistent = (e && e[0] == '1') ? 1 : (e && e[0] == 'a') ? -1 : 0;
-        e = getenv("S2ST_GL_PDL");
+        const char* e = getenv("S2ST_GL_PDL");
         p->opt_pdl = !(e && e[0] == '0');
         e = getenv("S2ST_GL_FRAMES");  // 0 = never the frame-parallel kernel, N > 1 = up to N frames
         p->opt_frames = !(e && e[0] == '0');
         p->opt_frames_max = (e && atoi(e) > 1) ? atoi(e) : 16 * 148 * 4;
-        e = getenv("S2ST_GL_TEAM");
-        p->opt_team = !(e && e[0] == '0');
         e = getenv("S2ST_INVERSE_MEL");
         p->opt_inverse_mel_simt = (e && e[0] == 's') ? 1 : 0;
         p->opt_frontend_generic = getenv("S2ST_LOGMEL_GENERIC") ? 1 : 0;
@@ -407,10 +403,6 @@ int s2st_plan_set_option(s2st_plan* plan, int option, int value) {
         return S2ST_EINVAL;
     }
     switch (option) {
-        case S2ST_OPT_GL_PERSISTENT:
-            if (value < -1 || value > 1) break;
-            plan->opt_persistent = value;
-            return S2ST_OK;
         case S2ST_OPT_GL_PDL:
             plan->opt_pdl = value != 0;
             return S2ST_OK;
@@ -418,9 +410,6 @@ int s2st_plan_set_option(s2st_plan* plan, int option, int value) {
             if (value < 0) break;
             plan->opt_frames = value != 0;
             if (value > 1) plan->opt_frames_max = value;
-            return S2ST_OK;
-        case S2ST_OPT_GL_TEAM:
-            plan->opt_team = value != 0;
             return S2ST_OK;
         case S2ST_OPT_INVERSE_MEL:
             if (value < 0 || value > 1) break;
@@ -533,8 +522,7 @@ int s2st_gl_launch_count(const s2st_plan* plan, int n_iter, int from_logmel, int
         return S2ST_EINVAL;
     }
     // What the last synthesis call of this plan launched, if there was one; else the per-pass count: build_tiles +
-    // [inverse_mel] + (n_iter + 1) passes (plus cudaMemsetAsync calls, not kernels of ours).  In persistent mode all
-    // iterations are one launch.
+    // [inverse_mel] + (n_iter + 1) passes (plus cudaMemsetAsync calls, not kernels of ours).
     *launches_out = plan->last_launches > 0 ? plan->last_launches : 1 + (from_logmel ? 1 : 0) + (n_iter + 1);
     return S2ST_OK;
 }

@@ -25,7 +25,7 @@ struct TileDesc {
     int f0;              // first frame (utterance-local) of the strip
     int nf;              // frames in the strip (1..S)
     int prev;            // strip table index of the strip before / after this one in the same utterance, -1 if none
-    int next;            // (the only strips whose output this strip reads: see k_gl_pass PERSIST)
+    int next;            // (kept for tools that walk an utterance's strips; the kernels do not need them)
 };
 
 // Everything the Griffin-Lim kernels need, passed by value.
@@ -59,12 +59,6 @@ struct GlParams {
     const float* in;         // normalised waveforms written by the previous pass
     float* out;              // waveforms written by this pass (seams pre-zeroed)
     float* zero_next;        // buffer the NEXT pass writes: this pass zeroes its seams
-    // persistent mode (k_gl_pass<..., PERSIST>): iterations it_first..it_last in one launch; iteration it reads
-    // bufs[(it + 2) % 3], writes bufs[it % 3], zeroes the seams of bufs[(it + 1) % 3]; done[strip] = last iteration
-    // the strip has finished (0 = the initial inverse, which is a launch of its own)
-    float* bufs[3];
-    int* done;
-    int it_first, it_last;
 };
 
 struct s2st_error_state;

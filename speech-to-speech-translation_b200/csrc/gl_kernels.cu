@@ -46,7 +46,7 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned lon
 }
 
 // Frame load, cold path: reflect padding (audio_utils.py:262-263) at utterance edges / unaligned data.
-template <int NZ, bool L2ONLY = false>
+template <int NZ>
 __device__ __forceinline__ void load_frame_edge(float2 (&a)[32], const float* __restrict__ y, int j, int L) {
 #pragma unroll 1
     for (int r = 0; r < NZ; ++r, j += 64) {
@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_frame_edge(float2 (&a)[32], const float* __
         j1 = j1 >= L ? 2 * (L - 1) - j1 : j1;
         j0 = min(max(j0, 0), L - 1);  // only reachable where the window is zero
         j1 = min(max(j1, 0), L - 1);
-        const float2 v = L2ONLY ? make_float2(__ldcg(y + j0), __ldcg(y + j1)) : make_float2(y[j0], y[j1]);
+        const float2 v = make_float2(y[j0], y[j1]);
         // registers cannot be indexed dynamically: scatter through a switch-free unrolled select
 #pragma unroll
         for (int q = 0; q < NZ; ++q)
@@ -117,14 +117,10 @@ constexpr int kStdHop = 300, kStdWs = 1200, kStdRot = 424;  // the vocoder's sta
 #endif
 constexpr bool kGlSharedFft = S2ST_GL_SHARED_FFT != 0;
 constexpr int kGlUnrollPass = kGlSharedFft ? 1 : 2;
-// PERSIST: all iterations p.it_first..p.it_last in ONE launch, without a grid-wide barrier between them.  Every warp
-// owns one strip for the whole launch (the host guarantees n_strips <= resident warps and launches cooperatively).  A
-// strip may start iteration `it` as soon as it and its two neighbours in the utterance have finished iteration it - 1:
-// those are the only strips whose output (their hops and the shared seams) its frames read, and the only ones that add
-// into or clear the seams it touches.  Completion is published per strip (release store after a fence), waited for by
-// lane 0 (acquire load); waveform loads bypass L1 (ld.global.cg), because an address is rewritten every third iteration.
-// This removes the tail of every pass (strips shorter than S, warps finishing apart, launch ramp): while a short strip
-// waits for its neighbour, the other warps of its SM run faster.  Measured: not a win (see use_persistent()).
+// Two variants of this kernel were measured and removed in round 2 (profiles/r02_small_calls.txt, git history): a
+// persistent launch of all iterations with per-strip neighbour flags (never faster: 15.82 vs 15.57 ms on the config-2
+// batch, 2.64 vs 2.16 ms for one 500-frame utterance) and a "team" mode with four warps per strip for small calls
+// (1.67 ms).  Small calls now run the frame-parallel kernel of gl_frames.cuh (0.50 ms), which uses the two helpers below.
 __device__ __forceinline__ int ld_acquire(const int* ptr) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
@@ -134,21 +130,8 @@ __device__ __forceinline__ void st_release(int* ptr, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 
-constexpr int kTeam = 4;  // warps per strip in team mode (small calls)
-constexpr unsigned kPersistSleepNs = 100;  // back-off of the neighbour wait (20 ns measured the same)
-
-// TEAM > 1 (small calls): TEAM consecutive warps share ONE strip.  The frames of the strip are dealt round-robin to the
-// team's warps, so their transforms -- all of a frame's latency, ~8 us when a warp has an SM nearly to itself -- run in
-// parallel; only the overlap-add into the (now team-shared) ring and the write-out of the finished hop are serialised,
-// in frame order, through a turn counter in shared memory.  The order of the additions is therefore exactly the one
-// of the single-warp strip: results are bitwise identical (test_team_mode_is_bitwise_identical).  A small call is
-// bound by the latency of one warp walking its 4-frame strip (profiles/r02_small_calls.txt); with TEAM = 4 a pass
-// lasts one frame plus four short ordered sections.
-template <int NZ, bool FIRST, bool PRUNED, bool STD, bool PERSIST = false, int TEAM = 1>
+template <int NZ, bool FIRST, bool PRUNED, bool STD>
 __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant__ GlParams p) {
-    static_assert(!PERSIST || (!FIRST && STD), "persistent mode is the standard-geometry iteration only");
-    static_assert(TEAM == 1 || (!PERSIST && kGlWarps % TEAM == 0), "team mode: whole teams per CTA, no persistent mode");
-    __shared__ int s_turn[kGlWarps];  // TEAM > 1: s_turn[team] = next frame of the team's strip whose ordered section may run
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);            // 1024
     float2* s_vtab = s_tw + 1024;                                  // 1024
@@ -160,10 +143,8 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
     const int ring_floats = (ws + 3) & ~3;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int team = warp / TEAM, member = warp % TEAM;  // TEAM == 1: team = warp, member = 0
     float* scratch = s_warp + warp * (kScratchFloats + ring_floats);
-    float* ring = s_warp + (team * TEAM) * (kScratchFloats + ring_floats) + kScratchFloats;  // the team's first warp's ring
-    if (TEAM > 1 && tid < kGlWarps) s_turn[tid] = 0;
+    float* ring = scratch + kScratchFloats;
     for (int i = tid; i < 1024; i += kGlThreads) {
         s_tw[i] = p.tw[i];
         s_vtab[i] = p.vtab[i];
@@ -184,7 +165,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
 
     // strips are dealt to SMs first, then to warps: a small batch spreads one warp per SM (a lone warp runs a frame
     // about twice as fast as one of 16 sharing the SM) instead of filling a few SMs
-    for (int strip = blockIdx.x + gridDim.x * team; strip < n_strips; strip += gridDim.x * (kGlWarps / TEAM)) {
+    for (int strip = blockIdx.x + gridDim.x * warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
         const TileDesc td = p.tiles[strip];
         UttDesc ud;
         ud.wave_off = td.wave_off;
@@ -193,46 +174,31 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
         const int T = ud.n_frames, L = (T - 1) * hop;
         const int j_base = td.f0 * hop + rot_half;  // output sample index of strip-relative sample 0
         const bool aligned = STD || (geom4 && ((ud.wave_off & 3) == 0));  // STD: wave_off is a multiple of hop
-#pragma unroll 1
-      for (int it = PERSIST ? p.it_first : 0; it <= (PERSIST ? p.it_last : 0); ++it) {
-        if constexpr (PERSIST) {
-            if (lane == 0) {
-                if (td.prev >= 0)
-                    while (ld_acquire(p.done + td.prev) < it - 1) __nanosleep(kPersistSleepNs);
-                if (td.next >= 0)
-                    while (ld_acquire(p.done + td.next) < it - 1) __nanosleep(kPersistSleepNs);
-            }
-            __syncwarp();
-        }
-        float* out = (PERSIST ? p.bufs[it % 3] : p.out) + ud.wave_off;
-        float* znext = (PERSIST ? p.bufs[(it + 1) % 3] : p.zero_next) + ud.wave_off;
-        const float* y = (PERSIST ? p.bufs[(it + 2) % 3] : p.in) + ud.wave_off;
-        const int f_first = TEAM > 1 ? member : 0;  // first frame of the strip this warp runs
-        const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0 + f_first) * p.mag_stride;
-        const float* phrow = (FIRST && p.phase) ? p.phase + ((size_t)ud.frame_off + td.f0 + f_first) * p.phase_stride : nullptr;
+        float* out = p.out + ud.wave_off;
+        float* znext = p.zero_next + ud.wave_off;
+        const float* y = p.in + ud.wave_off;
+        const float* magrow = p.mag + ((size_t)ud.frame_off + td.f0) * p.mag_stride;
+        const float* phrow = (FIRST && p.phase) ? p.phase + ((size_t)ud.frame_off + td.f0) * p.phase_stride : nullptr;
 
         float2 a[32];
         int slot0 = 0;  // ring slot of strip-relative sample f * hop
         // f = -1 only fetches frame 0; iteration f processes frame f and fetches frame f + 1, so the
         // (single) copy of the load code overlaps with the write-out of the previous hop.
-        // the frame load (one copy of the code): TEAM == 1 fetches frame f + 1 while hop f is written out, a team member
-        // fetches its own next frame at the top of its iteration
         auto fetch_frame = [&](int fi) {
             const int jf = j_base + fi * hop;  // first sample of the frame (lane 0)
             if (aligned && jf >= 0 && jf + 64 * NZ <= L) {
                 const float2* src = reinterpret_cast<const float2*>(y + jf) + lane;
 #pragma unroll
-                for (int r = 0; r < NZ; ++r) a[brev5(r)] = PERSIST ? __ldcg(src + 32 * r) : src[32 * r];
+                for (int r = 0; r < NZ; ++r) a[brev5(r)] = src[32 * r];
                 // the hop the frame after that adds is not in cache yet: ask L2 for it now (11 lines)
                 const int jp = jf + 64 * NZ - 16 + 32 * lane;
                 if (lane < 11 && jp < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + jp));
             } else {
-                load_frame_edge<NZ, PERSIST>(a, y, jf + 2 * lane, L);
+                load_frame_edge<NZ>(a, y, jf + 2 * lane, L);
             }
         };
 #pragma unroll 1
-        for (int f = TEAM > 1 ? member : (FIRST ? 0 : -1); f < td.nf; f += TEAM) {
-            if constexpr (TEAM > 1 && !FIRST) fetch_frame(f);
+        for (int f = FIRST ? 0 : -1; f < td.nf; ++f) {
             if (f >= 0) {
                 float ynyq = 0.0f;
                 float mg[kPrunedRows];
@@ -268,14 +234,14 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                             // CPU restatement after 64 iterations went from ~1e-4 to 6.7e-4 of the 1e-3 budget (measured).
                             constexpr int kRows = PRUNED ? kPrunedRows : 32;
                             float mgv[kRows], phv[kRows];
-                            if (f + TEAM < td.nf) {
+                            if (f + 1 < td.nf) {
                                 // the next frame's magnitude and phase rows (4.1 + 2.8 KB) are read exactly once, from
                                 // DRAM: ask L2 for them now, one transform ahead of their use (without this the pass
                                 // waits a full DRAM round trip per frame: 63 % of its stall samples)
-                                const char* nm = reinterpret_cast<const char*>(magrow + TEAM * p.mag_stride);
+                                const char* nm = reinterpret_cast<const char*>(magrow + p.mag_stride);
                                 for (int o = 128 * lane; o < 4 * kb; o += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + o));
                                 if (p.phase) {
-                                    const char* np = reinterpret_cast<const char*>(phrow + TEAM * p.phase_stride);
+                                    const char* np = reinterpret_cast<const char*>(phrow + p.phase_stride);
                                     for (int o = 128 * lane; o < 4 * kb; o += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + o));
                                 }
                             }
@@ -308,7 +274,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                                 const unsigned long long e = ((unsigned long long)ud.frame_off + td.f0 + f) * kBins + 1024;
                                 ynyq = __ldg(magrow + 1024) * (p.phase ? cosf(__ldg(phrow + 1024)) : cospif(2.0f * uniform01(p.phase_seed, e) - 1.0f));
                             }
-                            if (p.phase) phrow += TEAM * p.phase_stride;
+                            if (p.phase) phrow += p.phase_stride;
                         }
                         inv_merge<PRUNED, true, true>(a, ynyq, scratch, s_vtab, lane);
                     }
@@ -375,15 +341,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                         }
                     }
                 }
-                magrow += TEAM * p.mag_stride;
-                if constexpr (TEAM > 1) {
-                    // ordered section: frames add into the team's ring in frame order
-                    if (lane == 0)
-                        while (*reinterpret_cast<volatile int*>(&s_turn[team]) != f) {
-                        }
-                    __syncwarp();
-                    slot0 = (f * hop) % ws;
-                }
+                magrow += p.mag_stride;
                 // a[] holds the synthesis frame with the parts swapped (.y = even sample, .x = odd sample):
                 // window and overlap-add into the private ring
                 const float* w = s_win_a + 2 * lane;
@@ -427,7 +385,7 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                 }
             }
             // fetch the next frame (the loads fly while the finished hop is written out)
-            if constexpr (!FIRST && TEAM == 1) {
+            if constexpr (!FIRST) {
                 if (f + 1 < td.nf) fetch_frame(f + 1);
             }
             if (f >= 0) {
@@ -464,17 +422,10 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                 slot0 += hop;
                 if (slot0 >= ws) slot0 -= ws;
                 __syncwarp();
-                if constexpr (TEAM > 1) {
-                    if (f + 1 < td.nf) {  // (the owner of the last frame still has the tail to write)
-                        __threadfence_block();
-                        if (lane == 0) *reinterpret_cast<volatile int*>(&s_turn[team]) = f + 1;
-                    }
-                }
             }
         }
-        // the tail of the last frame: [nf*hop, (nf-1)*hop + ws) -- in team mode written by the warp that ran the last frame
-        if (TEAM > 1 && member != (td.nf - 1) % TEAM) {
-        } else if (STD && T - td.f0 - td.nf >= 3) {
+        // the tail of the last frame: [nf*hop, (nf-1)*hop + ws)
+        if (STD && T - td.f0 - td.nf >= 3) {
             // right seam of an interior strip (the next strip has at least three frames, so the window sum is the
             // steady one): add our part, and clear the same samples of the buffer the NEXT pass accumulates into
             const float4* iw = reinterpret_cast<const float4*>(s_inv_wss);
@@ -497,20 +448,6 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
             emit_generic(ring, s_inv_wss, p.w2, p.inv_nfft, out, znext, hop, ws, td.f0, td.nf, T, L, j_base, td.nf * hop, ws - hop, slot0, lane);
         }
         __syncwarp();
-        if constexpr (TEAM > 1) {
-            // end of the strip: the ring is all zero again; reset the turn counter for the team's next strip
-            if (member == (td.nf - 1) % TEAM) {
-                __threadfence_block();
-                if (lane == 0) *reinterpret_cast<volatile int*>(&s_turn[team]) = 0;
-            }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(32 * TEAM) : "memory");
-        }
-        if constexpr (PERSIST) {
-            __threadfence();  // every lane's stores / reductions of this iteration, before the strip is published
-            __syncwarp();
-            if (lane == 0) st_release(p.done + strip, it);
-        }
-      }
     }
 }
 
@@ -728,7 +665,6 @@ struct GlWorkspace {
     TileDesc* tiles;
     TileDesc* tiles_tmp;
     int* tile_pos;   // listing index -> position in the sorted table
-    int* done;       // persistent mode: last finished iteration per strip
     int* n_tiles;
     float* mag;
     float* buf[2];
@@ -754,7 +690,6 @@ GlWorkspace carve(const s2st_plan* plan, int n_utts, long long total_frames, voi
     w.tiles = reinterpret_cast<TileDesc*>(take(sizeof(TileDesc) * (size_t)w.max_tiles));
     w.tiles_tmp = reinterpret_cast<TileDesc*>(take(sizeof(TileDesc) * (size_t)w.max_tiles));
     w.tile_pos = reinterpret_cast<int*>(take(sizeof(int) * (size_t)w.max_tiles));
-    w.done = reinterpret_cast<int*>(take(sizeof(int) * (size_t)w.max_tiles));
     w.n_tiles = reinterpret_cast<int*>(take(sizeof(int)));
     w.mag = reinterpret_cast<float*>(take(sizeof(float) * (size_t)total_frames * w.mag_stride));
     for (int i = 0; i < 2; ++i)
@@ -804,19 +739,6 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
 
 // cudaFuncSetAttribute is a driver call per launch otherwise (65 per synthesis step): do it once per kernel, device
 // and size.  Not thread-safe by design (the worst case is a redundant call).
-// S2ST_GL_PERSISTENT=1 runs all iterations in one cooperative launch (k_gl_pass PERSIST).  Bitwise identical results,
-// parity-tested, but measured 1.6 % SLOWER than one launch per iteration with programmatic dependent launch on the
-// config-2 batch (15.82 vs 15.57 ms per step): what the missing grid barrier saves (pass tails, launch ramp) is less
-// than what the per-strip waits, fences and L2-only waveform loads cost.  Hence opt-in.
-// Persistent mode (S2ST_OPT_GL_PERSISTENT): 0 = one launch per iteration (default), 1 = one cooperative launch whenever
-// every strip is resident, -1 = automatic (persistent for small calls: at most a quarter of the resident warps get a
-// strip).  Results are bitwise identical in all modes (test_persistent_mode_is_bitwise_identical).  Measured on B200
-// (tools/time_small.py, profiles/r02_small_calls.txt): the persistent launch is never faster -- one 500-frame utterance
-// 2.56 ms vs 2.36 ms, 8 x 230 frames 2.80 vs 2.46 ms, the config-2 batch 15.82 vs 15.57 ms -- because a small call is
-// bound by the latency of ONE warp running its 4-frame strip (~8 us per frame when a warp has an SM to itself, i.e.
-// ~34 us per iteration whatever the launch mechanism), not by launch gaps or the per-launch prologue; the neighbour
-// waits, fences and L2-only waveform loads of the persistent kernel cost more than those.  Hence opt-in.
-
 template <auto Kernel>
 int allow_dynamic_smem(size_t smem, int device) {
     static size_t granted[64] = {};  // one table per kernel (the kernel is a template argument)
@@ -848,9 +770,9 @@ int launch_frames_t(const FrameGlParams& fp, int device, int grid, cudaStream_t 
     return S2ST_OK;
 }
 
-template <int NZ, bool FIRST, bool PRUNED, bool STD = false, int TEAM = 1>
+template <int NZ, bool FIRST, bool PRUNED, bool STD = false>
 int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream) {
-    if (int rc = allow_dynamic_smem<k_gl_pass<NZ, FIRST, PRUNED, STD, false, TEAM>>(smem, p.device)) return rc;
+    if (int rc = allow_dynamic_smem<k_gl_pass<NZ, FIRST, PRUNED, STD>>(smem, p.device)) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGlThreads);
@@ -861,7 +783,7 @@ int launch_pass_t(const GlParams& p, int grid, size_t smem, cudaStream_t stream)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.pdl ? 1 : 0;
-    S2ST_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gl_pass<NZ, FIRST, PRUNED, STD, false, TEAM>, p));
+    S2ST_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gl_pass<NZ, FIRST, PRUNED, STD>, p));
     return S2ST_OK;
 }
 
@@ -981,8 +903,6 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
     ring[n_iter % 3] = wave_out;
     ring[(n_iter + 1) % 3] = w.buf[0];
     ring[(n_iter + 2) % 3] = w.buf[1];
-    // Persistent mode (see k_gl_pass PERSIST): all iterations in one cooperative launch when every strip gets a
-    // resident warp of its own.  Needs the exact strip count, i.e. the host copy of the frame offsets.
     const bool std_geom0 = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                            plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
     // Calls that fit (a few frames per resident warp): the frame-parallel kernel, all iterations in one launch.
@@ -1040,51 +960,11 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
     S2ST_CUDA_CHECK(cudaGetLastError());
     // pass 0 accumulates its seams into ring[0]: clear it (later passes get theirs cleared by the pass before)
     S2ST_CUDA_CHECK(cudaMemsetAsync(ring[0], 0, sizeof(float) * (size_t)w.wave_samples, stream));
-    const int pmode = plan->opt_persistent;
-    bool persist = std_geom0 && n_iter >= 1 && frame_offsets_host && pmode != 0;
     plan->last_launches = 1 + (logmel ? 1 : 0) + (n_iter + 1);  // build_tiles, [inverse_mel], the passes
-    if (persist) {
-        long long strips = 0;
-        for (int u = 0; u < n_utts; ++u) strips += (frame_offsets_host[u + 1] - frame_offsets_host[u] + S - 1) / S;
-        persist = pmode == 1 ? strips <= (long long)grid * kGlWarps : 4 * strips <= (long long)plan->num_sms * kGlWarps;
-    }
     for (int it = 0; it <= n_iter; ++it) {
         p.in = ring[(it + 2) % 3];
         p.out = ring[it % 3];
         p.zero_next = ring[(it + 1) % 3];
-        if (persist && it == 1) {
-            if (timed) {  // events: [0] before the initial inverse, [1] before / [2] after the persistent launch
-                if (!plan->timing_events[1]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[1]));
-                S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[1], stream));
-            }
-            for (int k = 0; k < 3; ++k) p.bufs[k] = ring[k];
-            p.done = w.done;
-            p.it_first = 1;
-            p.it_last = n_iter;
-            S2ST_CUDA_CHECK(cudaMemsetAsync(w.done, 0, sizeof(int) * (size_t)w.max_tiles, stream));
-            if (int rc2 = allow_dynamic_smem<k_gl_pass<19, false, true, true, true>>(smem, p.device)) return rc2;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)grid);
-            cfg.blockDim = dim3(kGlThreads);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails
-            attr[0].val.cooperative = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            if (cudaLaunchKernelEx(&cfg, k_gl_pass<19, false, true, true, true>, p) == cudaSuccess) {
-                plan->last_launches = 1 + (logmel ? 1 : 0) + 2;
-                if (timed) {
-                    if (!plan->timing_events[2]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[2]));
-                    S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[2], stream));
-                    plan->timing_recorded = 3;
-                }
-                return S2ST_OK;
-            }
-            (void)cudaGetLastError();  // not co-resident (another kernel holds SMs): run the passes one by one
-            persist = false;
-        }
         if (timed) {
             if (!plan->timing_events[it]) S2ST_CUDA_CHECK(cudaEventCreate(&plan->timing_events[it]));
             S2ST_CUDA_CHECK(cudaEventRecord(plan->timing_events[it], stream));
@@ -1092,14 +972,7 @@ int gl_run(s2st_plan* plan, int n_utts, long long total_frames, const int32_t* f
         // the iteration kernel specialised for the vocoder's standard geometry, else the generic one
         const bool std_geom = plan->nz == 19 && plan->hop == kStdHop && plan->ws == kStdWs && plan->rot == kStdRot &&
                               plan->n_fft == kNfft && pruned && p.mag_stride >= 32 * kPrunedRows;
-        // small calls: the team kernels (kTeam warps per strip) -- same arithmetic, same order.  Only while every team
-        // can have an SM to itself: measured (tools/time_small.py), one 100- or 500-frame utterance gains 22 %, but with
-        // 464 strips (3-4 teams per SM, i.e. all 16 warps busy) the frames no longer run faster in parallel than in
-        // sequence and the ordered sections cost 12 %
-        const bool team = std_geom && plan->opt_team != 0 && strips_ub <= (long long)plan->num_sms;
-        const int rc = team ? (it > 0 ? launch_pass_t<19, false, true, true, kTeam>(p, grid, smem, stream)
-                                      : launch_pass_t<19, true, true, true, kTeam>(p, grid, smem, stream))
-                       : (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
+        const int rc = (it > 0 && std_geom) ? launch_pass_t<19, false, true, true>(p, grid, smem, stream)
                        : std_geom             ? launch_pass_t<19, true, true, true>(p, grid, smem, stream)
                        : (plan->nz == 19)     ? launch_pass<19>(p, it == 0, pruned, grid, smem, stream)
                                               : launch_pass<32>(p, it == 0, pruned, grid, smem, stream);

@@ -45,11 +45,9 @@ struct s2st_plan {
     // profiling aid (s2st_plan_set_pass_timing): CUDA events around every Griffin-Lim pass of the LAST call
     int strip_frames;             // 0 = choose per call (s2st_plan_set_strip_frames)
     // options (s2st_plan_set_option; initialised ONCE at plan creation from the S2ST_* environment variables)
-    int opt_persistent;           // -1 = automatic, 0 = one launch per iteration, 1 = one persistent launch when possible
     int opt_pdl;                  // programmatic dependent launch of the passes (default 1)
     int opt_frames;               // 1 (default): calls of up to opt_frames_max frames run the frame-parallel kernel (gl_frames.cuh)
     int opt_frames_max;
-    int opt_team;                 // 1 (default): small calls run 4 warps per strip (k_gl_pass TEAM); 0: always one warp per strip
     int opt_inverse_mel_simt;     // 0 = tcgen05 inverse-mel (default), 1 = FP32 SIMT kernel
     int opt_frontend_generic;     // 0 = register-resident log-mel kernel (default), 1 = generic k_stft path
     int last_launches;            // kernel launches of the last gl_run (0 before the first call)

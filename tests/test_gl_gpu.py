@@ -196,65 +196,6 @@ def test_ragged_batch_equals_per_utterance_and_oracle(pkg, voc, basis):
     assert all(torch.equal(a, b) for a, b in zip(outs, again))
 
 
-def test_persistent_mode_is_bitwise_identical(pkg, voc, monkeypatch):
-    """Persistent mode: all iterations in one cooperative launch, strips synchronising with their neighbours only
-    (no grid-wide barrier).  Same arithmetic, commuting seam reductions -> the waveforms must be bitwise equal to the
-    default one-launch-per-iteration path, for ragged batches with single-strip, multi-strip and tail-strip utterances."""
-    plan = voc._plan(torch.device("cuda", 0))
-    frames = [5, 9, 31, 64, 65, 100, 257, 400] + [120] * 40
-    feats = [synth_logmel(T, 300 + i, "smooth" if i % 2 else "iid").cuda() for i, T in enumerate(frames)]
-    phases = [seeded_phase(400 + i, T) for i, T in enumerate(frames)]
-    for strip in (0, 7):
-        plan.set_strip_frames(strip)
-        try:
-            plan.set_option(pkg._lib.OPT_GL_FRAMES, 0)  # this test is about the strip kernels
-            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 0)
-            base = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
-            assert plan.gl_launch_count(12) == 2 + 13  # build_tiles, inverse_mel, 13 passes
-            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 1)
-            pers = voc.synthesize_batch(feats, init_phase=phases, n_iter=12)
-            assert plan.gl_launch_count(12) == 4  # build_tiles, inverse_mel, initial inverse, the persistent launch
-        finally:
-            plan.set_option(pkg._lib.OPT_GL_PERSISTENT, 0)
-            plan.set_strip_frames(0)
-            plan.set_option(pkg._lib.OPT_GL_FRAMES, 1)
-        for a, b in zip(base, pers):
-            assert torch.equal(a, b)
-
-
-def test_team_mode_is_bitwise_identical(pkg, voc, basis):
-    """Small calls run four warps per strip (k_gl_pass TEAM = 4: frames of a strip transformed in parallel, overlap-add
-    serialised in frame order).  Same additions in the same order -> bitwise equal to the one-warp-per-strip kernels, for
-    single utterances of every tail shape, ragged small batches, the initial inverse alone, and pinned strip lengths."""
-    plan = voc._plan(torch.device("cuda", 0))
-    cases = [[5], [6], [7], [8], [9], [37], [500], [5, 9, 31, 64, 65, 100, 257, 400], [56] * 30]
-    plan.set_option(pkg._lib.OPT_GL_FRAMES, 0)  # this test is about the strip kernels
-    try:
-        for strip in (0, 7):
-            plan.set_strip_frames(strip)
-            for frames in cases:
-                feats = [synth_logmel(T, 900 + i, "smooth" if i % 2 else "iid").cuda() for i, T in enumerate(frames)]
-                phases = [seeded_phase(950 + i, T) for i, T in enumerate(frames)]
-                for n_iter in (0, 5):
-                    plan.set_option(pkg._lib.OPT_GL_TEAM, 0)
-                    base = voc.synthesize_batch(feats, init_phase=phases, n_iter=n_iter)
-                    plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
-                    team = voc.synthesize_batch(feats, init_phase=phases, n_iter=n_iter)
-                    for a, b in zip(base, team):
-                        assert torch.equal(a, b), (strip, frames, n_iter)
-        # the device-drawn initial phase goes through the same first pass
-        x = synth_logmel(300, 1).cuda()
-        plan.set_option(pkg._lib.OPT_GL_TEAM, 0)
-        a = voc.synthesize_flat(x, [300], None, n_iter=3, seed=11)
-        plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
-        assert torch.equal(a, voc.synthesize_flat(x, [300], None, n_iter=3, seed=11))
-    finally:
-        plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
-        plan.set_option(pkg._lib.OPT_GL_FRAMES, 1)
-        plan.set_strip_frames(0)
-    ref = ogl.vocoder_forward(synth_logmel(37, 905, "smooth").numpy(), seeded_phase(955, 37), 5, basis=basis)
-
-
 def test_frame_parallel_path_equals_one_strip_per_utterance(pkg, voc, basis):
     """Calls that fit the resident warps run k_gl_frames (gl_frames.cuh): all iterations in one cooperative launch, a warp
     per frame, the overlap-add gathered from the neighbours' raw frames in frame order -- the same additions in the same

@@ -1,6 +1,9 @@
+"""Phase breakdown of one warp of the frame-parallel kernel: run with a -DS2ST_FRAMES_PROF build of the library
+(python speech-to-speech-translation_b200/build.py -DS2ST_FRAMES_PROF -o$PWD/build_variants/frames_prof.so;
+S2ST_B200_LIB=$PWD/build_variants/frames_prof.so python tools/frames_prof.py 500).  Output -> profiles/r02_small_calls.txt."""
 import importlib, os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 pkg = importlib.import_module(bench.PKG)

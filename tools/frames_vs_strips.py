@@ -1,6 +1,8 @@
+"""Frame-parallel kernel against the strip kernels with one strip per utterance: rel-L2 and the largest difference per hop
+(the two are separately compiled and round differently in the last bit: see DESIGN.md 4.1c)."""
 import importlib, os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 from conftest import synth_logmel, seeded_phase

@@ -1,6 +1,8 @@
+"""Small synthesis calls as a user makes them: synthesize_flat (device-resident) and GriffinLimVocoder.forward on one
+utterance (numpy's global generator continued on the device): host enqueue time, time until done, single-call latency."""
 import importlib, os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 pkg = importlib.import_module(bench.PKG)

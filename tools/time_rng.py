@@ -1,6 +1,8 @@
+"""Device time of s2st_phase_from_mt19937 (the sequential MT19937 recurrence + the parallel phase kernel) and the host
+cost of the shim around it (draw_initial_phase_device with / without the state hand-back)."""
 import importlib, os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 pkg = importlib.import_module(bench.PKG)

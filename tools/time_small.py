@@ -1,5 +1,5 @@
 """Latency of small synthesis calls (config 1: one 500-frame utterance; a 100-frame one; one 60 s utterance; 8, 32 and 128
-utterances of 230 frames), device-resident: the strip kernels (one warp per strip / team mode) against the frame-parallel
+utterances of 230 frames), device-resident: the strip kernels (one launch per iteration) against the frame-parallel
 single-launch kernel (gl_frames.cuh, the default for calls of up to a few thousand frames)."""
 import importlib, os, sys
 import numpy as np, torch
@@ -18,8 +18,7 @@ for name, frames in cases:
     x = torch.from_numpy(np.concatenate([bench.synth_logmel_np(T, 1 + i) for i, T in enumerate(frames)])).cuda()
     ph = ((torch.rand(total, 1025, device="cuda") * 2 - 1) * np.pi).contiguous()
     res, outs = [], []
-    for mode in (0, 1, 2):  # 0: strips, one warp per strip; 1: strips, team mode where it applies; 2: frame-parallel kernel
-        plan.set_option(pkg._lib.OPT_GL_TEAM, 1 if mode >= 1 else 0)
+    for mode in (0, 2):  # 0: strip kernels, one launch per iteration; 2: frame-parallel kernel
         plan.set_option(pkg._lib.OPT_GL_FRAMES, 1 << 20 if mode == 2 else 0)
         try:
             for _ in range(3): y = voc.synthesize_flat(x, frames, ph)
@@ -33,9 +32,8 @@ for name, frames in cases:
         except Exception as e:  # noqa
             res.append((float("nan"), -1)); outs.append(None); print("  mode", mode, "failed:", e)
     audio = (total - len(frames)) * 300 / 24000
-    rel = float((outs[2] - outs[0]).norm() / outs[0].norm()) if outs[2] is not None and outs[0] is not None else float("nan")
-    print(f"{name:8s} strips {res[0][0]:.3f} ms ({audio / res[0][0] * 1e3:.0f} audio-s/s) | strips + team mode {res[1][0]:.3f} ms "
-          f"({audio / res[1][0] * 1e3:.0f}) | frame-parallel {res[2][0]:.3f} ms ({audio / res[2][0] * 1e3:.0f}, {res[2][1]} launches) | "
+    rel = float((outs[1] - outs[0]).norm() / outs[0].norm()) if outs[1] is not None and outs[0] is not None else float("nan")
+    print(f"{name:8s} strips {res[0][0]:.3f} ms ({audio / res[0][0] * 1e3:.0f} audio-s/s) | "
+          f"frame-parallel {res[1][0]:.3f} ms ({audio / res[1][0] * 1e3:.0f}, {res[1][1]} launches) | "
           f"rel-L2 frame-parallel vs strips {rel:.2e}", flush=True)
-plan.set_option(pkg._lib.OPT_GL_TEAM, 1)
 plan.set_option(pkg._lib.OPT_GL_FRAMES, 16 * 148 * 4)
