@@ -7,10 +7,11 @@ randomkit ``rk_double``).  Pinned against numpy itself (tests/test_oracle_golden
 ``('MT19937', key[624] uint32, pos, has_gauss, cached_gaussian)``; output k is ``temper(key[pos])`` with the whole block
 regenerated when ``pos == 624``; a double is ``((a >> 5) * 2**26 + (b >> 6)) / 2**53`` from two consecutive outputs.
 
-Written in the form the device kernel uses: ONE infinite untempered sequence X with X[0:624] = key and
+Written as ONE infinite untempered sequence X with X[0:624] = key and
     X[n] = X[n - 227] ^ twist(X[n - 624], X[n - 623])        (mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1])
-of which the outputs are temper(X[pos]), temper(X[pos + 1]), ...  The closest dependency is 227 back, so 227 consecutive
-elements can be computed at once.
+of which the outputs are temper(X[pos]), temper(X[pos + 1]), ...  ``next_block`` is the form the device kernel uses:
+the dependencies inside a block substituted away, so that all 624 words of the next block follow from the previous
+block in one parallel step.
 """
 import numpy as np
 
@@ -25,6 +26,20 @@ def temper(y):
     y = y ^ ((y << np.uint32(7)) & np.uint32(0x9D2C5680))
     y = y ^ ((y << np.uint32(15)) & np.uint32(0xEFC60000))
     return y ^ (y >> np.uint32(18))
+
+
+def next_block(old):
+    """X[624 (b + 1) : 624 (b + 2)] from X[624 b : 624 (b + 1)], every word from the OLD block alone (rng_kernels.cu)."""
+    old = np.asarray(old, np.uint32)
+    new = np.empty(624, np.uint32)
+    i = np.arange(0, 227)
+    new[i] = old[i + 397] ^ twist(old[i], old[i + 1])
+    i = np.arange(227, 454)
+    new[i] = old[i + 170] ^ twist(old[i - 227], old[i - 226]) ^ twist(old[i], old[i + 1])
+    i = np.arange(454, 624)
+    nxt = np.append(old[455:624], new[0])  # old[624] := new[0]
+    new[i] = old[i - 57] ^ twist(old[i - 454], old[i - 453]) ^ twist(old[i - 227], old[i - 226]) ^ twist(old[i], nxt)
+    return new
 
 
 def advance(key, pos, n_words):

@@ -221,6 +221,14 @@ def test_mt19937_restatement_is_numpy():
         v = np.random.rand(*shape)
         st3 = np.random.get_state()
         assert np.array_equal(u, v) and np.array_equal(st2[1], st3[1]) and st2[2] == st3[2], (seed, pre, shape)
+    # the block form the device kernel uses: numpy regenerates a whole block on the first draw after a seed
+    np.random.seed(11)
+    key = np.random.get_state()[1].copy()
+    for _ in range(3):
+        np.random.bytes(4 * 624)  # consumes exactly one block of 32-bit outputs
+        nxt = np.random.get_state()[1].copy()
+        assert np.array_equal(mt.next_block(key), nxt)
+        key = nxt
 
 
 def test_conv_formulation_reproduces_reference_bit_for_bit(golden_basis):
