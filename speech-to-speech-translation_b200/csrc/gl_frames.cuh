@@ -250,44 +250,20 @@ __global__ void __launch_bounds__(32 * WARPS, 1) k_gl_frames(const __grid_consta
                 } else {
                     // Every sample pair from the four frames that can cover it (missing frames are zero guard rows),
                     // normalised from the one table: pairs stay pairs, 76 independent 8-byte loads per lane.
-                    if constexpr (WARPS <= 8) {
-                        // 255 registers per thread: all 76 loads are issued before the first use (one L2 round trip)
-                        float2 yv[NZ][4];
 #pragma unroll
-                        for (int r = 0; r < NZ; ++r) {
-                            const int m = 64 * r + 2 * lane;
-                            const int h = m / HOP, o = m - h * HOP;
-                            const float* src = Yin + (yrow0 + f + h - 3) * kFrPitch + o + 3 * HOP;
+                    for (int r = 0; r < NZ; ++r) {
+                        const int m = 64 * r + 2 * lane;
+                        const int h = m / HOP, o = m - h * HOP;
+                        const float* src = Yin + (yrow0 + f + h - 3) * kFrPitch + o + 3 * HOP;
+                        float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-                            for (int dt = 0; dt < 4; ++dt) yv[r][dt] = __ldcg(reinterpret_cast<const float2*>(src + dt * (kFrPitch - HOP)));
+                        for (int dt = 0; dt < 4; ++dt) {
+                            const float2 y = __ldcg(reinterpret_cast<const float2*>(src + dt * (kFrPitch - HOP)));
+                            const float2 w = *reinterpret_cast<const float2*>(s_win + o + (3 - dt) * HOP);
+                            acc = fma2(swap2(y), w, acc);
                         }
-#pragma unroll
-                        for (int r = 0; r < NZ; ++r) {
-                            const int m = 64 * r + 2 * lane;
-                            const int h = m / HOP, o = m - h * HOP;
-                            float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-                            for (int dt = 0; dt < 4; ++dt)
-                                acc = fma2(swap2(yv[r][dt]), *reinterpret_cast<const float2*>(s_win + o + (3 - dt) * HOP), acc);
-                            const int i = f * HOP + m, e = i - T * HOP;
-                            a[brev5(r)] = mul2(acc, *reinterpret_cast<const float2*>(s_inv_head + (i < WS - HOP ? i : e >= 0 ? e + WS : o + (WS - HOP))));
-                        }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < NZ; ++r) {
-                            const int m = 64 * r + 2 * lane;
-                            const int h = m / HOP, o = m - h * HOP;
-                            const float* src = Yin + (yrow0 + f + h - 3) * kFrPitch + o + 3 * HOP;
-                            float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-                            for (int dt = 0; dt < 4; ++dt) {
-                                const float2 y = __ldcg(reinterpret_cast<const float2*>(src + dt * (kFrPitch - HOP)));
-                                const float2 w = *reinterpret_cast<const float2*>(s_win + o + (3 - dt) * HOP);
-                                acc = fma2(swap2(y), w, acc);
-                            }
-                            const int i = f * HOP + m, e = i - T * HOP;
-                            a[brev5(r)] = mul2(acc, *reinterpret_cast<const float2*>(s_inv_head + (i < WS - HOP ? i : e >= 0 ? e + WS : o + (WS - HOP))));
-                        }
+                        const int i = f * HOP + m, e = i - T * HOP;
+                        a[brev5(r)] = mul2(acc, *reinterpret_cast<const float2*>(s_inv_head + (i < WS - HOP ? i : e >= 0 ? e + WS : o + (WS - HOP))));
                     }
                     // Reflect padding (audio_utils.py:262-263): the first two and the last two frames of an utterance read
                     // mirrored samples in their first / last rows (frame 0: rows 0-9, frame 1: 0-4, frame T-1: 9-18,

@@ -20,6 +20,9 @@
 // bitwise deterministic.  Three waveform buffers rotate: pass i reads buf[(i-1)%3], writes buf[i%3]
 // and zeroes the seams of buf[(i+1)%3] for the next pass.
 #include <math_constants.h>
+
+#include <algorithm>
+#include <vector>
 #ifdef S2ST_FRAMES_PROF
 #include <cstdio>
 #endif
@@ -163,9 +166,14 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
     // fast paths need 16-byte friendly geometry (true for hop 300 / win 1200 / n_fft 2048)
     const bool geom4 = STD || ((hop % 4 == 0) && (hop >= 64) && (ws % hop == 0) && (rot_half % 4 == 0));
 
-    // strips are dealt to SMs first, then to warps: a small batch spreads one warp per SM (a lone warp runs a frame
-    // about twice as fast as one of 16 sharing the SM) instead of filling a few SMs
-    for (int strip = blockIdx.x + gridDim.x * warp; strip < n_strips; strip += gridDim.x * kGlWarps) {
+    // Strips are dealt to SMs first, then to warps, and -- the table is sorted by descending length -- in SNAKE order
+    // when there are more strips than warps: round 0 gives warp slot w strip w, round 1 strip 2 W - 1 - w, ... so the
+    // warps that hold the shortest strips of one round get the longest of the next (the shortest-processing-time fold
+    // of longest-first scheduling).  choose_strip() on the host evaluates exactly this assignment: on the config-2
+    // batch S = 25 with 82 folded utterance tails (longest warp: 25 frames) instead of S = 26 with one strip per warp.
+    const int w_slot = blockIdx.x + gridDim.x * warp, n_slots = gridDim.x * kGlWarps;
+    for (int round = 0, strip = w_slot; strip < n_strips;
+         ++round, strip = (round & 1) ? (round + 1) * n_slots - 1 - w_slot : round * n_slots + w_slot) {
         const TileDesc td = p.tiles[strip];
         UttDesc ud;
         ud.wave_off = td.wave_off;
@@ -720,15 +728,40 @@ int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, cons
     const int s_min = plan->nphase > kMinStrip ? plan->nphase : kMinStrip;
     int best = s_min;
     double best_cost = 1e300;
-    for (int S = s_min; S <= 64; ++S) {
-        long long strips = 0;
+    std::vector<float> load;
+    for (int S = s_min; S <= kMaxStrip; ++S) {
+        double cost;
         if (fo_host) {
-            for (int u = 0; u < n_utts; ++u) strips += (fo_host[u + 1] - fo_host[u] + S - 1) / S;
+            // exact: strip lengths (full strips of S + one tail per utterance), sorted by descending length like
+            // k_build_tiles does, dealt in the kernel's snake order; a strip costs its frames + 0.35 (flush / seams)
+            long long hist[kMaxStrip + 1] = {};
+            long long strips = 0;
+            for (int u = 0; u < n_utts; ++u) {
+                const int T = fo_host[u + 1] - fo_host[u];
+                if (T <= 0) continue;
+                const int nt = (T + S - 1) / S;
+                hist[S] += nt - 1;
+                hist[T - (nt - 1) * S] += 1;
+                strips += nt;
+            }
+            const long long slots = std::min<long long>(n_warps, std::max<long long>(strips, 1));
+            if (strips > 8 * slots) {
+                cost = (double)((strips + n_warps - 1) / n_warps) * (S + 0.35);  // many rounds: the average decides
+            } else {
+                load.assign((size_t)slots, 0.0f);
+                long long k = 0;
+                for (int len = kMaxStrip; len >= 1; --len)
+                    for (long long c = 0; c < hist[len]; ++c, ++k) {
+                        const long long round = k / slots, pos = k % slots;
+                        load[(size_t)((round & 1) ? slots - 1 - pos : pos)] += (float)len + 0.35f;
+                    }
+                cost = *std::max_element(load.begin(), load.end());
+            }
         } else {
-            strips = total_frames / S + (n_utts + 1) / 2;
+            const long long strips = total_frames / S + (n_utts + 1) / 2;
+            const long long waves = (strips + n_warps - 1) / n_warps;
+            cost = (double)waves * (S + 0.35);
         }
-        const long long waves = (strips + n_warps - 1) / n_warps;
-        const double cost = (double)waves * (S + 0.35);  // + the flush / seam work of a strip
         if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && S > best)) {
             best_cost = cost;
             best = S;

@@ -221,7 +221,7 @@ def test_mt19937_restatement_is_numpy():
         v = np.random.rand(*shape)
         st3 = np.random.get_state()
         assert np.array_equal(u, v) and np.array_equal(st2[1], st3[1]) and st2[2] == st3[2], (seed, pre, shape)
-    # the block form the device kernel uses: numpy regenerates a whole block on the first draw after a seed
+    # the block form (every word of a block from the previous block alone): numpy regenerates a whole block at once
     np.random.seed(11)
     key = np.random.get_state()[1].copy()
     for _ in range(3):
