@@ -726,46 +726,62 @@ size_t gl_pass_smem(const s2st_plan* plan) {
 int choose_strip(const s2st_plan* plan, int n_utts, long long total_frames, const int32_t* fo_host) {
     const long long n_warps = (long long)plan->num_sms * kGlWarps;
     const int s_min = plan->nphase > kMinStrip ? plan->nphase : kMinStrip;
-    int best = s_min;
+    if (!fo_host) {  // lengths unknown on the host: from the average
+        int best = s_min;
+        double best_cost = 1e300;
+        for (int S = s_min; S <= kMaxStrip; ++S) {
+            const long long strips = total_frames / S + (n_utts + 1) / 2;
+            const double cost = (double)((strips + n_warps - 1) / n_warps) * (S + 0.35);  // + the flush / seam work of a strip
+            if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && S > best)) best_cost = cost, best = S;
+        }
+        return best;
+    }
+    // Exact: a strip costs its frames + 0.35 (flush / seams); the strips (full ones of S frames + one tail per utterance)
+    // are sorted by descending length like k_build_tiles does and dealt in the kernel's snake order; the longest warp
+    // decides.  Candidates are visited by increasing lower bound (average load, one full strip) and the search stops
+    // when the bound reaches the best cost found, so only a few S are simulated (the host time of a call matters: the
+    // first version simulated all 61 and doubled it).
+    struct Cand { int S; long long strips; double bound; };
+    Cand cand[kMaxStrip + 1];
+    int n_cand = 0, t_max = 0;
+    for (int u = 0; u < n_utts; ++u) t_max = std::max(t_max, (int)(fo_host[u + 1] - fo_host[u]));
+    for (int S = s_min; S <= kMaxStrip; ++S) {
+        long long strips = 0;
+        for (int u = 0; u < n_utts; ++u) strips += (fo_host[u + 1] - fo_host[u] + S - 1) / S;
+        const long long slots = std::min<long long>(n_warps, std::max<long long>(strips, 1));
+        const double avg = ((double)total_frames + 0.35 * (double)strips) / (double)slots;
+        cand[n_cand++] = {S, strips, std::max(avg, (double)std::min(S, t_max) + 0.35)};
+    }
+    std::sort(cand, cand + n_cand, [](const Cand& a, const Cand& b) { return a.bound < b.bound || (a.bound == b.bound && a.S > b.S); });
+    int best = cand[0].S;
     double best_cost = 1e300;
     std::vector<float> load;
-    for (int S = s_min; S <= kMaxStrip; ++S) {
+    for (int c = 0; c < n_cand && cand[c].bound < best_cost - 1e-9; ++c) {
+        const int S = cand[c].S;
+        const long long strips = cand[c].strips;
+        const long long slots = std::min<long long>(n_warps, std::max<long long>(strips, 1));
         double cost;
-        if (fo_host) {
-            // exact: strip lengths (full strips of S + one tail per utterance), sorted by descending length like
-            // k_build_tiles does, dealt in the kernel's snake order; a strip costs its frames + 0.35 (flush / seams)
+        if (strips > 8 * slots) {
+            cost = (double)((strips + n_warps - 1) / n_warps) * (S + 0.35);  // many rounds: the average decides
+        } else {
             long long hist[kMaxStrip + 1] = {};
-            long long strips = 0;
             for (int u = 0; u < n_utts; ++u) {
                 const int T = fo_host[u + 1] - fo_host[u];
                 if (T <= 0) continue;
                 const int nt = (T + S - 1) / S;
                 hist[S] += nt - 1;
                 hist[T - (nt - 1) * S] += 1;
-                strips += nt;
             }
-            const long long slots = std::min<long long>(n_warps, std::max<long long>(strips, 1));
-            if (strips > 8 * slots) {
-                cost = (double)((strips + n_warps - 1) / n_warps) * (S + 0.35);  // many rounds: the average decides
-            } else {
-                load.assign((size_t)slots, 0.0f);
-                long long k = 0;
-                for (int len = kMaxStrip; len >= 1; --len)
-                    for (long long c = 0; c < hist[len]; ++c, ++k) {
-                        const long long round = k / slots, pos = k % slots;
-                        load[(size_t)((round & 1) ? slots - 1 - pos : pos)] += (float)len + 0.35f;
-                    }
-                cost = *std::max_element(load.begin(), load.end());
-            }
-        } else {
-            const long long strips = total_frames / S + (n_utts + 1) / 2;
-            const long long waves = (strips + n_warps - 1) / n_warps;
-            cost = (double)waves * (S + 0.35);
+            load.assign((size_t)slots, 0.0f);
+            long long k = 0;
+            for (int len = kMaxStrip; len >= 1; --len)
+                for (long long n = 0; n < hist[len]; ++n, ++k) {
+                    const long long round = k / slots, pos = k % slots;
+                    load[(size_t)((round & 1) ? slots - 1 - pos : pos)] += (float)len + 0.35f;
+                }
+            cost = *std::max_element(load.begin(), load.end());
         }
-        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && S > best)) {
-            best_cost = cost;
-            best = S;
-        }
+        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && S > best)) best_cost = cost, best = S;
     }
     return best;
 }
