@@ -162,8 +162,13 @@ __global__ void __launch_bounds__(32 * WARPS, 1) k_gl_frames(const __grid_consta
             if (it > 0) {
                 // the frames whose rows are read now -- and which read the row written below one iteration ago
                 const int t = f - kFrReach + lane;
-                if (lane <= 2 * kFrReach && t >= 0 && t < T)
-                    while (ld_acquire(p.done + (g - f + t)) < it) __nanosleep(20);
+                if (lane <= 2 * kFrReach && t >= 0 && t < T) {
+                    // poll relaxed, acquire once: every ld.acquire.gpu invalidates the L1 (CCTL.IVALL was 19 % of the
+                    // kernel's stall samples when each poll was an acquire)
+                    const int* flag = p.done + (g - f + t);
+                    while (ld_relaxed(flag) < it) __nanosleep(20);
+                    (void)ld_acquire(flag);
+                }
                 __syncwarp();
             }
             FR_STAMP(1);

@@ -129,6 +129,11 @@ __device__ __forceinline__ int ld_acquire(const int* ptr) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int* ptr) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release(int* ptr, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }

@@ -114,7 +114,8 @@ def _nccl_worker(rank, world, port, q):
     waves = voc.synthesize_batch(feats, init_phase=phases, n_iter=8)
     out = sh.gather_waveforms(mine, waves, len(frames), dst=0)
     if rank == 0:
-        # every utterance, wherever it was synthesised, must equal the single-GPU result bitwise (same strip length)
+        # every utterance, wherever it was synthesised, must equal the single-GPU result bitwise (small calls run the
+        # frame-parallel kernel, whose results do not depend on the batch)
         ok = True
         for i, T in enumerate(frames):
             alone = voc.synthesize_batch([synth_logmel(T, 700 + i).cuda()], init_phase=[seeded_phase(800 + i, T)], n_iter=8)[0]

@@ -34,6 +34,12 @@ for what in "$@"; do
       tail -2 gpurun_out/ncu_mel.log ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv env BENCH_NO_EXTRAS=1 python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1 ;;
+    ncu_frames)
+      # the frame-parallel kernel (cooperative, neighbour flags): one utterance of 500 frames (latency regime, 4 warps per
+      # SM) and 32 x 230 frames (throughput regime, 16 warps per SM, 3 frames per warp)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gl_frames -c 1 -f -o gpurun_out/glframes500 python tools/frames_prof.py 500 > gpurun_out/ncu_frames.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gl_frames -c 1 -f -o gpurun_out/glframes7360 python tools/frames_prof.py 7360 >> gpurun_out/ncu_frames.log 2>&1
+      tail -2 gpurun_out/ncu_frames.log ;;
     small)
       timeout 300 python tools/time_small.py > gpurun_out/small.log 2>&1; tail -12 gpurun_out/small.log ;;
   esac
