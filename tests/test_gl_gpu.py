@@ -228,6 +228,21 @@ def test_frame_parallel_path_equals_one_strip_per_utterance(pkg, voc, basis):
             if ci == 10:  # batch independence: an utterance alone equals the same utterance inside the batch, bitwise
                 alone = voc.synthesize_batch([feats[7]], init_phase=[phases[7]], n_iter=6)[0]
                 assert torch.equal(alone, fr[7])
+        # utterances of fewer than 4 frames (reachable with the initial inverse only: the reference's reflect padding
+        # needs T >= 5): both edges interact, the cold per-sample path of the kernel
+        for frames in ([2], [3], [4], [2, 3, 4, 9, 1, 5]):
+            feats = [synth_logmel(T, 2100 + i).cuda() for i, T in enumerate(frames)]
+            phases = [seeded_phase(2150 + i, T) for i, T in enumerate(frames)]
+            plan.set_strip_frames(max(frames))
+            base = voc.synthesize_batch(feats, init_phase=phases, n_iter=0)
+            plan.set_strip_frames(0)
+            fr = voc.synthesize_batch(feats, init_phase=phases, n_iter=0)
+            assert plan.gl_launch_count(0) == 3
+            for T, a, b, x, ph in zip(frames, base, fr, feats, phases):
+                assert a.shape == b.shape == ((T - 1) * 300,)
+                if T > 1:
+                    assert ogl.rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-6, (frames, T)
+                    assert ogl.rel_l2(b.cpu().numpy(), ogl.vocoder_forward(x.cpu().numpy(), ph, 0, basis=basis)) < 1e-5
         x = synth_logmel(300, 1).cuda()
         plan.set_strip_frames(300)
         a = voc.synthesize_flat(x, [300], None, n_iter=3, seed=11)
