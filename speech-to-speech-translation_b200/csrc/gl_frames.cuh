@@ -12,13 +12,18 @@
 //         x[j] = (sum over the <= 4 frames t covering j, ascending t, of fma(y_t[j - t hop], w[j - t hop], .)) * inv[j]
 //     gathered straight from the neighbours' Y rows (L2 resident: 4.9 KB per frame and buffer), windowed and
 //     transformed.  The additions are the same, in the same order, as the strip kernel's shared-memory ring performs
-//     for a strip that covers the whole utterance, and the edge normalisation follows emit_generic: the output is
-//     BITWISE what k_gl_pass produces with one strip per utterance (tests/test_gl_gpu.py), and, unlike the automatic
-//     strip length, independent of what else is in the batch.
-//   * utterances get three zero guard rows on both sides in Y, so "frame does not exist" needs no test in the gather.
+//     for a strip that covers the whole utterance, and the edge normalisation follows emit_generic: the arithmetic
+//     of k_gl_pass with one strip per utterance.  Every stage of every frame is bitwise equal to it in an instrumented
+//     build; in the release build the two kernels differ in the last bit, because ptxas (12.9) fuses mul.rn.f32x2 +
+//     add.rn.f32x2 pairs into FFMA2 as its scheduling sees fit (even with --fmad=false), i.e. two separately compiled
+//     kernels round the same packed source differently (tests/test_gl_gpu.py bounds the difference).
+//     Within this kernel results are deterministic and, unlike the automatic strip length, bitwise independent of
+//     what else is in the batch.
+//   * utterances get three zero guard rows on both sides in Y, so "frame does not exist" needs no test in the gather;
+//     the reflect padding of the first / last two frames mirrors the frame's OWN samples through the warp scratch.
 // Calls with more frames than resident warps give every warp several frames per iteration (same dependencies, no
 // deadlock: all warps are co-resident and a warp never waits for a later iteration); the gather reads 4x the waveform
-// from L2, so large batches stay on the strip kernel (see use_frames_path()).
+// from L2, so large batches stay on the strip kernel (gl_run: kFramesPathMax, S2ST_OPT_GL_FRAMES).
 #pragma once
 
 constexpr int kFrPitch = 64 * 19;     // floats per Y row (19 rows of 32 (odd, even) sample pairs)
