@@ -273,6 +273,11 @@ int s2st_time_warp(int n_utts, int64_t total_rows, const int32_t* frame_offsets_
  * waveform, which soundfile stores as 16-bit PCM): pcm[i] = saturate_int16(lrint(wave[i] * 32767)), NaN -> 0.  Runs on
  * the concatenated batch so the device-to-host copy carries 2 bytes per sample. */
 int s2st_wave_to_pcm16(int64_t n_samples, const float* wave_dev, int16_t* pcm_out_dev, void* stream);
+/* The input side (fairseq/data/audio/audio_utils.py:65-109, get_waveform: soundfile reads a 16-bit PCM file as float32,
+ * value / 32768 with normalization=True, the int16 value itself for get_fbank's Kaldi-style input): the samples are uploaded
+ * as the 2 bytes they occupy on disk and converted on the device, wave[i] = (float)pcm[i] * scale  (scale = 1 / 32768 or 1;
+ * exact).  Halves the host-to-device traffic of the PCIe-bound feature front-end. */
+int s2st_pcm16_to_wave(int64_t n_samples, const int16_t* pcm_dev, float scale, float* wave_out_dev, void* stream);
 
 /* The padded distance batch of batch_compute_distortion (s2s_translation.py:489-505) in one launch: pair b compares rows
  * offsets1[b] .. offsets1[b+1] of x1_dev [sum M_b, d] with rows offsets2[b] .. offsets2[b+1] of x2_dev [sum N_b, d];

@@ -22,7 +22,8 @@ from .feature_transforms.utterance_cmvn import UtteranceCMVN  # noqa: F401
 from .features import (extract_fbank_features, extract_logmel_spectrogram, gcmvn_denormalize,  # noqa: F401
                        get_global_cmvn, global_cmvn_from_sums, global_cmvn_stats, logmel_batch)
 from .io_utils import (create_zip, get_zip_manifest, is_npy_data, is_sf_audio_data, load_feature_batch,  # noqa: F401
-                       mmap_read, parse_path, read_from_stored_zip, read_wav16, waves_to_pcm16, write_wav_batch)
+                       mmap_read, parse_path, pcm16_to_waves, read_from_stored_zip, read_wav16, waves_to_pcm16,
+                       write_wav_batch)
 from .vocoder import GriffinLim, GriffinLimVocoder, PseudoInverseMelScale, get_vocoder  # noqa: F401
 
 __version__ = "0.1.0"

@@ -968,6 +968,14 @@ int s2st_time_warp(int n_utts, int64_t total_rows, const int32_t* frame_offsets_
     return launch_time_warp(n_utts, total_rows, frame_offsets_dev, n_cols, warp_dev, arithmetic, x_dev, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int s2st_pcm16_to_wave(int64_t n_samples, const int16_t* pcm_dev, float scale, float* wave_out_dev, void* stream) {
+    if (n_samples < 0 || (n_samples > 0 && (!pcm_dev || !wave_out_dev))) {
+        set_error("bad argument to s2st_pcm16_to_wave");
+        return S2ST_EINVAL;
+    }
+    return launch_pcm16_to_wave(n_samples, pcm_dev, scale, wave_out_dev, static_cast<cudaStream_t>(stream));
+}
+
 int s2st_wave_to_pcm16(int64_t n_samples, const float* wave_dev, int16_t* pcm_out_dev, void* stream) {
     if (n_samples < 0 || (n_samples > 0 && (!wave_dev || !pcm_out_dev))) {
         set_error("bad argument to s2st_wave_to_pcm16");

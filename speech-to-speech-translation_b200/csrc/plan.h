@@ -137,6 +137,7 @@ int launch_fill_rects(int n_rects, const int32_t* rects, const float* values, in
 int launch_time_warp(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const int32_t* warp, int arithmetic,
                      const float* x, float* out, cudaStream_t stream);
 int launch_wave_to_pcm16(long long n, const float* x, short* out, cudaStream_t stream);
+int launch_pcm16_to_wave(long long n, const short* pcm, float scale, float* out, cudaStream_t stream);
 
 // dtw_kernels.cu
 int launch_dtw(int bsz, int m, int n, const float* dist, const long long* shapes, float* cum, int* bp, int* path,

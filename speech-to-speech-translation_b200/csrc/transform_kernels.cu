@@ -229,7 +229,36 @@ __global__ void __launch_bounds__(256) k_wave_to_pcm16(long long n, const float*
         out[i] = (short)cvt(x[i]);
 }
 
+// The other direction, for the front-end's input (audio_utils.py:65-109: soundfile reads 16-bit PCM files as float32,
+// value / 32768 when normalised, the int16 value itself for the Kaldi-style fbank of get_fbank): samples cross PCIe as
+// the 2 bytes they occupy on disk and become float32 here, wave[i] = (float)pcm[i] * scale (exact).  HBM-bound: 2 B in +
+// 4 B out, 16-byte loads / stores.
+__global__ void __launch_bounds__(256) k_pcm16_to_wave(long long n, const short* __restrict__ pcm, float scale, float* __restrict__ out) {
+    const long long n8 = n >> 3;
+    const bool vec = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(pcm) + i);
+            auto lo = [](unsigned w) { return (float)(short)(w & 0xFFFFu); };
+            auto hi = [](unsigned w) { return (float)(short)(w >> 16); };
+            __stcs(reinterpret_cast<float4*>(out) + 2 * i, make_float4(lo(v.x) * scale, hi(v.x) * scale, lo(v.y) * scale, hi(v.y) * scale));
+            __stcs(reinterpret_cast<float4*>(out) + 2 * i + 1, make_float4(lo(v.z) * scale, hi(v.z) * scale, lo(v.w) * scale, hi(v.w) * scale));
+        }
+    }
+    const long long tail0 = vec ? n8 << 3 : 0;
+    for (long long i = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (float)pcm[i] * scale;
+}
+
 }  // namespace
+
+int launch_pcm16_to_wave(long long n, const short* pcm, float scale, float* out, cudaStream_t stream) {
+    if (n <= 0) return S2ST_OK;
+    const int grid = (int)min((long long)148 * 8, (n / 8 + 255) / 256 + 1);
+    k_pcm16_to_wave<<<grid, 256, 0, stream>>>(n, pcm, scale, out);
+    S2ST_CUDA_CHECK(cudaGetLastError());
+    return S2ST_OK;
+}
 
 int launch_time_warp(int n_utts, long long n_rows, const int32_t* fo, int n_cols, const int32_t* warp, int arithmetic,
                      const float* x, float* out, cudaStream_t stream) {

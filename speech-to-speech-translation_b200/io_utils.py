@@ -199,6 +199,21 @@ def waves_to_pcm16(wave_flat: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pcm16_to_waves(pcm: torch.Tensor, normalization: bool = True, device=None) -> torch.Tensor:
+    """int16 PCM (a CUDA tensor, or a -- preferably pinned -- host tensor, which is uploaded as 2 bytes per sample) ->
+    float32 CUDA waveform (``s2st_pcm16_to_wave``): value / 32768 like ``get_waveform(normalization=True)``
+    (audio_utils.py:65-109), the int16 value itself otherwise (the input ``get_fbank`` feeds Kaldi's fbank)."""
+    assert pcm.dtype == torch.int16
+    dev = require_cuda(pcm.device if pcm.is_cuda else device)
+    p = pcm.to(dev, non_blocking=True).contiguous()
+    out = torch.empty(p.numel(), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2st_pcm16_to_wave(p.numel(), _lib.ptr(p), 1.0 / 32768.0 if normalization else 1.0, _lib.ptr(out),
+                                            _lib.stream_ptr(dev))
+    _lib.check(rc, "s2st_pcm16_to_wave")
+    return out.view(pcm.shape)
+
+
 def write_wav_batch(out_dir: Path, sample_ids: Sequence[str], wave_flat: torch.Tensor, lengths: Sequence[int],
                     sample_rate: int, output_sample_rate: Optional[int] = None, ext: str = "wav") -> List[Path]:
     """``dump_result``'s waveform branch (generate_waveform.py:115-124) for a synthesised batch: utterance i is

@@ -96,3 +96,27 @@ def test_write_wav_batch_from_synthesis(pkg, built_lib, tmp_path):
         off += n
     with pytest.raises(NotImplementedError):
         pkg.write_wav_batch(tmp_path / "x", ["a", "b"], wavef, lens, 24000, output_sample_rate=16000)
+
+
+@pytest.mark.gpu
+def test_pcm16_upload_path_equals_float_path(pkg, built_lib):
+    """The front-end's input side: 16-bit PCM uploaded as 2 bytes per sample and converted on the device
+    (s2st_pcm16_to_wave) is exactly what soundfile's float32 read gives (value / 32768, or the int16 value for the
+    Kaldi-style fbank input, audio_utils.py:65-109), for aligned / unaligned and odd lengths, from pinned host memory
+    and from a device tensor; and fbank80 of the converted samples equals fbank80 of the float samples bitwise."""
+    rng = np.random.RandomState(3)
+    for n in (1, 7, 8, 4001, 160000):
+        pcm = rng.randint(-32768, 32768, n).astype(np.int16)
+        pcm[:3] = (-32768, 32767, 0)[: min(3, n)]
+        for norm in (True, False):
+            want = pcm.astype(np.float32) / np.float32(32768.0) if norm else pcm.astype(np.float32)
+            a = pkg.pcm16_to_waves(torch.from_numpy(pcm).pin_memory(), normalization=norm).cpu().numpy()
+            b = pkg.pcm16_to_waves(torch.from_numpy(pcm).cuda()[1:] if n > 1 else torch.from_numpy(pcm).cuda(), normalization=norm).cpu().numpy()
+            assert a.dtype == np.float32 and np.array_equal(a, want)
+            assert np.array_equal(b, want[1:] if n > 1 else want)  # a 2-byte aligned (not 16-byte aligned) view
+    pcm = (synth_audio(32000, 16000, 5) * 20000).astype(np.int16)
+    wave_f = torch.from_numpy(pcm.astype(np.float32)).cuda()
+    wave_p = pkg.pcm16_to_waves(torch.from_numpy(pcm).pin_memory(), normalization=False)
+    fa = pkg.fbank_batch([wave_f], 16000)[0]
+    fb = pkg.fbank_batch([wave_p], 16000)[0]
+    assert torch.equal(fa, fb)
