@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) k_gl_frames(const __grid_consta
                             acc = fma2(swap2(y), w, acc);
                         }
                         const int i = f * HOP + m, e = i - T * HOP;
-                        a[brev5(r)] = mul2(acc, *reinterpret_cast<const float2*>(s_inv_head + (i < WS - HOP ? i : e >= 0 ? e + WS : o + (WS - HOP))));
+                        // (the last frame's zero-weight samples m >= 1200 lie past the tail table: clamped, their value is multiplied by 0)
+                        a[brev5(r)] = mul2(acc, *reinterpret_cast<const float2*>(s_inv_head + (i < WS - HOP ? i : e >= 0 ? min(e, WS - HOP - 2) + WS : o + (WS - HOP))));
                     }
                     // Reflect padding (audio_utils.py:262-263): the first two and the last two frames of an utterance read
                     // mirrored samples in their first / last rows (frame 0: rows 0-9, frame 1: 0-4, frame T-1: 9-18,

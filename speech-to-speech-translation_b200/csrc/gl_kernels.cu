@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                 // window and overlap-add into the private ring
                 const float* w = s_win_a + 2 * lane;
                 if (geom4) {
-                    // samples past the window support have zero weight: they wrap onto a live slot and add
-                    // +0, so every row can accumulate without a bounds test (slots stay even -> 8-byte RMW)
+                    // every row accumulates without a bounds test (slots stay even -> 8-byte RMW); only the lanes of
+                    // the last row that lie past the window support are predicated off
                     // (Measured and rejected, round 2: issuing the ring / window loads of a batch of rows ahead of the
                     // stores -- the compiler serialises them as written, possible alias -- costs registers the loop does
                     // not have: 20-32 bytes of spills, 0.2425 ms per pass instead of 0.2369; specialising the section on
@@ -370,6 +370,9 @@ __global__ void __launch_bounds__(kGlThreads, 1) k_gl_pass(const __grid_constant
                     const int until_wrap = ws - first;  // rows with 64 r >= until_wrap wrap around once
 #pragma unroll
                     for (int r = 0; r < NZ; ++r) {
+                        // the lanes of the last row that lie past the window support (zero weight) would wrap onto slots
+                        // the first row's lanes have just updated: skipped (for STD this is one predicate, on row 18)
+                        if (64 * r + 62 >= ws && 64 * r + 2 * lane >= ws) continue;
                         float* dst = ring + first + 64 * r - (64 * r >= until_wrap ? ws : 0);
                         float2 o = *reinterpret_cast<float2*>(dst);
                         const float2 ww = *reinterpret_cast<const float2*>(w + 64 * r);
