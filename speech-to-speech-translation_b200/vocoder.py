@@ -67,6 +67,7 @@ class _NumpyStreamOnDevice:
             self.key_out = torch.empty(624, dtype=torch.int32, device=dev)
             self.words = torch.empty(0, dtype=torch.int32, device=dev)
         self.done = torch.cuda.Event()
+        self.pending = None  # finish() of a draw whose state has not been handed back to numpy yet
 
     def words_buffer(self, n_words, dev):
         if self.words.numel() < n_words:
@@ -86,6 +87,9 @@ def draw_initial_phase_device(shape, dev):
 
     Returns ``(phase, finish)``: call ``finish()`` once the rest of the work has been enqueued -- it waits for the
     generator kernel (not for the synthesis) and hands the advanced state to ``np.random.set_state``."""
+    for res in _NumpyStreamOnDevice._by_device.values():
+        if res.pending is not None:  # a caller that drew without finishing: numpy's state is still the old one
+            res.pending()
     st = np.random.get_state()
     n = int(np.prod(shape))
     if st[0] != "MT19937" or n == 0:
@@ -115,9 +119,12 @@ def draw_initial_phase_device(shape, dev):
     new_pos = end - 624 * ((end - 1) // 624)
 
     def finish():
-        res.done.synchronize()
-        np.random.set_state((st[0], res.key_host.numpy().view(np.uint32).copy(), new_pos, st[3], st[4]))
+        if res.pending is finish:
+            res.pending = None
+            res.done.synchronize()
+            np.random.set_state((st[0], res.key_host.numpy().view(np.uint32).copy(), new_pos, st[3], st[4]))
 
+    res.pending = finish
     return phase, finish
 
 

@@ -447,6 +447,16 @@ def test_initial_phase_on_device_equals_host_draw(pkg, voc):
         prepare()
         dev2 = vm._draw_initial_phase_host_rng(shape, dev0).cpu().numpy()
         assert np.array_equal(np.random.rand(3), after_host) and np.array_equal(dev2, want)
+    # a second draw before the first one's finish(): the pending state is handed back first (and finish() is idempotent)
+    np.random.seed(21)
+    h1, h2 = vm.draw_initial_phase((33, 7)), vm.draw_initial_phase((33, 9))
+    tail = np.random.rand()
+    np.random.seed(21)
+    d1, f1 = vm.draw_initial_phase_device((33, 7), dev0)
+    d2, f2 = vm.draw_initial_phase_device((33, 9), dev0)
+    f1(); f2(); f1()
+    assert np.random.rand() == tail
+    assert np.array_equal(d1.cpu().numpy(), h1.T) and np.array_equal(d2.cpu().numpy(), h2.T)
     # forward() itself: seeding numpy reproduces the call, and two calls in a row continue the stream
     x = synth_logmel(30, 3).cuda()
     voc.gl_transform.n_iter = 2
