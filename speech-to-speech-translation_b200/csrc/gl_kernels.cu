@@ -671,7 +671,10 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // The frame-parallel path keeps two raw synthesis frames per frame in the workspace (9.7 KB): only calls of up to this
 // many frames carry that space (and can take the path).
-constexpr long long kFramesPathMax = 16 * 148 * 4;
+#ifndef S2ST_FRAMES_PATH_MAX
+#define S2ST_FRAMES_PATH_MAX (16 * 148 * 4)
+#endif
+constexpr long long kFramesPathMax = S2ST_FRAMES_PATH_MAX;
 
 struct GlWorkspace {
     int4* frames;    // frame-parallel path: (T, f, utterance) per frame, or NULL

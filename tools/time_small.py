@@ -10,7 +10,7 @@ pkg = importlib.import_module(bench.PKG)
 voc = pkg.GriffinLimVocoder(24000, 1200, 300, 2048, 80, 20, 8000, torch.hann_window, spec_bwd_max_iter=64).cuda()
 plan = voc._plan(torch.device("cuda", 0))
 cases = [("T=100", [100]), ("T=500", [500]), ("T=1000", [1000]), ("T=2300", [2300]), ("T=4800", [4800]), ("8x230", [230] * 8),
-         ("16x230", [230] * 16), ("32x230", [230] * 32), ("40x230", [230] * 40), ("64x230", [230] * 64), ("128x230", [230] * 128)]
+         ("16x230", [230] * 16), ("32x230", [230] * 32), ("40x230", [230] * 40), ("64x230", [230] * 64), ("80x230", [230] * 80), ("100x230", [230] * 100), ("128x230", [230] * 128)]
 if len(sys.argv) > 1:
     cases = [c for c in cases if c[0] in sys.argv[1:]]
 for name, frames in cases:
